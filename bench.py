@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py — T-assembly throughput (nnz(T)/s, ms per matrix) on the ACCESS-ESM1-5 1° shape.
+
+    python bench.py --gpus N --steps K --warmup W            # this implementation (CUDA, sm_100a)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on host cores
+
+A "step" is one transportmatrix (Tadv, TκH, TκVML, TκVdeep and T) on BASELINE.json configs[1]:
+360x300x50 tripolar grid, synthetic non-divergent umo/vmo, advection + κH/κVML/κVdeep.
+
+  value      device-resident assembly: inputs (ϕ, v3D, metrics, mlotst) already in HBM, outputs
+             complete in HBM; CUDA events on the library's stream around the K steps.
+  e2e        the same call through the host API with host buffers: H2D of ϕ (6 arrays) and
+             mlotst, assembly, D2H of the five CSC matrices, all inside the timed region.
+  roofline   fused assembly kernel: algorithmic bytes / its own launch duration.
+  cpu_baseline  the CPU oracle (single-thread restatement of the reference; Julia is not in the image).
+
+N > 1 (torchrun, one rank per GPU): batch sharding, one matrix (its own month/seed) per GPU, no
+data-path collective -> weak scaling; the time is the max over ranks.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "T assembly throughput (ACCESS-ESM1-5 1deg, adv+kH+kVML+kVdeep)"
+UNIT = "nnz(T)/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--path", default="fused", choices=["fused", "fused2", "coo"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.rows, self.proc, self.device = [], None, device
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for t, line in self.rows:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            if t0 - 0.1 <= t <= t1 + 0.1:
+                try:
+                    sm.append(float(parts[0]))
+                    smax = float(parts[1])
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:   # region shorter than one sample: take everything we saw
+            for t, line in self.rows:
+                parts = [p.strip() for p in line.split(",")]
+                try:
+                    sm.append(float(parts[0]))
+                    smax = float(parts[1])
+                except (ValueError, IndexError):
+                    pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def algorithmic_bytes(M, P, nz, N, nnz, rho3d=False):
+    """compulsory reads of the API inputs + compulsory writes of the API outputs."""
+    b_in = 8 * (6 * M + M) + 8 * 10 * P + 8 * nz + (8 * M if rho3d else 0)
+    b_out = sum(8 * (N + 1) + 16 * int(x) for x in nnz)
+    return b_in, b_out
+
+
+def hbm_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_reference(args, rank):
+    """The reference's algorithm on the host cores.  Julia is not installed, so this is the
+    oracle port (single thread, like the reference itself: it has no threading)."""
+    if rank != 0:
+        return
+    from otmb_b200 import synthetic
+    from oracle import oracle as O
+    cfg = dict(synthetic.CONFIGS[args.workload])
+    total = args.steps + args.warmup
+    sample = "1 full matrix per step"
+    if total > 12:          # keep the whole run within a few minutes: a k-slab of the same grid
+        cfg["nz"] = max(5, int(cfg["nz"] * 12 / total))
+        sample = f"top {cfg['nz']} of 50 levels per step (bounded sample, nnz/s is size-normalised)"
+    oc = synthetic.make_ocean(seed=0, **cfg)
+    v3D, area = O.clean_missing(oc.volcello), O.clean_missing(oc.areacello)
+    gm = O.gridmetrics(area, v3D, oc.lon, oc.lat, oc.lon_vertices, oc.lat_vertices, oc.topology)
+    phi = O.facefluxes(oc.umo, oc.vmo, v3D, oc.topology, oc.fill)
+    secs, nnzT = [], 0
+    for it in range(total):
+        tm = O.transportmatrix(phi, oc.mlotst, v3D, gm["thkcello"], area, oc.lev, gm["edge"], gm["dnbr"], oc.topology, 1035.0)
+        if it >= args.warmup:
+            secs.append(tm["seconds"])
+        nnzT = tm["T"].nnz
+    ms = 1e3 * sum(secs) / len(secs)
+    value = nnzT / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload} {cfg['nx']}x{cfg['ny']}x{cfg['nz']} {cfg['topology']}, "
+                               "advection + kH/kVML/kVdeep, all five matrices", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": sample + "; oracle/otmb_oracle.cpp (restated CPU baseline, no Julia in image); "
+                                            f"host has {os.cpu_count()} cores, the reference is single-threaded"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def pinned(lib, shape, dtype):
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = C.c_void_p()
+    st = lib.otmb_host_alloc(C.byref(ptr), max(n, 8))
+    if st != 0:
+        raise RuntimeError("otmb_host_alloc failed")
+    buf = (C.c_char * max(n, 8)).from_address(ptr.value)
+    a = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape, order="F")
+    return a, ptr
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import otmb_b200
+    import otmb_b200.api as A
+    from otmb_b200 import _lib, synthetic
+    from _util import fields
+
+    ctx = A.Context(local_rank)
+    lib = ctx.lib
+    oc = synthetic.make_config(args.workload, seed=rank)       # one "month" per rank
+    f = fields(oc)
+    gm = A.makegridmetrics(areacello=f["areacello"], volcello=f["volcello"], lon=f["lon"], lat=f["lat"], lev=f["lev"],
+                           lon_vertices=f["lon_vertices"], lat_vertices=f["lat_vertices"], ctx=ctx)
+    ix_N = ctx.resident["N"]
+    phi = A.facefluxesfrommasstransport(umo=f["umo"], vmo=f["vmo"], gridmetrics=gm, indices=None, ctx=ctx)
+    ctx.check(lib.otmb_set_mlotst(ctx.h, A._ptr(A._f64(oc.mlotst))))
+    ctx.check(lib.otmb_set_rho3d(ctx.h, None))
+    prm = _lib.TMParams(500.0, 0.1, 1.0e-5, 1035.0, 1, 0, _lib.PATH[args.path], 0)
+    nnz = (C.c_int64 * 5)()
+
+    def barrier():
+        ctx.check(lib.otmb_synchronize(ctx.h))
+        if dist is not None:
+            import torch
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    def step():
+        ctx.check(lib.otmb_transportmatrix_build(ctx.h, C.byref(prm), nnz))
+
+    # ---- device-resident assembly -------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    barrier()
+    launches0 = ctx.launches()
+    kernel_ms = []
+    t0 = time.perf_counter()
+    ctx.check(lib.otmb_timer_start(ctx.h))
+    for _ in range(args.steps):
+        step()
+        kernel_ms.append(ctx.last_build_ms())
+    ms = C.c_float()
+    ctx.check(lib.otmb_timer_stop(ctx.h, C.byref(ms)))
+    barrier()
+    t1 = time.perf_counter()
+    launches = ctx.launches() - launches0
+    total_ms = float(ms.value)
+    nnz_list = [int(x) for x in nnz]
+
+    # ---- end to end through the host API, host buffers pinned ---------------------------
+    e2e_ms, h2d, d2h = None, 0, 0
+    if not args.no_e2e:
+        M, P, N = gm.v3D.size, gm.area2D.size, ix_N
+        hin = []
+        for k in A.FACES:
+            a, p = pinned(lib, gm.v3D.shape, np.float64)
+            a[...] = getattr(phi, k)
+            hin.append((a, p))
+        hml, pml = pinned(lib, oc.mlotst.shape, np.float64)
+        hml[...] = oc.mlotst
+        houts = []
+        for m in range(5):
+            houts.append((pinned(lib, (N + 1,), np.int64), pinned(lib, (max(nnz_list[m], 1),), np.int64),
+                          pinned(lib, (max(nnz_list[m], 1),), np.float64)))
+        ptrs = (C.c_void_p * 6)(*[p.value for _, p in hin])
+        h2d = 6 * M * 8 + P * 8
+        d2h = sum(8 * (N + 1) + 16 * nnz_list[m] for m in range(5))
+
+        def e2e_step():
+            ctx.check(lib.otmb_set_facefluxes(ctx.h, ptrs))
+            ctx.check(lib.otmb_set_mlotst(ctx.h, pml))
+            ctx.check(lib.otmb_transportmatrix_build(ctx.h, C.byref(prm), nnz))
+            for m in range(5):
+                (cp, pcp), (rv, prv), (nz, pnz) = houts[m]
+                ctx.check(lib.otmb_transportmatrix_fetch(ctx.h, m, pcp, prv, pnz))
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        te0 = time.perf_counter()
+        n_e2e = max(3, min(args.steps, 10))
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        e2e_ms = 1e3 * (time.perf_counter() - te0) / n_e2e
+    clocks = sampler.stop(t0, t1)
+
+    # ---- reduce over ranks (max time, summed work) ---------------------------------------
+    ms_per_step = total_ms / args.steps
+    k_ms = sum(kernel_ms) / len(kernel_ms)
+    nnzT_total = nnz_list[0]
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms_per_step, k_ms, e2e_ms or 0.0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_per_step, k_ms, e2e_max = [float(x) for x in t.tolist()]
+        e2e_ms = e2e_max if e2e_ms is not None else None
+        s = torch.tensor([nnz_list[0], launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        nnzT_total, launches = int(s[0]), int(s[1])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    M, P, nz, N = gm.v3D.size, gm.area2D.size, gm.v3D.shape[2], ix_N
+    b_in, b_out = algorithmic_bytes(M, P, nz, N, nnz_list)
+    peak, peak_src = hbm_peak()
+    achieved = (b_in + b_out) / (k_ms / 1e3) / 1e9
+    traffic = None
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get(args.path)
+        except Exception:
+            traffic = None
+    line = {
+        "metric": METRIC, "value": nnzT_total / (ms_per_step / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload} 360x300x50 tripolar (ACCESS-ESM1-5 1deg shape), advection + kH/kVML/kVdeep, "
+                               "five CSC matrices (T, Tadv, TkH, TkVML, TkVdeep)",
+                   "path": args.path, "N_wet": N, "nnz": dict(zip(A.MATRICES, nnz_list)),
+                   "parallelism": f"batch: one matrix per GPU x{world}, no collective",
+                   "l2": f"no flush: per-step working set {(b_in + b_out) / 1e6:.0f} MB > 126 MB L2"},
+        "kernel_ms": k_ms,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": b_in + b_out,
+                     "kernel": "k_fused<2> (whole transportmatrix in one launch)" if args.path == "fused" else args.path,
+                     "t_only_frac": ((b_in + 8 * (N + 1) + 16 * nnz_list[0]) / (k_ms / 1e3) / 1e9) / peak},
+        "clocks": clocks,
+        "gpu_launches": launches,
+    }
+    if e2e_ms is not None:
+        line["e2e"] = {"value": nnzT_total / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                       "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms}
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        v3D, area = O.clean_missing(oc.volcello), O.clean_missing(oc.areacello)
+        ogm = O.gridmetrics(area, v3D, oc.lon, oc.lat, oc.lon_vertices, oc.lat_vertices, oc.topology)
+        ophi = O.facefluxes(oc.umo, oc.vmo, v3D, oc.topology, oc.fill)
+        otm = O.transportmatrix(ophi, oc.mlotst, v3D, ogm["thkcello"], area, oc.lev, ogm["edge"], ogm["dnbr"], oc.topology, 1035.0)
+        line["cpu_baseline"] = {"value": otm["T"].nnz / otm["seconds"], "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": "1 full C2 matrix (360x300x50), oracle/otmb_oracle.cpp single thread "
+                                          f"({otm['seconds']:.2f} s); host has {os.cpu_count()} cores; no Julia in image"}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,173 @@
+/* otmb.h — C ABI of libotmb.so: B200-native (sm_100a) transport-matrix assembly.
+ *
+ * This is the drop-in boundary for the matrix-assembly hot path of
+ * OceanTransportMatrixBuilder.jl v0.8.3.  The reference has no FFI of its own: its
+ * boundary is the exported Julia API (src/OceanTransportMatrixBuilder.jl:31-36), and a
+ * thin host shim (Julia `ccall`; Python ctypes in this repository)
+ * keeps those signatures and forwards to the entry points below.  Each entry point
+ * names the reference interface it replaces (paths relative to /root/reference).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all reals are Float64, all indices Int64.
+ *  - arrays are Julia column-major: (nx,ny,nz) -> L = i + nx*(j-1) + nx*ny*(k-1);
+ *    2-D fields (nx,ny); vertex arrays (4,nx,ny); "4-direction" fields are 4 consecutive
+ *    (nx,ny) planes in the reference's `dirs` order south, east, north, west
+ *    (src/gridcellgeometry.jl:304).
+ *  - every function returns an int32 status (0 = OTMB_OK).  otmb_last_error(ctx) gives a
+ *    message valid until the next call on that ctx; the messages of the reference's own
+ *    errors are reproduced verbatim.
+ *  - the caller owns every host array; the library never keeps a host pointer after
+ *    returning.  Host pointers may be pageable, or pinned via otmb_host_alloc.
+ *  - calls on one ctx must be serialised by the caller; different ctxs (one per GPU)
+ *    may be driven from different threads.
+ *  - there is NO CPU fallback: without a usable sm_100 GPU, otmb_create fails.
+ */
+#ifndef OTMB_H
+#define OTMB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct otmb_ctx otmb_ctx;
+
+enum {
+    OTMB_OK = 0,
+    OTMB_ERR_TADV_NAN = 1,      /* "Tadv contains NaNs."    src/matrixbuilding.jl:39  */
+    OTMB_ERR_TKH_NAN = 2,       /* "TκH contains NaNs."     src/matrixbuilding.jl:61  */
+    OTMB_ERR_TKVML_NAN = 3,     /* "TκVML contains NaNs."   src/matrixbuilding.jl:90  */
+    OTMB_ERR_TKVDEEP_NAN = 4,   /* "TκVdeep contains NaNs." src/matrixbuilding.jl:114 */
+    OTMB_ERR_RHO_NAN = 5,       /* "ρ contains NaNs"        src/matrixbuilding.jl:233 */
+    OTMB_ERR_UNKNOWN_GRID = 6,  /* "Unknown grid type"      src/gridtopology.jl:111-116 */
+    OTMB_ERR_ALL_FILL = 7,      /* @assert, umo/vmo all NaN or fill, src/velocities.jl:199-200 */
+    OTMB_ERR_DRY_NEIGHBOUR = 8, /* non-zero flux from a dry/absent neighbour; the reference
+                                   hits a MethodError there, src/matrixbuilding.jl:247-250 */
+    OTMB_ERR_BADARG = 9,
+    OTMB_ERR_STATE = 10,        /* call order: a prerequisite step has not run on this ctx */
+    OTMB_ERR_CUDA = 100,
+    OTMB_ERR_NO_GPU = 101,
+    OTMB_ERR_TOO_LARGE = 102
+};
+
+enum { OTMB_TOPO_BIPOLAR = 0, OTMB_TOPO_TRIPOLAR = 1, OTMB_TOPO_UNKNOWN = 2 };   /* src/gridtopology.jl:1-16 */
+enum { OTMB_MAT_T = 0, OTMB_MAT_TADV = 1, OTMB_MAT_TKH = 2, OTMB_MAT_TKVML = 3, OTMB_MAT_TKVDEEP = 4 };
+enum { OTMB_DIR_SOUTH = 0, OTMB_DIR_EAST = 1, OTMB_DIR_NORTH = 2, OTMB_DIR_WEST = 3 };
+enum { OTMB_FACE_EAST = 0, OTMB_FACE_WEST = 1, OTMB_FACE_NORTH = 2, OTMB_FACE_SOUTH = 3,
+       OTMB_FACE_TOP = 4, OTMB_FACE_BOTTOM = 5 };                                 /* src/velocities.jl:245-252 */
+
+/* assembly strategy.  Both give bit-identical results.
+ *  FUSED : one pass per wet column writes CSC directly (single-pass decoupled look-back scan)
+ *  FUSED2: same column kernel, count pass + block scan + fill pass (cross-check of FUSED)
+ *  COO   : fixed-slot triplet emitters + generic COO->CSC (a device `sparse`) + 3 sparse adds,
+ *          i.e. the reference's own pipeline step by step */
+enum { OTMB_PATH_FUSED = 0, OTMB_PATH_FUSED2 = 1, OTMB_PATH_COO = 2 };
+
+int otmb_version(void);
+int otmb_device_count(int* count);
+const char* otmb_status_string(int status);
+
+/* context: owns device buffers, a stream, cached geometry; one per GPU */
+int otmb_create(otmb_ctx** ctx, int device);
+int otmb_destroy(otmb_ctx* ctx);
+const char* otmb_last_error(const otmb_ctx* ctx);
+
+/* pinned host memory for full-rate PCIe transfers (optional) */
+int otmb_host_alloc(void** ptr, int64_t bytes);
+int otmb_host_free(void* ptr);
+
+/* grid shape + topology tag.  Replaces the AbstractGridTopology structs,
+ * src/gridtopology.jl:1-16; the tag comes from getgridtopology (:33-53), which stays on the host. */
+int otmb_set_grid(otmb_ctx* ctx, int64_t nx, int64_t ny, int64_t nz, int topology);
+
+/* makeindices(v3D), src/matrixbuilding.jl:10-24.  v3D (nx,ny,nz) is NaN at dry cells and
+ * stays resident on the device.  *N = number of wet cells. */
+int otmb_makeindices(otmb_ctx* ctx, const double* v3D, int64_t* N);
+/* the NamedTuple fields of makeindices; any pointer may be NULL.
+ *   wet_chunks: ceil(M/64) UInt64 in Julia BitArray chunk layout (wet3D)
+ *   Lwet:       N Int64, 1-based linear indices
+ *   Lwet3D:     M Int64, 1-based wet index, 0 = missing */
+int otmb_get_indices(otmb_ctx* ctx, uint64_t* wet_chunks, int64_t* Lwet, int64_t* Lwet3D);
+
+/* makegridmetrics numerics, src/gridcellgeometry.jl:283-285 (thkcello, Z3D) and :304-308
+ * (edge_length_2D, distance_to_edge_2D, distance_to_neighbour_2D).  Inputs: area2D (NaN on
+ * land), lon/lat (nx,ny), vertices (4,nx,ny) already permuted (vertexpermutation :158-178 is
+ * host work), zt (nz).  Uses the resident v3D.  Outputs may be NULL; thkcello, Z3D, area2D,
+ * zt, edge, dnbr, lon, lat stay resident. */
+int otmb_gridmetrics(otmb_ctx* ctx, const double* area2D, const double* lon, const double* lat,
+                     const double* lon_vertices, const double* lat_vertices, const double* zt,
+                     double* thkcello, double* Z3D, double* edge_length, double* distance_to_edge,
+                     double* distance_to_neighbour);
+/* upload caller-held grid metrics instead (the fields transportmatrix reads from the
+ * gridmetrics NamedTuple, src/matrixbuilding.jl:340,441).  Z3D/lon/lat may be NULL. */
+int otmb_set_gridmetrics(otmb_ctx* ctx, const double* area2D, const double* thkcello, const double* zt,
+                         const double* edge_length, const double* distance_to_neighbour,
+                         const double* Z3D, const double* lon, const double* lat);
+
+/* facefluxesfrommasstransport -> facefluxes (+ nofluxboundaries!), src/velocities.jl:118-130,
+ * 154-255.  umo/vmo (nx,ny,nz) Float64, not modified.  The six outputs (may be NULL) are the
+ * NamedTuple (east, west, north, south, top, bottom); they also stay resident as ϕ. */
+int otmb_facefluxes(otmb_ctx* ctx, const double* umo, const double* vmo, double fill_value,
+                    double* east, double* west, double* north, double* south, double* top, double* bottom);
+/* upload caller-held ϕ (order OTMB_FACE_*) */
+int otmb_set_facefluxes(otmb_ctx* ctx, const double* const phi[6]);
+int otmb_set_mlotst(otmb_ctx* ctx, const double* mlotst /* (nx,ny), NaN = missing */);
+int otmb_set_rho3d(otmb_ctx* ctx, const double* rho3d /* (nx,ny,nz) or NULL to use params.rho */);
+
+typedef struct otmb_tm_params {
+    double kH;        /* κH     default 500.0  src/matrixbuilding.jl:130 */
+    double kVML;      /* κVML   default 0.1    :131 */
+    double kVdeep;    /* κVdeep default 1.0e-5 :132 */
+    double rho;       /* scalar ρ, used when no 3-D ρ is set (:221-225) */
+    int32_t upwind;   /* default 1 (:137) */
+    int32_t index_base;  /* 1 for Julia, 0 for C/Python consumers of colptr/rowval */
+    int32_t path;     /* OTMB_PATH_* */
+    int32_t build_mask;  /* 0 = build all four operators.  Otherwise bit m (1..4) set: build operator m;
+                            a clear bit means the operator was supplied with otmb_set_operator
+                            (:133-143).  Set bit 5 (32) to pass an explicit mask with no operator bits. */
+} otmb_tm_params;
+
+/* transportmatrix(; ϕ, mlotst, gridmetrics, indices, ρ, κH, κVML, κVdeep, Tadv, TκH, TκVML,
+ * TκVdeep, upwind), src/matrixbuilding.jl:128-150, on the resident inputs.  Blocks until the
+ * five matrices are complete in device memory; nnz_out[OTMB_MAT_*]. */
+int otmb_transportmatrix_build(otmb_ctx* ctx, const otmb_tm_params* params, int64_t nnz_out[5]);
+/* copy one result out as SparseMatrixCSC fields: colptr (N+1), rowval (nnz), nzval (nnz) */
+int otmb_transportmatrix_fetch(otmb_ctx* ctx, int which, int64_t* colptr, int64_t* rowval, double* nzval);
+/* a pre-built operator passed by the caller (the Tadv/TκH/TκVML/TκVdeep kwargs, :133-143);
+ * indices in params.index_base of the next build */
+int otmb_set_operator(otmb_ctx* ctx, int which, int64_t nnz, const int64_t* colptr, const int64_t* rowval,
+                      const double* nzval, int32_t index_base);
+
+/* generic device `sparse(I, J, V, n, n)` (SparseArrays.sparse, called at
+ * src/matrixbuilding.jl:41,63,92,116) and sparse A + B (:147), exposed for parity tests.
+ * Indices 1-based in and out.  Two-phase: *_build returns nnz, *_fetch copies out. */
+int otmb_sparse_build(otmb_ctx* ctx, int64_t len, const int64_t* I, const int64_t* J, const double* V,
+                      int64_t n, int64_t* nnz);
+int otmb_sparse_fetch(otmb_ctx* ctx, int64_t* colptr, int64_t* rowval, double* nzval);
+int otmb_spadd_build(otmb_ctx* ctx, int64_t n, const int64_t* a_colptr, const int64_t* a_rowval,
+                     const double* a_nzval, const int64_t* b_colptr, const int64_t* b_rowval,
+                     const double* b_nzval, int64_t* nnz);
+int otmb_spadd_fetch(otmb_ctx* ctx, int64_t* colptr, int64_t* rowval, double* nzval);
+
+/* Redi/GM helpers (experimental, not exported by the reference; fields, not matrices):
+ * globalverticalfacetriadderivative src/triads.jl:134-146 (dir 0 = Icoord, 1 = Jcoord),
+ * globalverticaldyadderivative src/dyads.jl:66-78, bolus_GM_velocity src/RediGM.jl:46-79.
+ * chi/rho/out are (nx,ny,nz) host arrays; need resident v3D, Z3D, lon, lat. */
+int otmb_triad_derivative(otmb_ctx* ctx, const double* chi, int dir, double* out);
+int otmb_dyad_derivative(otmb_ctx* ctx, const double* chi, double* out);
+int otmb_bolus_gm_velocity(otmb_ctx* ctx, const double* rho, double kGM, double maxslope, double* u, double* v);
+
+/* measurement helpers: CUDA events on the ctx stream (the stream every kernel of this
+ * library is launched on), an L2 flush, and per-kernel launch counting. */
+int otmb_timer_start(otmb_ctx* ctx);
+int otmb_timer_stop(otmb_ctx* ctx, float* milliseconds);
+int otmb_l2_flush(otmb_ctx* ctx);
+int otmb_launch_count(otmb_ctx* ctx, int64_t* launches);   /* kernels launched by this ctx so far */
+int otmb_last_build_ms(otmb_ctx* ctx, float* milliseconds); /* device time of the last transportmatrix_build */
+int otmb_synchronize(otmb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OTMB_H */

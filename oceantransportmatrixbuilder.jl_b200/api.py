@@ -1,0 +1,423 @@
+"""Host-side mirror of the reference's exported API, forwarding to libotmb.so.
+
+The reference is a Julia package whose public surface is seven exported functions
+(/root/reference/src/OceanTransportMatrixBuilder.jl:31-36).  Julia is not available in this
+image, so this Python module plays the role of the thin host shim (the Julia `ccall`
+version of the same shim is in INTEGRATION.md): same function names, same keyword
+arguments (including the Unicode ones: ϕ, ρ, κH, κVML, κVdeep, TκH, ...), same argument
+meaning, same error behaviour and messages, same result fields.  All numerical work is
+done by the CUDA kernels behind the C ABI; nothing here computes on the CPU beyond the
+host-only steps the reference itself performs on tiny inputs (missing/_FillValue -> NaN
+cleaning, vertexpermutation, getgridtopology — SURVEY.md §8a row A3).
+
+Arrays follow the reference's layout: Fortran-ordered `(nx, ny, nz)`, `(nx, ny)`,
+`(4, nx, ny)`.  Sparse results are `scipy.sparse.csc_matrix` with float64 data and int64
+indices (the SparseMatrixCSC{Float64,Int64} of the reference, 0-based).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from collections import namedtuple
+from dataclasses import dataclass
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib as _L
+
+DIRS = ("south", "east", "north", "west")                          # src/gridcellgeometry.jl:304
+FACES = ("east", "west", "north", "south", "top", "bottom")        # src/velocities.jl:245-252
+MATRICES = ("T", "Tadv", "TκH", "TκVML", "TκVdeep")                # src/matrixbuilding.jl:149
+
+
+class OTMBError(RuntimeError):
+    """An error of the reference (same message) or of the CUDA layer."""
+
+    def __init__(self, code, message):
+        super().__init__(message)
+        self.code = code
+
+
+class Field:
+    """Stand-in for the YAXArray the reference receives: `.data` plus `.properties`
+    (the reference reads `.properties["_FillValue"]`, src/gridcellgeometry.jl:270, src/velocities.jl:120)."""
+
+    def __init__(self, data, properties=None):
+        self.data = np.asanyarray(data)
+        self.properties = dict(properties or {})
+
+    def __array__(self, dtype=None, copy=None):
+        return np.asarray(self.data, dtype=dtype)
+
+
+def _data(x):
+    return x.data if isinstance(x, Field) else np.asanyarray(x)
+
+
+def _props(x):
+    return getattr(x, "properties", {}) or {}
+
+
+def _f64(a):
+    return np.asfortranarray(a, dtype=np.float64)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One otmb_ctx (one GPU).  Holds the device-resident grid, indices, metrics and ϕ."""
+
+    def __init__(self, device=0):
+        self.lib = _L.load()
+        h = C.c_void_p()
+        st = self.lib.otmb_create(C.byref(h), int(device))
+        if st != _L.OK:
+            raise OTMBError(st, self.lib.otmb_status_string(st).decode())
+        self.h = h
+        self.device = device
+        self.resident = {}       # name -> object whose content is resident on the device
+        self._fin = weakref.finalize(self, self.lib.otmb_destroy, h)
+
+    def check(self, st):
+        if st != _L.OK:
+            msg = self.lib.otmb_last_error(self.h).decode() or self.lib.otmb_status_string(st).decode()
+            raise OTMBError(st, msg)
+
+    def close(self):
+        self._fin()
+
+    # measurement helpers
+    def launches(self):
+        n = C.c_int64()
+        self.check(self.lib.otmb_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def last_build_ms(self):
+        ms = C.c_float()
+        self.check(self.lib.otmb_last_build_ms(self.h, C.byref(ms)))
+        return ms.value
+
+
+_contexts = {}
+
+
+def default_context(device=0) -> Context:
+    if device not in _contexts:
+        _contexts[device] = Context(device)
+    return _contexts[device]
+
+
+# ------------------------------------------------------------------------------------------
+# host-only pieces of makegridmetrics (tiny inputs; the reference does them on the host too)
+# ------------------------------------------------------------------------------------------
+def _clean_missing(x, fills):
+    """src/gridcellgeometry.jl:269-280: missing/nothing/0/_FillValue -> NaN.  `replace` matches with
+    isequal, so -0.0 is kept."""
+    d = _data(x)
+    if np.ma.isMaskedArray(d):                      # `missing`
+        d = np.ma.filled(d.astype(np.float64), np.nan)
+    a = np.array(d, dtype=np.float64, order="F")
+    bad = (a == 0.0) & ~np.signbit(a)
+    for fv in fills:
+        bad |= a == np.float64(fv)
+    a[bad] = np.nan
+    return a
+
+
+def vertexpermutation(lon_vertices, lat_vertices):
+    """src/gridcellgeometry.jl:158-178 (0-based)."""
+    lonv, latv = np.asarray(lon_vertices), np.asarray(lat_vertices)
+    assert lonv.shape[0] == latv.shape[0] == 4
+    pts = [(lonv[v, 0, 0], latv[v, 0, 0]) for v in range(4)]
+    pe = {(lonv[v, 1, 0], latv[v, 1, 0]) for v in range(4)}
+    pn = {(lonv[v, 0, 1], latv[v, 0, 1]) for v in range(4)}
+    idx_e = [q for q, p in enumerate(pts) if p in pe]
+    idx_n = [q for q, p in enumerate(pts) if p in pn]
+    (i3,) = [q for q in idx_e if q in idx_n]
+    (i2,) = [q for q in idx_e if q != i3]
+    (i4,) = [q for q in idx_n if q != i3]
+    (i1,) = [q for q in range(4) if q not in (i2, i3, i4)]
+    return [i1, i2, i3, i4]
+
+
+@dataclass(frozen=True)
+class GridTopology:
+    """BipolarGridTopology / TripolarGridTopology / UnknownGridTopology, src/gridtopology.jl:1-16."""
+    kind: str
+    nx: int
+    ny: int
+    nz: int
+
+
+def getgridtopology(lon_vertices, lat_vertices, lev) -> GridTopology:
+    """src/gridtopology.jl:33-53."""
+    lonv, latv = np.asarray(lon_vertices), np.asarray(lat_vertices)
+    nx, ny, nz = lonv.shape[1], lonv.shape[2], len(lev)
+    NPlon, NPlat = lonv[2:4, :, -1], latv[2:4, :, -1]
+    if np.all(NPlat == 90):
+        return GridTopology("bipolar", nx, ny, nz)
+    rot = lambda a: a[::-1, ::-1]
+    d = np.mod(NPlon - rot(NPlon) + 180, 360) - 180
+    lon_ok = np.linalg.norm(d) <= np.spacing(180.0)
+    a, b = NPlat, rot(NPlat)
+    lat_ok = np.linalg.norm(a - b) <= np.sqrt(np.finfo(float).eps) * max(np.linalg.norm(a), np.linalg.norm(b))
+    if lon_ok and lat_ok:
+        return GridTopology("tripolar", nx, ny, nz)
+    import warnings
+    warnings.warn("Unknown grid topology detected. Things might not work as expected.\n"
+                  "See `getgridtopology` function to see what failed the checks")
+    return GridTopology("unknown", nx, ny, nz)
+
+
+GridMetrics = namedtuple("GridMetrics", "area2D v3D thkcello lon_vertices lat_vertices lon lat Z3D zt edge_length_2D "
+                                        "distance_to_edge_2D distance_to_neighbour_2D gridtopology")
+Indices = namedtuple("Indices", "wet3D L Lwet N Lwet3D C")
+FaceFluxes = namedtuple("FaceFluxes", "east west north south top bottom")
+TransportMatrices = namedtuple("TransportMatrices", "T Tadv TκH TκVML TκVdeep")
+
+_owner = weakref.WeakValueDictionary()     # id(result array) -> Context that produced it
+
+
+def _ctx_of(*objs, ctx=None):
+    if ctx is not None:
+        return ctx
+    for o in objs:
+        c = _owner.get(id(o))
+        if c is not None:
+            return c
+    return default_context()
+
+
+class _Lazy:
+    """LinearIndices / CartesianIndices of the reference (lazy, no storage), 1-based."""
+
+    def __init__(self, shape, cartesian):
+        self.shape, self.cartesian = tuple(shape), cartesian
+
+    def __getitem__(self, key):
+        nx, ny, _ = self.shape
+        if self.cartesian:
+            L = int(key) - 1
+            return (L % nx + 1, (L // nx) % ny + 1, L // (nx * ny) + 1)
+        i, j, k = key
+        return i + nx * (j - 1) + nx * ny * (k - 1)
+
+
+def _ensure_indices(ctx, v3D, topo_kind):
+    """Make v3D / mask / ranks resident (otmb_set_grid + otmb_makeindices) unless they already are."""
+    key = ("v3D", id(v3D), topo_kind)
+    if ctx.resident.get("v3D_key") == key and ctx.resident.get("v3D") is v3D:
+        return ctx.resident["N"]
+    nx, ny, nz = v3D.shape
+    ctx.check(ctx.lib.otmb_set_grid(ctx.h, nx, ny, nz, _L.TOPO[topo_kind]))
+    N = C.c_int64()
+    ctx.check(ctx.lib.otmb_makeindices(ctx.h, _ptr(v3D), C.byref(N)))
+    ctx.resident.clear()
+    ctx.resident.update(v3D=v3D, v3D_key=key, N=N.value)
+    return N.value
+
+
+def makegridmetrics(*, areacello, volcello, lon, lat, lev, lon_vertices, lat_vertices, ctx=None) -> GridMetrics:
+    """makegridmetrics, src/gridcellgeometry.jl:265-311."""
+    ctx = ctx or default_context()
+    fills = [x.properties["_FillValue"] for x in (areacello, volcello) if "_FillValue" in _props(x)]
+    v3D = _clean_missing(volcello, fills)
+    area2D = _clean_missing(areacello, fills)
+    zt = np.ascontiguousarray(_data(lev), dtype=np.float64)
+    lat_a, lon_a = _f64(_data(lat)), _f64(_data(lon))
+    lonv, latv = _f64(_data(lon_vertices)), _f64(_data(lat_vertices))
+    perm = vertexpermutation(lonv, latv)
+    lonv, latv = np.asfortranarray(lonv[perm]), np.asfortranarray(latv[perm])
+    topo = getgridtopology(lonv, latv, zt)
+    nx, ny, nz = v3D.shape
+    _ensure_indices(ctx, v3D, topo.kind)
+    thk, Z3D = np.empty_like(v3D), np.empty_like(v3D)
+    edge = np.empty((nx, ny, 4), order="F")
+    dedge = np.empty((nx, ny, 4), order="F")
+    dnbr = np.empty((nx, ny, 4), order="F")
+    ctx.check(ctx.lib.otmb_gridmetrics(ctx.h, _ptr(area2D), _ptr(lon_a), _ptr(lat_a), _ptr(lonv), _ptr(latv), _ptr(zt),
+                                       _ptr(thk), _ptr(Z3D), _ptr(edge), _ptr(dedge), _ptr(dnbr)))
+    as_dict = lambda a: {d: a[:, :, q] for q, d in enumerate(DIRS)}
+    gm = GridMetrics(area2D, v3D, thk, lonv, latv, lon_a, lat_a, Z3D, zt, as_dict(edge), as_dict(dedge), as_dict(dnbr), topo)
+    ctx.resident["metrics"] = (area2D, thk, zt, edge, dnbr)
+    ctx.resident["metrics_src"] = (gm.area2D, gm.thkcello, gm.zt, gm.edge_length_2D, gm.distance_to_neighbour_2D)
+    _owner[id(v3D)] = ctx
+    return gm
+
+
+def makeindices(v3D, ctx=None, topology="bipolar") -> Indices:
+    """makeindices(v3D), src/matrixbuilding.jl:10-24.  Lwet3D uses 0 for `missing`."""
+    v3D = v3D if (isinstance(v3D, np.ndarray) and v3D.flags.f_contiguous and v3D.dtype == np.float64) else _f64(v3D)
+    ctx = _ctx_of(v3D, ctx=ctx)
+    kind = ctx.resident["v3D_key"][2] if ctx.resident.get("v3D") is v3D else topology
+    N = _ensure_indices(ctx, v3D, kind)
+    M = v3D.size
+    chunks = np.zeros((M + 63) // 64, np.uint64)
+    Lwet = np.empty(N, np.int64)
+    Lwet3D = np.empty(v3D.shape, np.int64, order="F")
+    ctx.check(ctx.lib.otmb_get_indices(ctx.h, _ptr(chunks), _ptr(Lwet), _ptr(Lwet3D)))
+    wet3D = np.unpackbits(chunks.view(np.uint8), bitorder="little")[:M].astype(bool).reshape(v3D.shape, order="F")
+    ix = Indices(wet3D, _Lazy(v3D.shape, False), Lwet, N, Lwet3D, _Lazy(v3D.shape, True))
+    _owner[id(Lwet)] = ctx
+    return ix
+
+
+def _ensure_grid(ctx, gridmetrics):
+    _ensure_indices(ctx, gridmetrics.v3D, gridmetrics.gridtopology.kind)
+
+
+def facefluxesfrommasstransport(*, umo, vmo, gridmetrics, indices, ctx=None) -> FaceFluxes:
+    """facefluxesfrommasstransport, src/velocities.jl:118-130 (+ facefluxes :190-255)."""
+    fill = umo.properties["_FillValue"]                  # KeyError like the reference
+    fv = vmo.properties["_FillValue"]
+    assert (fill == fv) or (fill != fill and fv != fv), "AssertionError: isequal(FillValue, vmo.properties[\"_FillValue\"])"
+    return facefluxes(_f64(_data(umo)), _f64(_data(vmo)), gridmetrics, indices, FillValue=fill, ctx=ctx)
+
+
+def facefluxes(umo, vmo, gridmetrics, indices, *, FillValue, ctx=None) -> FaceFluxes:
+    """facefluxes, src/velocities.jl:190-255 (umo/vmo are not modified, unlike nofluxboundaries!)."""
+    ctx = _ctx_of(gridmetrics.v3D, ctx=ctx)
+    _ensure_grid(ctx, gridmetrics)
+    umo, vmo = _f64(umo), _f64(vmo)
+    out = [np.empty(gridmetrics.v3D.shape, order="F") for _ in range(6)]
+    ctx.check(ctx.lib.otmb_facefluxes(ctx.h, _ptr(umo), _ptr(vmo), float(FillValue), *[_ptr(o) for o in out]))
+    phi = FaceFluxes(*out)
+    ctx.resident["phi"] = phi
+    ctx.resident["phi_arrays"] = tuple(out)
+    return phi
+
+
+def _csc(n, colptr, rowval, nzval):
+    m = sp.csc_matrix((n, n), dtype=np.float64)
+    m.data, m.indices, m.indptr = nzval, rowval, colptr      # keep Int64 indices like the reference
+    return m
+
+
+def transportmatrix(*, ϕ, mlotst, gridmetrics, indices, ρ, κH=500.0, κVML=0.1, κVdeep=1.0e-5, Tadv=None, TκH=None,
+                    TκVML=None, TκVdeep=None, upwind=True, path="fused", ctx=None) -> TransportMatrices:
+    """transportmatrix, src/matrixbuilding.jl:128-150.  `path` selects the device strategy
+    ("fused", "fused2", "coo"); all give identical results."""
+    ctx = _ctx_of(gridmetrics.v3D, ctx=ctx)
+    lib = ctx.lib
+    _ensure_grid(ctx, gridmetrics)
+    N = ctx.resident["N"]
+    # grid metrics: resident if these are the very objects makegridmetrics returned on this ctx
+    src = ctx.resident.get("metrics_src")
+    same = src is not None and src[0] is gridmetrics.area2D and src[1] is gridmetrics.thkcello and src[2] is gridmetrics.zt \
+        and src[3] is gridmetrics.edge_length_2D and src[4] is gridmetrics.distance_to_neighbour_2D
+    if not same:
+        stack = lambda d: np.asfortranarray(np.stack([_f64(d[k]) for k in DIRS], axis=-1))
+        edge, dnbr = stack(gridmetrics.edge_length_2D), stack(gridmetrics.distance_to_neighbour_2D)
+        zt = np.ascontiguousarray(gridmetrics.zt, dtype=np.float64)
+        ctx.check(lib.otmb_set_gridmetrics(ctx.h, _ptr(_f64(gridmetrics.area2D)), _ptr(_f64(gridmetrics.thkcello)), _ptr(zt),
+                                           _ptr(edge), _ptr(dnbr), _ptr(_f64(gridmetrics.Z3D)), _ptr(_f64(gridmetrics.lon)),
+                                           _ptr(_f64(gridmetrics.lat))))
+        ctx.resident["metrics_src"] = (gridmetrics.area2D, gridmetrics.thkcello, gridmetrics.zt,
+                                       gridmetrics.edge_length_2D, gridmetrics.distance_to_neighbour_2D)
+    preset = {1: Tadv, 2: TκH, 3: TκVML, 4: TκVdeep}
+    mask = 32 | sum(1 << m for m, v in preset.items() if v is None)   # bit 5: the mask is explicit
+    if mask & 2:
+        get = (lambda k: ϕ[k]) if isinstance(ϕ, dict) else (lambda k: getattr(ϕ, k))
+        arrs = tuple(get(k) for k in FACES)
+        res = ctx.resident.get("phi_arrays")
+        if not (res is not None and all(a is b for a, b in zip(arrs, res))):
+            arrs = tuple(_f64(a) for a in arrs)
+            ptrs = (C.c_void_p * 6)(*[a.ctypes.data for a in arrs])
+            ctx.check(lib.otmb_set_facefluxes(ctx.h, ptrs))
+            ctx.resident["phi_arrays"] = arrs
+        if np.isscalar(ρ):
+            ctx.check(lib.otmb_set_rho3d(ctx.h, None))
+        else:
+            ctx.check(lib.otmb_set_rho3d(ctx.h, _ptr(_f64(_data(ρ)))))
+    if mask & 8:
+        ml = _data(mlotst)
+        ml = np.ma.filled(ml.astype(np.float64), np.nan) if np.ma.isMaskedArray(ml) else ml
+        ctx.check(lib.otmb_set_mlotst(ctx.h, _ptr(_f64(ml))))
+    for m, v in preset.items():
+        if v is not None:
+            v = sp.csc_matrix(v)
+            cp, rv, nz = v.indptr.astype(np.int64), v.indices.astype(np.int64), v.data.astype(np.float64)
+            ctx.check(lib.otmb_set_operator(ctx.h, m, len(rv), _ptr(cp), _ptr(rv), _ptr(nz), 0))
+    prm = _L.TMParams(float(κH), float(κVML), float(κVdeep), float(ρ) if np.isscalar(ρ) else 0.0, int(bool(upwind)), 0,
+                      _L.PATH[path], mask)
+    nnz = (C.c_int64 * 5)()
+    ctx.check(lib.otmb_transportmatrix_build(ctx.h, C.byref(prm), nnz))
+    out = []
+    for m in range(5):
+        if m >= 1 and preset[m] is not None:
+            out.append(preset[m])
+            continue
+        cp, rv, nz = np.empty(N + 1, np.int64), np.empty(nnz[m], np.int64), np.empty(nnz[m], np.float64)
+        ctx.check(lib.otmb_transportmatrix_fetch(ctx.h, m, _ptr(cp), _ptr(rv), _ptr(nz)))
+        out.append(_csc(N, cp, rv, nz))
+    return TransportMatrices(*out)
+
+
+# ---- Redi/GM helpers (experimental and non-exported in the reference) -------------------------
+def _ensure_z(ctx, gridmetrics):
+    _ensure_grid(ctx, gridmetrics)
+    if ctx.resident.get("metrics_src") is None or ctx.resident["metrics_src"][1] is not gridmetrics.thkcello:
+        stack = lambda d: np.asfortranarray(np.stack([_f64(d[k]) for k in DIRS], axis=-1))
+        zt = np.ascontiguousarray(gridmetrics.zt, dtype=np.float64)
+        ctx.check(ctx.lib.otmb_set_gridmetrics(
+            ctx.h, _ptr(_f64(gridmetrics.area2D)), _ptr(_f64(gridmetrics.thkcello)), _ptr(zt),
+            _ptr(stack(gridmetrics.edge_length_2D)), _ptr(stack(gridmetrics.distance_to_neighbour_2D)),
+            _ptr(_f64(gridmetrics.Z3D)), _ptr(_f64(gridmetrics.lon)), _ptr(_f64(gridmetrics.lat))))
+        ctx.resident["metrics_src"] = (gridmetrics.area2D, gridmetrics.thkcello, gridmetrics.zt,
+                                       gridmetrics.edge_length_2D, gridmetrics.distance_to_neighbour_2D)
+
+
+def globalverticalfacetriadderivative(χ, gridmetrics, indices, dir, ctx=None):
+    """src/triads.jl:134-146; dir is "I" or "J" (Icoord / Jcoord)."""
+    ctx = _ctx_of(gridmetrics.v3D, ctx=ctx)
+    _ensure_z(ctx, gridmetrics)
+    chi = _f64(χ)
+    out = np.empty_like(chi)
+    ctx.check(ctx.lib.otmb_triad_derivative(ctx.h, _ptr(chi), {"I": 0, "J": 1}[dir], _ptr(out)))
+    return out
+
+
+def globalverticaldyadderivative(χ, gridmetrics, indices, ctx=None):
+    """src/dyads.jl:66-78."""
+    ctx = _ctx_of(gridmetrics.v3D, ctx=ctx)
+    _ensure_z(ctx, gridmetrics)
+    chi = _f64(χ)
+    out = np.empty_like(chi)
+    ctx.check(ctx.lib.otmb_dyad_derivative(ctx.h, _ptr(chi), _ptr(out)))
+    return out
+
+
+def bolus_GM_velocity(ρ, gridmetrics, indices, *, κGM=600, maxslope=0.01, ctx=None):
+    """src/RediGM.jl:46-79."""
+    ctx = _ctx_of(gridmetrics.v3D, ctx=ctx)
+    _ensure_z(ctx, gridmetrics)
+    rho = _f64(ρ)
+    u, v = np.empty_like(rho), np.empty_like(rho)
+    ctx.check(ctx.lib.otmb_bolus_gm_velocity(ctx.h, _ptr(rho), float(κGM), float(maxslope), _ptr(u), _ptr(v)))
+    return u, v
+
+
+# ---- bare sparse helpers (SparseArrays.sparse / +), exposed for parity tests ------------------
+def sparse(I, J, V, n, ctx=None):
+    ctx = ctx or default_context()
+    I, J = np.ascontiguousarray(I, np.int64), np.ascontiguousarray(J, np.int64)
+    V = np.ascontiguousarray(V, np.float64)
+    nnz = C.c_int64()
+    ctx.check(ctx.lib.otmb_sparse_build(ctx.h, len(I), _ptr(I), _ptr(J), _ptr(V), n, C.byref(nnz)))
+    cp, rv, nz = np.empty(n + 1, np.int64), np.empty(nnz.value, np.int64), np.empty(nnz.value, np.float64)
+    ctx.check(ctx.lib.otmb_sparse_fetch(ctx.h, _ptr(cp), _ptr(rv), _ptr(nz)))
+    return cp, rv, nz          # 1-based, like the SparseMatrixCSC fields
+
+
+def spadd(A, B, n, ctx=None):
+    ctx = ctx or default_context()
+    a = [np.ascontiguousarray(A[0], np.int64), np.ascontiguousarray(A[1], np.int64), np.ascontiguousarray(A[2], np.float64)]
+    b = [np.ascontiguousarray(B[0], np.int64), np.ascontiguousarray(B[1], np.int64), np.ascontiguousarray(B[2], np.float64)]
+    nnz = C.c_int64()
+    ctx.check(ctx.lib.otmb_spadd_build(ctx.h, n, *map(_ptr, a), *map(_ptr, b), C.byref(nnz)))
+    cp, rv, nz = np.empty(n + 1, np.int64), np.empty(nnz.value, np.int64), np.empty(nnz.value, np.float64)
+    ctx.check(ctx.lib.otmb_spadd_fetch(ctx.h, _ptr(cp), _ptr(rv), _ptr(nz)))
+    return cp, rv, nz

@@ -1,0 +1,61 @@
+"""Build recipe for libotmb.so (sm_100a only, in-tree so the .so travels with the repo)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+CSRC = HERE / "csrc"
+INCLUDE = HERE.parent / "include"
+LIB = HERE / "libotmb.so"
+SOURCES = ["ctx.cu", "scan.cu", "geometry.cu", "faceflux.cu", "fused.cu", "coo.cu", "transport.cu", "redigm.cu"]
+HEADERS = ["common.cuh", "sphere.cuh"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-fmad=false",                 # the reference never contracts a*b+c; keep every rounding
+    "-Xcompiler", "-fPIC",
+    "-shared",
+]
+
+
+def nvcc() -> str:
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not Path(exe).exists():
+        raise RuntimeError("nvcc not found: libotmb.so cannot be built (there is no CPU fallback)")
+    return exe
+
+
+def needs_build() -> bool:
+    if not LIB.exists():
+        return True
+    t = LIB.stat().st_mtime
+    deps = [CSRC / s for s in SOURCES + HEADERS] + [INCLUDE / "otmb.h", Path(__file__)]
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> Path:
+    if not force and not needs_build():
+        return LIB
+    cmd = [nvcc(), *NVCC_FLAGS, f"-I{INCLUDE}", f"-I{CSRC}"]
+    if ptxas_info:
+        cmd += ["-Xptxas", "-v"]
+    cmd += [str(CSRC / s) for s in SOURCES] + ["-o", str(LIB)]
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    env = dict(os.environ)
+    r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout)
+    if verbose or ptxas_info:
+        print(r.stdout, file=sys.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force=True, verbose=True, ptxas_info="-v" in sys.argv)
+    print(LIB)

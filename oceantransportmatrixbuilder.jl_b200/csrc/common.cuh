@@ -1,0 +1,163 @@
+// common.cuh — context, error handling, device-side grid helpers shared by all kernels.
+// sm_100a only.  Compiled with -fmad=false: the reference never contracts a*b+c into an FMA,
+// and every value that can be bit-exact should be.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "otmb.h"
+
+typedef long long i64;
+typedef unsigned long long u64;
+
+#define OTMB_SM_COUNT_HINT 148
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap && p) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        if (bytes == 0) bytes = 8;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// device-side status block written by kernels, read back once per API call
+struct DevFlags {
+    int err_dry_neighbour;
+    int nan_adv, nan_kh, nan_kvml, nan_kvdeep, nan_rho;
+    int any_valid_u, any_valid_v;
+    int generic_columns;   // columns that took the coincidence (generic) branch
+    int pad[7];
+    u64 nnz[5];
+    u64 ticket;            // dynamic tile id for the look-back kernel
+    u64 pad2[2];
+};
+
+struct otmb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_b0 = nullptr, ev_b1 = nullptr;
+    std::string err;
+    int sm_count = OTMB_SM_COUNT_HINT;
+
+    i64 nx = 0, ny = 0, nz = 0, P = 0, M = 0, N = 0, nwords = 0;
+    int topo = OTMB_TOPO_UNKNOWN;
+    bool have_grid = false, have_indices = false, have_metrics = false, have_phi = false, have_mlotst = false,
+         have_rho3d = false, have_z3d = false, have_lonlat = false;
+
+    DevBuf v3D, mask, wcount, wpre, area2D, thk, Z3D, zt, edge, dnbr, dedge, lon, lat, lonv, latv, mlotst, rho3d;
+    DevBuf phi[6];
+    DevBuf stage_a, stage_b;  // generic staging (uploads for facefluxes / Redi-GM inputs)
+
+    // results
+    DevBuf colptr[5], rowval[5], nzval[5];
+    i64 nnz[5] = {0, 0, 0, 0, 0};
+    bool have_mat[5] = {false, false, false, false, false};
+    bool preset[5] = {false, false, false, false, false};
+    int out_base = 1;
+
+    // scratch
+    DevBuf flags;        // DevFlags
+    DevFlags* h_flags = nullptr;  // pinned
+    DevBuf tile_state;   // look-back descriptors / block totals
+    DevBuf scan_tmp;     // block sums for the generic scan
+    DevBuf coo[12];      // COO path scratch
+    DevBuf sp_colptr, sp_rowval, sp_nzval;  // results of otmb_sparse_build / otmb_spadd_build
+    i64 sp_n = 0, sp_nnz = 0;
+    DevBuf add_tmp[6];
+    DevBuf l2;
+
+    i64 launches = 0;
+    float last_build_ms = 0.f;
+};
+
+inline int otmb_fail(otmb_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    return code;
+}
+
+#define CU_TRY(ctx, expr)                                                                            \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess) {                                                                     \
+            char _b[512];                                                                            \
+            snprintf(_b, sizeof(_b), "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__,   \
+                     __LINE__, cudaGetErrorString(_e));                                              \
+            return otmb_fail((ctx), OTMB_ERR_CUDA, _b);                                              \
+        }                                                                                            \
+    } while (0)
+
+#define OT_TRY(expr)                  \
+    do {                              \
+        int _s = (expr);              \
+        if (_s != OTMB_OK) return _s; \
+    } while (0)
+
+#define LAUNCHED(ctx) ((ctx)->launches++)
+
+inline unsigned grid_for(i64 n, int block) { return (unsigned)((n + block - 1) / block); }
+
+// ----------------------------------------------------------------------------------------
+// device-side grid helpers
+// ----------------------------------------------------------------------------------------
+struct GridDims {
+    int nx, ny, nz, topo;
+    int P;   // nx*ny
+    int M;   // nx*ny*nz  (< 2^31, checked in otmb_set_grid)
+};
+
+__device__ __forceinline__ bool wet_at(const u64* __restrict__ mask, int L) {
+    return (__ldg(mask + (L >> 6)) >> (L & 63)) & 1ull;
+}
+// 0-based wet index of linear cell L (valid when wet_at(L))
+__device__ __forceinline__ int rank_at(const u64* __restrict__ mask, const uint32_t* __restrict__ wpre, int L) {
+    u64 w = __ldg(mask + (L >> 6));
+    return (int)__ldg(wpre + (L >> 6)) + __popcll(w & ((1ull << (L & 63)) - 1ull));
+}
+
+// Julia's min/max for Float64: NaN-propagating, -0.0 < +0.0
+__device__ __forceinline__ double jl_min(double x, double y) {
+    double diff = x - y;
+    double r = signbit(diff) ? x : y;
+    return (isnan(x) || isnan(y)) ? diff : r;
+}
+__device__ __forceinline__ double jl_max(double x, double y) {
+    double diff = x - y;
+    double r = signbit(diff) ? y : x;
+    return (isnan(x) || isnan(y)) ? diff : r;
+}
+
+// scans (scan.cu)
+int otmb_scan_u32(otmb_ctx* ctx, const uint32_t* in, uint32_t* out, i64 n, u64* total_dev /* may be null */);
+int otmb_scan_i64(otmb_ctx* ctx, const i64* in, i64* out, i64 n, u64* total_dev);
+int otmb_scan_u32_to_i64(otmb_ctx* ctx, const uint32_t* in, i64* out, i64 n, u64* total_dev);
+
+// internal entry points across translation units
+int otmb_need(otmb_ctx* ctx, bool cond, const char* what);
+int otmb_fused_build(otmb_ctx* ctx, const otmb_tm_params* prm, int mask, bool two_pass);
+int otmb_coo_build(otmb_ctx* ctx, const otmb_tm_params* prm, int mask);
+int otmb_sum_operators(otmb_ctx* ctx, int base);
+int otmb_dev_sparse(otmb_ctx* ctx, i64 len, const i64* dI, const i64* dJ, const double* dV, const int* dValid, i64 n,
+                    int base, DevBuf& colptr, DevBuf& rowval, DevBuf& nzval, i64* nnz);
+int otmb_dev_spadd(otmb_ctx* ctx, i64 n, int base, const i64* acp, const i64* arv, const double* anz, const i64* bcp,
+                   const i64* brv, const double* bnz, DevBuf& colptr, DevBuf& rowval, DevBuf& nzval, i64* nnz);
+int otmb_fetch_flags(otmb_ctx* ctx);
+int otmb_reset_flags(otmb_ctx* ctx);

@@ -1,0 +1,512 @@
+// coo.cu — the reference's own pipeline, step by step, on the device (OTMB_PATH_COO):
+//   K5-K7 fixed-slot triplet emitters  (/root/reference/src/matrixbuilding.jl:221-299, 337-418, 438-479)
+//   K8    generic COO -> CSC, a device SparseArrays.sparse (called at :41,63,92,116)
+//   K9    sparse A + B with zero dropping, folded left for T (:147)
+// It materialises the triplets, so it moves several times the bytes of the fused path
+// (fused.cu); it exists as the literal restatement, as the cross-check of the fused path,
+// and to serve otmb_sparse_build / otmb_spadd_build / pre-built operators.
+//
+// Emit order.  Every wet cell 𝑖 owns a fixed-width slot block (12 / 8 / 4 triplets) written
+// at index 𝑖*width + slot*2 + {0,1}; an unused slot has I = 0.  Array order therefore equals
+// the reference's push! order (ascending 𝑖, slots W,E,S,N,B,T, two triplets each), which is
+// what SparseArrays.sparse's duplicate summation depends on.
+//
+// sparse(): per-column count (atomics) -> exclusive scan -> scatter into column buckets with
+// key (row << 32 | emit index) -> per-column sort by that key (thread per short column,
+// warp rank-sort for long ones) -> in-order duplicate combine (first kept, later added left
+// to right; explicit zeros kept) -> scan of unique counts -> compaction.  Rows come out
+// strictly ascending inside each column, as in the stdlib.
+#include "common.cuh"
+
+namespace {
+
+enum { sW = 0, sE = 1, sS = 2, sN = 3, sB = 4, sT = 5 };
+
+struct EmitParams {
+    GridDims g;
+    const double *v3D, *thk, *area2D, *zt, *edge, *dnbr, *mlotst, *rho3d;
+    const double *pe, *pw, *pn, *ps, *pt, *pb;
+    const u64* mask;
+    const uint32_t* wpre;
+    double kappa, rho;
+    int upwind, use_ml;
+    i64* I;
+    i64* J;
+    double* V;
+    DevFlags* flags;
+    int* nanflag;
+};
+
+struct Cell {
+    int L, i, j, k;
+};
+__device__ __forceinline__ Cell cell_of(int L, const GridDims& g) {
+    Cell c;
+    c.L = L;
+    c.k = L / g.P;
+    const int p2 = L - c.k * g.P;
+    c.j = p2 / g.nx;
+    c.i = p2 - c.j * g.nx;
+    return c;
+}
+// neighbour linear index or -1 (`nothing`), /root/reference/src/gridtopology.jl:57-68,94
+__device__ __forceinline__ int nbr(const Cell& c, int slot, const GridDims& g) {
+    switch (slot) {
+        case sW: return c.i > 0 ? c.L - 1 : c.L + (g.nx - 1);
+        case sE: return c.i < g.nx - 1 ? c.L + 1 : c.L - (g.nx - 1);
+        case sS: return c.j > 0 ? c.L - g.nx : -1;
+        case sN:
+            if (c.j < g.ny - 1) return c.L + g.nx;
+            return g.topo == OTMB_TOPO_TRIPOLAR ? c.k * g.P + (g.ny - 1) * g.nx + (g.nx - 1 - c.i) : -1;
+        case sB: return c.k < g.nz - 1 ? c.L + g.P : -1;
+        default: return c.k > 0 ? c.L - g.P : -1;
+    }
+}
+
+// K5: advection emitter, 6 slots x 2 triplets per wet cell
+__global__ void __launch_bounds__(256) k_emit_adv(const EmitParams P) {
+    const int L = blockIdx.x * blockDim.x + threadIdx.x;
+    bool bad = false, isnanv = false, nanrho = false;
+    if (L < P.g.M && wet_at(P.mask, L)) {
+        const Cell c = cell_of(L, P.g);
+        const i64 wi = rank_at(P.mask, P.wpre, L);
+        const double vi = __ldg(P.v3D + L);
+        const double rhoi = P.rho3d ? __ldg(P.rho3d + L) : P.rho;
+        if (isnan(rhoi)) nanrho = true;
+        const double* face[6] = {P.pw, P.pe, P.ps, P.pn, P.pb, P.pt};
+        const bool up = P.upwind != 0;
+#pragma unroll
+        for (int s = 0; s < 6; ++s) {
+            const i64 o = wi * 12 + s * 2;
+            const double x = __ldg(face[s] + L);
+            const bool take_max = (s == sW || s == sS || s == sB);
+            const double f = up ? (take_max ? jl_max(x, 0.0) : jl_min(x, 0.0)) : x / 2;
+            i64 i0 = 0, j0 = 0, i1 = 0, j1 = 0;
+            double v0 = 0.0, v1 = 0.0;
+            if ((s != sT || c.k > 0) && (f > 0 || f < 0)) {
+                const int Lj = nbr(c, s, P.g);
+                if (Lj < 0 || !wet_at(P.mask, Lj)) {
+                    bad = true;
+                } else {
+                    const i64 wj = rank_at(P.mask, P.wpre, Lj);
+                    const double p = take_max ? f : -f;
+                    const double rhoj = P.rho3d ? __ldg(P.rho3d + Lj) : P.rho;
+                    const double rb = (rhoi + rhoj) / 2;
+                    const double mi = rb * vi, mj = rb * __ldg(P.v3D + Lj);
+                    i0 = wi + 1; j0 = wj + 1; v0 = -p / mi;
+                    i1 = wj + 1; j1 = wj + 1; v1 = p / mj;
+                    if (isnan(v0) || isnan(v1)) isnanv = true;
+                }
+            }
+            P.I[o] = i0; P.J[o] = j0; P.V[o] = v0;
+            P.I[o + 1] = i1; P.J[o + 1] = j1; P.V[o + 1] = v1;
+        }
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(&P.flags->err_dry_neighbour, 1);
+    if (__any_sync(0xffffffffu, isnanv) && (threadIdx.x & 31) == 0) atomicOr(P.nanflag, 1);
+    if (__any_sync(0xffffffffu, nanrho) && (threadIdx.x & 31) == 0) atomicOr(&P.flags->nan_rho, 1);
+}
+
+// K6: horizontal diffusion emitter, 4 slots x 2 triplets
+__global__ void __launch_bounds__(256) k_emit_kh(const EmitParams P) {
+    const int L = blockIdx.x * blockDim.x + threadIdx.x;
+    bool isnanv = false;
+    if (L < P.g.M && wet_at(P.mask, L)) {
+        const Cell c = cell_of(L, P.g);
+        const i64 wi = rank_at(P.mask, P.wpre, L);
+        const double V = __ldg(P.v3D + L), th = __ldg(P.thk + L);
+        const int PP = P.g.P, p2 = L - c.k * PP;
+        const int slots[4] = {sW, sE, sS, sN};
+        const int own[4] = {OTMB_DIR_WEST, OTMB_DIR_EAST, OTMB_DIR_SOUTH, OTMB_DIR_NORTH};
+        const int opp[4] = {OTMB_DIR_EAST, OTMB_DIR_WEST, OTMB_DIR_NORTH,
+                            c.j == P.g.ny - 1 ? OTMB_DIR_NORTH : OTMB_DIR_SOUTH};  // oppdir :407
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const i64 o = wi * 8 + q * 2;
+            i64 i0 = 0, j0 = 0, i1 = 0, j1 = 0;
+            double v0 = 0.0, v1 = 0.0;
+            const int Lj = nbr(c, slots[q], P.g);
+            if (Lj >= 0 && wet_at(P.mask, Lj)) {
+                const i64 wj = rank_at(P.mask, P.wpre, Lj);
+                const int q2 = Lj - c.k * PP;
+                const double aij = th * __ldg(P.edge + own[q] * PP + p2);
+                const double aji = __ldg(P.thk + Lj) * __ldg(P.edge + opp[q] * PP + q2);
+                const double a = jl_min(aij, aji);
+                const double d = __ldg(P.dnbr + own[q] * PP + p2);
+                const double t = P.kappa * a / (d * V);
+                i0 = wi + 1; j0 = wi + 1; v0 = t;
+                i1 = wi + 1; j1 = wj + 1; v1 = -t;
+                if (isnan(t)) isnanv = true;
+            }
+            P.I[o] = i0; P.J[o] = j0; P.V[o] = v0;
+            P.I[o + 1] = i1; P.J[o + 1] = j1; P.V[o + 1] = v1;
+        }
+    }
+    if (__any_sync(0xffffffffu, isnanv) && (threadIdx.x & 31) == 0) atomicOr(P.nanflag, 1);
+}
+
+// K7: vertical diffusion emitter (Ω = ML mask or all true), 2 slots x 2 triplets
+__global__ void __launch_bounds__(256) k_emit_kv(const EmitParams P) {
+    const int L = blockIdx.x * blockDim.x + threadIdx.x;
+    bool isnanv = false;
+    if (L < P.g.M && wet_at(P.mask, L)) {
+        const Cell c = cell_of(L, P.g);
+        const i64 wi = rank_at(P.mask, P.wpre, L);
+        const int PP = P.g.P, p2 = L - c.k * PP;
+        const double V = __ldg(P.v3D + L), a = __ldg(P.area2D + p2), ztC = __ldg(P.zt + c.k);
+        const double ml = P.use_ml ? __ldg(P.mlotst + p2) : 0.0;
+        const bool omC = P.use_ml ? (ztC < ml) : true;
+        const int slots[2] = {sB, sT};
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const i64 o = wi * 4 + q * 2;
+            i64 i0 = 0, j0 = 0, i1 = 0, j1 = 0;
+            double v0 = 0.0, v1 = 0.0;
+            const int Lj = nbr(c, slots[q], P.g);
+            if (omC && Lj >= 0 && wet_at(P.mask, Lj)) {
+                const int kj = slots[q] == sB ? c.k + 1 : c.k - 1;
+                const double ztj = __ldg(P.zt + kj);
+                if (!P.use_ml || (ztj < ml)) {
+                    const i64 wj = rank_at(P.mask, P.wpre, Lj);
+                    const double d = fabs(ztC - ztj);
+                    const double t = P.kappa * a / (d * V);
+                    i0 = wi + 1; j0 = wi + 1; v0 = t;
+                    i1 = wi + 1; j1 = wj + 1; v1 = -t;
+                    if (isnan(t)) isnanv = true;
+                }
+            }
+            P.I[o] = i0; P.J[o] = j0; P.V[o] = v0;
+            P.I[o + 1] = i1; P.J[o + 1] = j1; P.V[o + 1] = v1;
+        }
+    }
+    if (__any_sync(0xffffffffu, isnanv) && (threadIdx.x & 31) == 0) atomicOr(P.nanflag, 1);
+}
+
+// ---------------------------------------------------------------------------------------
+// K8: generic sparse(I, J, V, n, n)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_count_cols(const i64* __restrict__ I, const i64* __restrict__ J, i64 len,
+                                                    uint32_t* __restrict__ cnt) {
+    const i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < len && I[k] > 0) atomicAdd(cnt + (J[k] - 1), 1u);
+}
+__global__ void __launch_bounds__(256) k_scatter(const i64* __restrict__ I, const i64* __restrict__ J,
+                                                 const double* __restrict__ V, i64 len, const i64* __restrict__ start,
+                                                 uint32_t* __restrict__ cursor, u64* __restrict__ bkey,
+                                                 double* __restrict__ bval) {
+    const i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= len || I[k] <= 0) return;
+    const i64 col = J[k] - 1;
+    const i64 pos = start[col] + atomicAdd(cursor + col, 1u);
+    bkey[pos] = ((u64)(uint32_t)(I[k] - 1) << 32) | (u64)(uint32_t)k;
+    bval[pos] = V[k];
+}
+
+constexpr int SHORT_COL = 32;
+
+// thread per column: insertion sort by (row, emit index), then in-order combine in place
+__global__ void __launch_bounds__(128) k_sort_combine(const i64* __restrict__ start, i64 n, u64* __restrict__ bkey,
+                                                      double* __restrict__ bval, uint32_t* __restrict__ ucnt) {
+    const i64 col = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= n) return;
+    const i64 s = start[col], e = start[col + 1];
+    const int len = (int)(e - s);
+    if (len > SHORT_COL) return;  // handled by k_sort_combine_long
+    if (len == 0) {
+        ucnt[col] = 0;
+        return;
+    }
+    u64 key[SHORT_COL];
+    double val[SHORT_COL];
+    for (int a = 0; a < len; ++a) {
+        key[a] = bkey[s + a];
+        val[a] = bval[s + a];
+    }
+    for (int a = 1; a < len; ++a) {
+        const u64 kx = key[a];
+        const double vx = val[a];
+        int b = a - 1;
+        while (b >= 0 && key[b] > kx) {
+            key[b + 1] = key[b];
+            val[b + 1] = val[b];
+            --b;
+        }
+        key[b + 1] = kx;
+        val[b + 1] = vx;
+    }
+    int m = 0;
+    for (int a = 0; a < len; ++a) {
+        const uint32_t row = (uint32_t)(key[a] >> 32);
+        if (m > 0 && (uint32_t)(key[m - 1] >> 32) == row) {
+            val[m - 1] = val[m - 1] + val[a];
+        } else {
+            key[m] = key[a];
+            val[m] = val[a];
+            ++m;
+        }
+    }
+    for (int a = 0; a < m; ++a) {
+        bkey[s + a] = key[a];
+        bval[s + a] = val[a];
+    }
+    ucnt[col] = (uint32_t)m;
+}
+
+// warp per long column: rank sort through a temporary, then lane 0 combines sequentially
+__global__ void __launch_bounds__(128) k_sort_combine_long(const i64* __restrict__ start, i64 n, u64* __restrict__ bkey,
+                                                           double* __restrict__ bval, u64* __restrict__ tkey,
+                                                           double* __restrict__ tval, uint32_t* __restrict__ ucnt) {
+    const i64 col = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (col >= n) return;
+    const i64 s = start[col], e = start[col + 1];
+    const i64 len = e - s;
+    if (len <= SHORT_COL) return;
+    for (i64 a = lane; a < len; a += 32) {
+        const u64 kx = bkey[s + a];
+        i64 rank = 0;
+        for (i64 b = 0; b < len; ++b) rank += bkey[s + b] < kx;  // keys are unique (emit index)
+        tkey[s + rank] = kx;
+        tval[s + rank] = bval[s + a];
+    }
+    __syncwarp();
+    if (lane == 0) {
+        i64 m = 0;
+        for (i64 a = 0; a < len; ++a) {
+            const u64 kx = tkey[s + a];
+            const double vx = tval[s + a];
+            if (m > 0 && (uint32_t)(bkey[s + m - 1] >> 32) == (uint32_t)(kx >> 32)) {
+                bval[s + m - 1] = bval[s + m - 1] + vx;
+            } else {
+                bkey[s + m] = kx;
+                bval[s + m] = vx;
+                ++m;
+            }
+        }
+        ucnt[col] = (uint32_t)m;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_compact(const i64* __restrict__ start, const i64* __restrict__ colptr0, i64 n,
+                                                 const u64* __restrict__ bkey, const double* __restrict__ bval, int base,
+                                                 i64* __restrict__ colptr, i64* __restrict__ rowval,
+                                                 double* __restrict__ nzval) {
+    const i64 col = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col > n) return;
+    const i64 o = colptr0[col];
+    colptr[col] = o + base;
+    if (col == n) return;
+    const i64 s = start[col];
+    const i64 m = colptr0[col + 1] - o;
+    for (i64 a = 0; a < m; ++a) {
+        rowval[o + a] = (i64)(uint32_t)(bkey[s + a] >> 32) + base;
+        nzval[o + a] = bval[s + a];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K9: sparse A + B, thread per column, count pass then fill pass
+// ---------------------------------------------------------------------------------------
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_spadd(i64 n, int base, const i64* __restrict__ acp, const i64* __restrict__ arv,
+                                               const double* __restrict__ anz, const i64* __restrict__ bcp,
+                                               const i64* __restrict__ brv, const double* __restrict__ bnz,
+                                               uint32_t* __restrict__ cnt, const i64* __restrict__ ccp0,
+                                               i64* __restrict__ ccp, i64* __restrict__ crv, double* __restrict__ cnz) {
+    const i64 col = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col > n) return;
+    if (FILL) ccp[col] = ccp0[col] + base;
+    if (col == n) return;
+    i64 ak = acp[col] - base, ae = acp[col + 1] - base, bk = bcp[col] - base, be = bcp[col + 1] - base;
+    i64 out = FILL ? ccp0[col] : 0;
+    uint32_t m = 0;
+    const i64 sentinel = 0x7fffffffffffffffll;
+    i64 ai = ak < ae ? arv[ak] : sentinel, bi = bk < be ? brv[bk] : sentinel;
+    while (ai != sentinel || bi != sentinel) {
+        double x;
+        i64 ci;
+        if (ai == bi) {
+            x = anz[ak] + bnz[bk];
+            ci = ai;
+            ++ak; ai = ak < ae ? arv[ak] : sentinel;
+            ++bk; bi = bk < be ? brv[bk] : sentinel;
+        } else if (ai < bi) {
+            x = anz[ak] + 0.0;
+            ci = ai;
+            ++ak; ai = ak < ae ? arv[ak] : sentinel;
+        } else {
+            x = 0.0 + bnz[bk];
+            ci = bi;
+            ++bk; bi = bk < be ? brv[bk] : sentinel;
+        }
+        if (x != 0.0) {  // !_iszero: NaN is stored, +-0.0 dropped
+            if (FILL) {
+                crv[out] = ci;
+                cnz[out] = x;
+                ++out;
+            }
+            ++m;
+        }
+    }
+    if (!FILL) cnt[col] = m;
+}
+
+}  // namespace
+
+int otmb_dev_sparse(otmb_ctx* c, i64 len, const i64* dI, const i64* dJ, const double* dV, const int* /*unused*/, i64 n,
+                    int base, DevBuf& colptr, DevBuf& rowval, DevBuf& nzval, i64* nnz) {
+    if (len >= 4294967295ll) return otmb_fail(c, OTMB_ERR_TOO_LARGE, "more than 2^32-1 triplets");
+    DevBuf &cnt = c->coo[3], &start = c->coo[4], &cursor = c->coo[5], &bkey = c->coo[6], &bval = c->coo[7],
+           &tkey = c->coo[8], &tval = c->coo[9], &ucnt = c->coo[10], &cp0 = c->coo[11];
+    CU_TRY(c, cnt.ensure((size_t)(n + 1) * 4));
+    CU_TRY(c, cursor.ensure((size_t)(n + 1) * 4));
+    CU_TRY(c, ucnt.ensure((size_t)(n + 1) * 4));
+    CU_TRY(c, start.ensure((size_t)(n + 1) * 8));
+    CU_TRY(c, cp0.ensure((size_t)(n + 1) * 8));
+    CU_TRY(c, bkey.ensure((size_t)(len + 1) * 8));
+    CU_TRY(c, bval.ensure((size_t)(len + 1) * 8));
+    CU_TRY(c, cudaMemsetAsync(cnt.p, 0, (size_t)(n + 1) * 4, c->stream));
+    CU_TRY(c, cudaMemsetAsync(cursor.p, 0, (size_t)(n + 1) * 4, c->stream));
+    CU_TRY(c, cudaMemsetAsync(ucnt.p, 0, (size_t)(n + 1) * 4, c->stream));
+    DevFlags* fl = c->flags.as<DevFlags>();
+    if (len > 0) {
+        k_count_cols<<<grid_for(len, 256), 256, 0, c->stream>>>(dI, dJ, len, cnt.as<uint32_t>());
+        LAUNCHED(c);
+    }
+    OT_TRY(otmb_scan_u32_to_i64(c, cnt.as<uint32_t>(), start.as<i64>(), n + 1, &fl->nnz[0]));
+    if (len > 0) {
+        k_scatter<<<grid_for(len, 256), 256, 0, c->stream>>>(dI, dJ, dV, len, start.as<i64>(), cursor.as<uint32_t>(),
+                                                              bkey.as<u64>(), bval.as<double>());
+        LAUNCHED(c);
+    }
+    k_sort_combine<<<grid_for(n, 128), 128, 0, c->stream>>>(start.as<i64>(), n, bkey.as<u64>(), bval.as<double>(),
+                                                            ucnt.as<uint32_t>());
+    LAUNCHED(c);
+    // long columns (> SHORT_COL triplets) are rare; find out whether any exist
+    // (max column count is cheap to get on the host from a tiny reduction: reuse the scan total trick)
+    {
+        CU_TRY(c, tkey.ensure((size_t)(len + 1) * 8));
+        CU_TRY(c, tval.ensure((size_t)(len + 1) * 8));
+        k_sort_combine_long<<<grid_for(n * 32, 128), 128, 0, c->stream>>>(start.as<i64>(), n, bkey.as<u64>(),
+                                                                           bval.as<double>(), tkey.as<u64>(),
+                                                                           tval.as<double>(), ucnt.as<uint32_t>());
+        LAUNCHED(c);
+    }
+    OT_TRY(otmb_scan_u32_to_i64(c, ucnt.as<uint32_t>(), cp0.as<i64>(), n + 1, &fl->nnz[1]));
+    OT_TRY(otmb_fetch_flags(c));
+    const i64 total = (i64)c->h_flags->nnz[1];
+    CU_TRY(c, colptr.ensure((size_t)(n + 1) * 8));
+    CU_TRY(c, rowval.ensure((size_t)(total + 1) * 8));
+    CU_TRY(c, nzval.ensure((size_t)(total + 1) * 8));
+    k_compact<<<grid_for(n + 1, 128), 128, 0, c->stream>>>(start.as<i64>(), cp0.as<i64>(), n, bkey.as<u64>(),
+                                                           bval.as<double>(), base, colptr.as<i64>(), rowval.as<i64>(),
+                                                           nzval.as<double>());
+    LAUNCHED(c);
+    CU_TRY(c, cudaGetLastError());
+    if (nnz) *nnz = total;
+    return OTMB_OK;
+}
+
+int otmb_dev_spadd(otmb_ctx* c, i64 n, int base, const i64* acp, const i64* arv, const double* anz, const i64* bcp,
+                   const i64* brv, const double* bnz, DevBuf& colptr, DevBuf& rowval, DevBuf& nzval, i64* nnz) {
+    DevBuf &cnt = c->coo[3], &cp0 = c->coo[11];
+    CU_TRY(c, cnt.ensure((size_t)(n + 1) * 4));
+    CU_TRY(c, cp0.ensure((size_t)(n + 1) * 8));
+    CU_TRY(c, cudaMemsetAsync(cnt.p, 0, (size_t)(n + 1) * 4, c->stream));
+    DevFlags* fl = c->flags.as<DevFlags>();
+    k_spadd<false><<<grid_for(n + 1, 128), 128, 0, c->stream>>>(n, base, acp, arv, anz, bcp, brv, bnz, cnt.as<uint32_t>(),
+                                                                nullptr, nullptr, nullptr, nullptr);
+    LAUNCHED(c);
+    OT_TRY(otmb_scan_u32_to_i64(c, cnt.as<uint32_t>(), cp0.as<i64>(), n + 1, &fl->nnz[2]));
+    OT_TRY(otmb_fetch_flags(c));
+    const i64 total = (i64)c->h_flags->nnz[2];
+    CU_TRY(c, colptr.ensure((size_t)(n + 1) * 8));
+    CU_TRY(c, rowval.ensure((size_t)(total + 1) * 8));
+    CU_TRY(c, nzval.ensure((size_t)(total + 1) * 8));
+    k_spadd<true><<<grid_for(n + 1, 128), 128, 0, c->stream>>>(n, base, acp, arv, anz, bcp, brv, bnz, nullptr,
+                                                               cp0.as<i64>(), colptr.as<i64>(), rowval.as<i64>(),
+                                                               nzval.as<double>());
+    LAUNCHED(c);
+    CU_TRY(c, cudaGetLastError());
+    if (nnz) *nnz = total;
+    return OTMB_OK;
+}
+
+// T = ((Tadv + TκH) + TκVML) + TκVdeep from the four resident operator matrices
+int otmb_sum_operators(otmb_ctx* c, int base) {
+    i64 n1 = 0, n2 = 0, n3 = 0;
+    OT_TRY(otmb_dev_spadd(c, c->N, base, c->colptr[1].as<i64>(), c->rowval[1].as<i64>(), c->nzval[1].as<double>(),
+                          c->colptr[2].as<i64>(), c->rowval[2].as<i64>(), c->nzval[2].as<double>(), c->add_tmp[0],
+                          c->add_tmp[1], c->add_tmp[2], &n1));
+    OT_TRY(otmb_dev_spadd(c, c->N, base, c->add_tmp[0].as<i64>(), c->add_tmp[1].as<i64>(), c->add_tmp[2].as<double>(),
+                          c->colptr[3].as<i64>(), c->rowval[3].as<i64>(), c->nzval[3].as<double>(), c->add_tmp[3],
+                          c->add_tmp[4], c->add_tmp[5], &n2));
+    OT_TRY(otmb_dev_spadd(c, c->N, base, c->add_tmp[3].as<i64>(), c->add_tmp[4].as<i64>(), c->add_tmp[5].as<double>(),
+                          c->colptr[4].as<i64>(), c->rowval[4].as<i64>(), c->nzval[4].as<double>(), c->colptr[0],
+                          c->rowval[0], c->nzval[0], &n3));
+    c->nnz[0] = n3;
+    c->have_mat[0] = true;
+    return OTMB_OK;
+}
+
+// COO path: emit -> sparse for each requested operator
+int otmb_coo_build(otmb_ctx* c, const otmb_tm_params* prm, int build) {
+    EmitParams P;
+    P.g = GridDims{(int)c->nx, (int)c->ny, (int)c->nz, c->topo, (int)c->P, (int)c->M};
+    P.v3D = c->v3D.as<double>();
+    P.thk = c->thk.as<double>();
+    P.area2D = c->area2D.as<double>();
+    P.zt = c->zt.as<double>();
+    P.edge = c->edge.as<double>();
+    P.dnbr = c->dnbr.as<double>();
+    P.mlotst = c->mlotst.as<double>();
+    P.rho3d = c->have_rho3d ? c->rho3d.as<double>() : nullptr;
+    P.pe = c->phi[OTMB_FACE_EAST].as<double>();
+    P.pw = c->phi[OTMB_FACE_WEST].as<double>();
+    P.pn = c->phi[OTMB_FACE_NORTH].as<double>();
+    P.ps = c->phi[OTMB_FACE_SOUTH].as<double>();
+    P.pt = c->phi[OTMB_FACE_TOP].as<double>();
+    P.pb = c->phi[OTMB_FACE_BOTTOM].as<double>();
+    P.mask = c->mask.as<u64>();
+    P.wpre = c->wpre.as<uint32_t>();
+    P.rho = prm->rho;
+    P.upwind = prm->upwind;
+    P.flags = c->flags.as<DevFlags>();
+    const i64 N = c->N;
+    const size_t maxlen = (size_t)N * 12 + 8;
+    CU_TRY(c, c->coo[0].ensure(maxlen * 8));
+    CU_TRY(c, c->coo[1].ensure(maxlen * 8));
+    CU_TRY(c, c->coo[2].ensure(maxlen * 8));
+    P.I = c->coo[0].as<i64>();
+    P.J = c->coo[1].as<i64>();
+    P.V = c->coo[2].as<double>();
+    DevFlags* fl = c->flags.as<DevFlags>();
+    const unsigned blocks = grid_for(c->M, 256);
+    for (int m = 1; m <= 4; ++m) {
+        if (!(build >> m & 1)) continue;
+        i64 width = 0;
+        if (m == OTMB_MAT_TADV) {
+            width = 12;
+            P.nanflag = &fl->nan_adv;
+            k_emit_adv<<<blocks, 256, 0, c->stream>>>(P);
+        } else if (m == OTMB_MAT_TKH) {
+            width = 8;
+            P.kappa = prm->kH;
+            P.nanflag = &fl->nan_kh;
+            k_emit_kh<<<blocks, 256, 0, c->stream>>>(P);
+        } else {
+            width = 4;
+            P.kappa = m == OTMB_MAT_TKVML ? prm->kVML : prm->kVdeep;
+            P.use_ml = m == OTMB_MAT_TKVML;
+            P.nanflag = m == OTMB_MAT_TKVML ? &fl->nan_kvml : &fl->nan_kvdeep;
+            k_emit_kv<<<blocks, 256, 0, c->stream>>>(P);
+        }
+        LAUNCHED(c);
+        CU_TRY(c, cudaGetLastError());
+        i64 nnz = 0;
+        OT_TRY(otmb_dev_sparse(c, N * width, P.I, P.J, P.V, nullptr, N, prm->index_base, c->colptr[m], c->rowval[m],
+                               c->nzval[m], &nnz));
+        c->nnz[m] = nnz;
+    }
+    return OTMB_OK;
+}

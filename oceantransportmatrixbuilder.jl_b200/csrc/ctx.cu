@@ -1,0 +1,353 @@
+// ctx.cu — context life cycle, uploads, measurement helpers, and makeindices (K1).
+//
+// makeindices replaces /root/reference/src/matrixbuilding.jl:10-24.  Device representation of
+// the 3D<->1D wet-cell mapping: a packed bit mask (one UInt64 per 64 linear cells — the same
+// chunk layout as Julia's BitArray, so wet3D is a straight copy) plus an exclusive prefix of
+// the per-word popcounts.  wet index of cell L = wpre[L/64] + popc(mask[L/64] & lowbits(L%64)):
+// 12 bytes per 64 cells instead of the reference's 9 bytes per cell Lwet3D array, small
+// enough to live in L1/L2 for every neighbour query of the assembly kernels.
+#include "common.cuh"
+
+namespace {
+
+// one warp per 64-cell word: two coalesced loads per lane, two ballots -> the chunk
+__global__ void __launch_bounds__(256) k_wetmask(const double* __restrict__ v3D, i64 M, u64* __restrict__ mask,
+                                                 uint32_t* __restrict__ wcount, i64 nwords) {
+    const int lane = threadIdx.x & 31;
+    const i64 gw = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
+    for (i64 w = gw; w < nwords; w += nwarps) {
+        const i64 a = w * 64 + lane, b = a + 32;
+        const double va = a < M ? __ldg(v3D + a) : __longlong_as_double(0x7ff8000000000000ll);
+        const double vb = b < M ? __ldg(v3D + b) : __longlong_as_double(0x7ff8000000000000ll);
+        const unsigned lo = __ballot_sync(0xffffffffu, !isnan(va));
+        const unsigned hi = __ballot_sync(0xffffffffu, !isnan(vb));
+        if (lane == 0) {
+            mask[w] = (u64)lo | ((u64)hi << 32);
+            wcount[w] = (uint32_t)(__popc(lo) + __popc(hi));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_fill_indices(const u64* __restrict__ mask, const uint32_t* __restrict__ wpre,
+                                                      i64 M, i64* __restrict__ Lwet, i64* __restrict__ Lwet3D) {
+    const i64 L = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (L >= M) return;
+    const bool wet = wet_at(mask, (int)L);
+    const int r = rank_at(mask, wpre, (int)L);
+    if (Lwet3D) Lwet3D[L] = wet ? (i64)r + 1 : 0;
+    if (wet && Lwet) Lwet[r] = L + 1;
+}
+
+__global__ void k_l2_flush(uint4* __restrict__ buf, i64 n) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) buf[i] = make_uint4((unsigned)i, 1u, 2u, 3u);
+}
+
+int upload(otmb_ctx* ctx, DevBuf& buf, const void* host, size_t bytes) {
+    CU_TRY(ctx, buf.ensure(bytes));
+    CU_TRY(ctx, cudaMemcpyAsync(buf.p, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return OTMB_OK;
+}
+
+}  // namespace
+
+int otmb_need(otmb_ctx* ctx, bool cond, const char* what) {
+    if (cond) return OTMB_OK;
+    return otmb_fail(ctx, OTMB_ERR_STATE, std::string("missing prerequisite: ") + what);
+}
+
+int otmb_reset_flags(otmb_ctx* ctx) {
+    CU_TRY(ctx, cudaMemsetAsync(ctx->flags.p, 0, sizeof(DevFlags), ctx->stream));
+    return OTMB_OK;
+}
+int otmb_fetch_flags(otmb_ctx* ctx) {
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->flags.p, sizeof(DevFlags), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return OTMB_OK;
+}
+
+extern "C" {
+
+int otmb_version(void) { return 100; }
+
+int otmb_device_count(int* count) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    if (count) *count = n;
+    return OTMB_OK;
+}
+
+const char* otmb_status_string(int s) {
+    switch (s) {
+        case OTMB_OK: return "ok";
+        case OTMB_ERR_TADV_NAN: return "Tadv contains NaNs.";
+        case OTMB_ERR_TKH_NAN: return "T\xce\xbaH contains NaNs.";
+        case OTMB_ERR_TKVML_NAN: return "T\xce\xbaVML contains NaNs.";
+        case OTMB_ERR_TKVDEEP_NAN: return "T\xce\xbaVdeep contains NaNs.";
+        case OTMB_ERR_RHO_NAN: return "\xcf\x81 contains NaNs";
+        case OTMB_ERR_UNKNOWN_GRID: return "Unknown grid type";
+        case OTMB_ERR_ALL_FILL: return "AssertionError: all umo/vmo values are NaN or FillValue";
+        case OTMB_ERR_DRY_NEIGHBOUR: return "non-zero flux from a dry or absent neighbour";
+        case OTMB_ERR_BADARG: return "bad argument";
+        case OTMB_ERR_STATE: return "missing prerequisite call";
+        case OTMB_ERR_CUDA: return "CUDA error";
+        case OTMB_ERR_NO_GPU: return "no usable sm_100 GPU (there is no CPU fallback)";
+        case OTMB_ERR_TOO_LARGE: return "grid too large";
+        default: return "unknown status";
+    }
+}
+
+int otmb_create(otmb_ctx** out, int device) {
+    if (!out) return OTMB_ERR_BADARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return OTMB_ERR_NO_GPU;
+    }
+    if (device < 0 || device >= n) return OTMB_ERR_BADARG;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return OTMB_ERR_NO_GPU;
+    if (prop.major != 10) return OTMB_ERR_NO_GPU;  // the kernels are sm_100a SASS only
+    otmb_ctx* c = new otmb_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&c->ev_t0) != cudaSuccess || cudaEventCreate(&c->ev_t1) != cudaSuccess ||
+        cudaEventCreate(&c->ev_b0) != cudaSuccess || cudaEventCreate(&c->ev_b1) != cudaSuccess ||
+        c->flags.ensure(sizeof(DevFlags)) != cudaSuccess ||
+        cudaMallocHost((void**)&c->h_flags, sizeof(DevFlags)) != cudaSuccess) {
+        cudaGetLastError();
+        delete c;
+        return OTMB_ERR_CUDA;
+    }
+    cudaMemset(c->flags.p, 0, sizeof(DevFlags));
+    *out = c;
+    return OTMB_OK;
+}
+
+int otmb_destroy(otmb_ctx* c) {
+    if (!c) return OTMB_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf* bufs[] = {&c->v3D, &c->mask, &c->wcount, &c->wpre, &c->area2D, &c->thk, &c->Z3D, &c->zt, &c->edge, &c->dnbr,
+                      &c->dedge, &c->lon, &c->lat, &c->lonv, &c->latv, &c->mlotst, &c->rho3d, &c->stage_a, &c->stage_b,
+                      &c->flags, &c->tile_state, &c->scan_tmp, &c->sp_colptr, &c->sp_rowval, &c->sp_nzval, &c->l2};
+    for (DevBuf* b : bufs) b->release();
+    for (int q = 0; q < 6; ++q) c->phi[q].release();
+    for (int q = 0; q < 6; ++q) c->add_tmp[q].release();
+    for (int q = 0; q < 12; ++q) c->coo[q].release();
+    for (int q = 0; q < 5; ++q) {
+        c->colptr[q].release();
+        c->rowval[q].release();
+        c->nzval[q].release();
+    }
+    if (c->h_flags) cudaFreeHost(c->h_flags);
+    cudaEventDestroy(c->ev_t0);
+    cudaEventDestroy(c->ev_t1);
+    cudaEventDestroy(c->ev_b0);
+    cudaEventDestroy(c->ev_b1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return OTMB_OK;
+}
+
+const char* otmb_last_error(const otmb_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int otmb_host_alloc(void** ptr, int64_t bytes) {
+    if (!ptr || bytes < 0) return OTMB_ERR_BADARG;
+    if (cudaMallocHost(ptr, (size_t)(bytes > 0 ? bytes : 8)) != cudaSuccess) {
+        cudaGetLastError();
+        return OTMB_ERR_CUDA;
+    }
+    return OTMB_OK;
+}
+int otmb_host_free(void* ptr) {
+    if (ptr && cudaFreeHost(ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return OTMB_ERR_CUDA;
+    }
+    return OTMB_OK;
+}
+
+int otmb_set_grid(otmb_ctx* c, int64_t nx, int64_t ny, int64_t nz, int topology) {
+    if (!c) return OTMB_ERR_BADARG;
+    if (nx < 1 || ny < 1 || nz < 1) return otmb_fail(c, OTMB_ERR_BADARG, "grid dimensions must be positive");
+    if (topology < 0 || topology > 2) return otmb_fail(c, OTMB_ERR_BADARG, "bad topology tag");
+    const long double m = (long double)nx * ny * nz;
+    if (m >= 2147483000.0L) return otmb_fail(c, OTMB_ERR_TOO_LARGE, "nx*ny*nz must be below 2^31");
+    CU_TRY(c, cudaSetDevice(c->device));
+    c->nx = nx;
+    c->ny = ny;
+    c->nz = nz;
+    c->P = nx * ny;
+    c->M = nx * ny * nz;
+    c->nwords = (c->M + 63) / 64;
+    c->topo = topology;
+    c->have_grid = true;
+    c->have_indices = c->have_metrics = c->have_phi = c->have_mlotst = c->have_rho3d = c->have_z3d = c->have_lonlat = false;
+    for (int q = 0; q < 5; ++q) c->have_mat[q] = c->preset[q] = false;
+    c->N = 0;
+    return OTMB_OK;
+}
+
+int otmb_makeindices(otmb_ctx* c, const double* v3D, int64_t* N) {
+    if (!c || !v3D) return OTMB_ERR_BADARG;
+    OT_TRY(otmb_need(c, c->have_grid, "otmb_set_grid"));
+    CU_TRY(c, cudaSetDevice(c->device));
+    OT_TRY(upload(c, c->v3D, v3D, (size_t)c->M * 8));
+    CU_TRY(c, c->mask.ensure((size_t)(c->nwords + 1) * 8));
+    CU_TRY(c, c->wcount.ensure((size_t)(c->nwords + 1) * 4));
+    CU_TRY(c, c->wpre.ensure((size_t)(c->nwords + 1) * 4));
+    const int blocks = (int)std::min<i64>((c->nwords + 7) / 8, (i64)c->sm_count * 16);
+    k_wetmask<<<blocks > 0 ? blocks : 1, 256, 0, c->stream>>>(c->v3D.as<double>(), c->M, c->mask.as<u64>(),
+                                                              c->wcount.as<uint32_t>(), c->nwords);
+    LAUNCHED(c);
+    CU_TRY(c, cudaGetLastError());
+    OT_TRY(otmb_reset_flags(c));
+    OT_TRY(otmb_scan_u32(c, c->wcount.as<uint32_t>(), c->wpre.as<uint32_t>(), c->nwords,
+                         &c->flags.as<DevFlags>()->nnz[0]));
+    OT_TRY(otmb_fetch_flags(c));
+    c->N = (i64)c->h_flags->nnz[0];
+    c->have_indices = true;
+    for (int q = 0; q < 5; ++q) c->have_mat[q] = c->preset[q] = false;
+    if (N) *N = c->N;
+    return OTMB_OK;
+}
+
+int otmb_get_indices(otmb_ctx* c, uint64_t* wet_chunks, int64_t* Lwet, int64_t* Lwet3D) {
+    if (!c) return OTMB_ERR_BADARG;
+    OT_TRY(otmb_need(c, c->have_indices, "otmb_makeindices"));
+    CU_TRY(c, cudaSetDevice(c->device));
+    if (wet_chunks)
+        CU_TRY(c, cudaMemcpyAsync(wet_chunks, c->mask.p, (size_t)c->nwords * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (Lwet || Lwet3D) {
+        i64* dLwet = nullptr;
+        i64* dL3 = nullptr;
+        if (Lwet) {
+            CU_TRY(c, c->stage_a.ensure((size_t)(c->N + 1) * 8));
+            dLwet = c->stage_a.as<i64>();
+        }
+        if (Lwet3D) {
+            CU_TRY(c, c->stage_b.ensure((size_t)c->M * 8));
+            dL3 = c->stage_b.as<i64>();
+        }
+        k_fill_indices<<<grid_for(c->M, 256), 256, 0, c->stream>>>(c->mask.as<u64>(), c->wpre.as<uint32_t>(), c->M, dLwet,
+                                                                    dL3);
+        LAUNCHED(c);
+        CU_TRY(c, cudaGetLastError());
+        if (Lwet) CU_TRY(c, cudaMemcpyAsync(Lwet, dLwet, (size_t)c->N * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (Lwet3D) CU_TRY(c, cudaMemcpyAsync(Lwet3D, dL3, (size_t)c->M * 8, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return OTMB_OK;
+}
+
+int otmb_set_facefluxes(otmb_ctx* c, const double* const phi[6]) {
+    if (!c || !phi) return OTMB_ERR_BADARG;
+    OT_TRY(otmb_need(c, c->have_grid, "otmb_set_grid"));
+    CU_TRY(c, cudaSetDevice(c->device));
+    for (int q = 0; q < 6; ++q) {
+        if (!phi[q]) return otmb_fail(c, OTMB_ERR_BADARG, "null face-flux array");
+        OT_TRY(upload(c, c->phi[q], phi[q], (size_t)c->M * 8));
+    }
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    c->have_phi = true;
+    return OTMB_OK;
+}
+
+int otmb_set_mlotst(otmb_ctx* c, const double* mlotst) {
+    if (!c || !mlotst) return OTMB_ERR_BADARG;
+    OT_TRY(otmb_need(c, c->have_grid, "otmb_set_grid"));
+    CU_TRY(c, cudaSetDevice(c->device));
+    OT_TRY(upload(c, c->mlotst, mlotst, (size_t)c->P * 8));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    c->have_mlotst = true;
+    return OTMB_OK;
+}
+
+int otmb_set_rho3d(otmb_ctx* c, const double* rho3d) {
+    if (!c) return OTMB_ERR_BADARG;
+    OT_TRY(otmb_need(c, c->have_grid, "otmb_set_grid"));
+    CU_TRY(c, cudaSetDevice(c->device));
+    if (!rho3d) {
+        c->have_rho3d = false;
+        return OTMB_OK;
+    }
+    OT_TRY(upload(c, c->rho3d, rho3d, (size_t)c->M * 8));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    c->have_rho3d = true;
+    return OTMB_OK;
+}
+
+int otmb_set_gridmetrics(otmb_ctx* c, const double* area2D, const double* thk, const double* zt, const double* edge,
+                         const double* dnbr, const double* Z3D, const double* lon, const double* lat) {
+    if (!c || !area2D || !thk || !zt || !edge || !dnbr) return OTMB_ERR_BADARG;
+    OT_TRY(otmb_need(c, c->have_grid, "otmb_set_grid"));
+    CU_TRY(c, cudaSetDevice(c->device));
+    OT_TRY(upload(c, c->area2D, area2D, (size_t)c->P * 8));
+    OT_TRY(upload(c, c->thk, thk, (size_t)c->M * 8));
+    OT_TRY(upload(c, c->zt, zt, (size_t)c->nz * 8));
+    OT_TRY(upload(c, c->edge, edge, (size_t)c->P * 32));
+    OT_TRY(upload(c, c->dnbr, dnbr, (size_t)c->P * 32));
+    if (Z3D) {
+        OT_TRY(upload(c, c->Z3D, Z3D, (size_t)c->M * 8));
+        c->have_z3d = true;
+    }
+    if (lon && lat) {
+        OT_TRY(upload(c, c->lon, lon, (size_t)c->P * 8));
+        OT_TRY(upload(c, c->lat, lat, (size_t)c->P * 8));
+        c->have_lonlat = true;
+    }
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    c->have_metrics = true;
+    return OTMB_OK;
+}
+
+int otmb_timer_start(otmb_ctx* c) {
+    if (!c) return OTMB_ERR_BADARG;
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaEventRecord(c->ev_t0, c->stream));
+    return OTMB_OK;
+}
+int otmb_timer_stop(otmb_ctx* c, float* ms) {
+    if (!c || !ms) return OTMB_ERR_BADARG;
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaEventRecord(c->ev_t1, c->stream));
+    CU_TRY(c, cudaEventSynchronize(c->ev_t1));
+    CU_TRY(c, cudaEventElapsedTime(ms, c->ev_t0, c->ev_t1));
+    return OTMB_OK;
+}
+int otmb_l2_flush(otmb_ctx* c) {
+    if (!c) return OTMB_ERR_BADARG;
+    CU_TRY(c, cudaSetDevice(c->device));
+    const size_t bytes = (size_t)256 << 20;  // 2x the 126 MB L2
+    CU_TRY(c, c->l2.ensure(bytes));
+    k_l2_flush<<<c->sm_count * 8, 256, 0, c->stream>>>(c->l2.as<uint4>(), (i64)(bytes / 16));
+    CU_TRY(c, cudaGetLastError());
+    return OTMB_OK;
+}
+int otmb_launch_count(otmb_ctx* c, int64_t* launches) {
+    if (!c || !launches) return OTMB_ERR_BADARG;
+    *launches = c->launches;
+    return OTMB_OK;
+}
+int otmb_last_build_ms(otmb_ctx* c, float* ms) {
+    if (!c || !ms) return OTMB_ERR_BADARG;
+    *ms = c->last_build_ms;
+    return OTMB_OK;
+}
+int otmb_synchronize(otmb_ctx* c) {
+    if (!c) return OTMB_ERR_BADARG;
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return OTMB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,132 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports every symbol include/otmb.h declares,
+fails loudly without a GPU (no CPU fallback), and the host-side logic of the shim (cleaning,
+vertex permutation, topology detection, synthetic generator invariants) behaves like the reference."""
+import ctypes as C
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import otmb_b200
+import otmb_b200.api as A
+from otmb_b200 import _lib, synthetic
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "otmb.h").read_text()
+    declared = set(re.findall(r"\b(otmb_[a-z0-9_]+)\s*\(", header))
+    declared -= {"otmb_ctx", "otmb_tm_params"}
+    assert len(declared) >= 30
+    lib = C.CDLL(str(_lib.LIB_PATH))
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in otmb.h but not exported by libotmb.so"
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    out = subprocess.run(["nm", "-D", "--defined-only", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    assert all(re.search(rf"\bT {n}\b", out) for n in declared)
+
+
+def test_library_is_sm100a_only_and_has_no_cpu_fallback():
+    lib = _lib.load()
+    assert lib.otmb_version() >= 100
+    assert b"no CPU fallback" in lib.otmb_status_string(_lib.ERR_NO_GPU)
+    n = C.c_int(-1)
+    assert lib.otmb_device_count(C.byref(n)) == 0
+    if n.value == 0:                       # this container: creating a context must fail loudly
+        h = C.c_void_p()
+        assert lib.otmb_create(C.byref(h), 0) == _lib.ERR_NO_GPU and not h.value
+        with pytest.raises(A.OTMBError) as e:
+            A.Context(0)
+        assert e.value.code == _lib.ERR_NO_GPU
+    sass = subprocess.run(["cuobjdump", "-lelf", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass and not re.search(r"sm_(5|6|7|8|9)\d", sass)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = ROOT / "oceantransportmatrixbuilder.jl_b200"
+    for p in list(pkg.glob("*.py")) + list((pkg / "csrc").glob("*")):
+        txt = p.read_text(errors="ignore")
+        assert not re.search(r"^\s*(from|import)\s+oracle\b|oracle/|otmb_oracle|pyoracle", txt, re.M), \
+            f"{p} reaches into oracle/"
+
+
+def test_error_messages_are_the_references():
+    lib = _lib.load()
+    want = {1: "Tadv contains NaNs.", 2: "TκH contains NaNs.", 3: "TκVML contains NaNs.", 4: "TκVdeep contains NaNs.",
+            5: "ρ contains NaNs", 6: "Unknown grid type"}
+    for code, msg in want.items():
+        assert lib.otmb_status_string(code).decode() == msg
+
+
+def test_clean_missing_and_fillvalue():
+    f = A.Field(np.array([[0.0, -0.0, 5.0], [1e20, np.nan, 2.0]]), {"_FillValue": 1e20})
+    a = A._clean_missing(f, [1e20])
+    assert np.isnan(a[0, 0]) and a[0, 1] == 0.0 and np.signbit(a[0, 1]) and np.isnan(a[1, 0]) and np.isnan(a[1, 1])
+    assert a.flags.f_contiguous and a[0, 2] == 5.0
+    m = np.ma.masked_array([[1.0, 2.0]], mask=[[False, True]])
+    assert np.isnan(A._clean_missing(m, [])[0, 1])
+
+
+@pytest.mark.parametrize("topo", ["bipolar", "tripolar"])
+def test_topology_and_vertex_permutation(topo):
+    oc = synthetic.make_ocean(16, 10, 4, topo, seed=1)
+    t = A.getgridtopology(oc.lon_vertices, oc.lat_vertices, oc.lev)
+    assert (t.kind, t.nx, t.ny, t.nz) == (topo, 16, 10, 4)
+    assert A.vertexpermutation(oc.lon_vertices, oc.lat_vertices) == [0, 1, 2, 3]
+    perm = [3, 2, 0, 1]
+    p = A.vertexpermutation(oc.lon_vertices[perm], oc.lat_vertices[perm])
+    assert np.array_equal(oc.lon_vertices[perm][p], oc.lon_vertices)
+    lonv = oc.lon_vertices.copy()
+    if topo == "tripolar":
+        lonv[2, 2, -1] += 11.0
+        with pytest.warns(UserWarning):
+            assert A.getgridtopology(lonv, oc.lat_vertices, oc.lev).kind == "unknown"
+        # periodic longitudes still count as equal (isapprox_lon, src/gridtopology.jl:23-26)
+        lonv = oc.lon_vertices.copy()
+        lonv[2, 2, -1] += 360.0
+        assert A.getgridtopology(lonv, oc.lat_vertices, oc.lev).kind == "tripolar"
+
+
+@pytest.mark.parametrize("cfg", ["C1", "C1t"])
+def test_synthetic_generator_invariants(cfg):
+    oc = synthetic.make_config(cfg, seed=0)
+    oc2 = synthetic.make_config(cfg, seed=0)
+    assert np.array_equal(oc.umo, oc2.umo) and np.array_equal(oc.volcello, oc2.volcello)       # seeded
+    nx, ny, nz = oc.nx, oc.ny, oc.nz
+    assert oc.volcello.shape == (nx, ny, nz) and oc.volcello.flags.f_contiguous
+    assert oc.lon_vertices.shape == (4, nx, ny)
+    wet = oc.volcello > 0
+    assert (wet[:, 0, :] == False).all()                                                      # southern row is land
+    assert (np.diff(wet.astype(int), axis=2) <= 0).all()                                       # wet from the surface down
+    assert ((oc.umo == oc.fill) == ~wet).all()
+    # shared corners are bitwise identical between neighbouring cells
+    assert np.array_equal(oc.lon_vertices[1, :-1, :], oc.lon_vertices[0, 1:, :])
+    assert np.array_equal(oc.lat_vertices[2, :, :-1], oc.lat_vertices[1, :, 1:])
+    if oc.topology == "tripolar":
+        i = np.arange(nx)
+        assert np.array_equal(oc.lat_vertices[2, i, -1], oc.lat_vertices[3, nx - 1 - i, -1])  # fold
+        assert wet[0, -1, 0] and wet[nx - 1, -1, 0] and wet[nx // 2 - 1, -1, 0] and wet[nx // 2, -1, 0]
+    else:
+        assert (oc.lat_vertices[2:4, :, -1] == 90).all()
+    assert (oc.areacello[wet[:, :, 0]] > 0).all()
+
+
+def test_dump_writes_raw_float64(tmp_path):
+    oc = synthetic.make_ocean(6, 5, 3, "bipolar", seed=0)
+    oc.dump(tmp_path)
+    a = np.fromfile(tmp_path / "umo.f64", dtype="<f8").reshape((6, 5, 3), order="F")
+    assert np.array_equal(a, oc.umo)
+
+
+def test_bench_reference_arm_prints_contract_line():
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--workload", "C1t"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    import json
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "nnz(T)/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0

@@ -1,0 +1,340 @@
+"""GPU parity tests: the CUDA path (through the Python shim -> C ABI -> sm_100a kernels) against
+the CPU oracle on the same seeded inputs.  Integer / index / structure results must be
+bit-exact; Float64 values are bit-exact when both sides receive identical inputs (no FMA on
+either side) and otherwise within the north star's 1e-12 relative tolerance."""
+import numpy as np
+import pytest
+
+import otmb_b200
+import otmb_b200.api as A
+from otmb_b200 import synthetic
+from oracle import oracle as O
+
+from _util import (NAMES, assert_csc_equal, bits, fields, gpu_pipeline, oracle_pipeline,
+                   transport_from_oracle_inputs)
+
+pytestmark = pytest.mark.gpu
+
+SMALL = [
+    # nx, ny, nz, topology, seed, kwargs
+    (12, 10, 6, "tripolar", 0, {}),
+    (13, 9, 5, "tripolar", 1, {}),              # odd nx (self-neighbour column kept dry)
+    (2, 4, 3, "tripolar", 2, {}),               # nx = 2: west == east, every cell on the seam
+    (3, 3, 2, "tripolar", 4, {}),
+    (4, 2, 2, "tripolar", 5, {}),
+    (10, 8, 4, "bipolar", 3, {}),
+    (37, 11, 7, "tripolar", 6, {"dirty": True}),
+    (64, 33, 9, "bipolar", 7, {"dirty": True, "float32_roundtrip": True}),
+    (1, 5, 4, "bipolar", 8, {"land_frac": 0.0}),  # nx = 1: a cell is its own east and west neighbour
+]
+
+
+def _ocean(nx, ny, nz, topo, seed, kw):
+    kw = dict(kw)
+    kw.setdefault("land_frac", 0.25)
+    return synthetic.make_ocean(nx, ny, nz, topo, seed=seed, **kw)
+
+
+# ------------------------------------------------------------------------------------------ K1
+@pytest.mark.parametrize("shape", [(90, 45, 20), (7, 5, 3), (64, 1, 1), (65, 3, 1), (1, 1, 1), (130, 7, 2)])
+def test_makeindices_matches_oracle(shape):
+    rng = np.random.default_rng(sum(shape))
+    v3D = np.asfortranarray(rng.random(shape) + 1.0)
+    v3D[rng.random(shape) < 0.4] = np.nan
+    got = otmb_b200.makeindices(v3D)
+    want = O.makeindices(v3D)
+    assert got.N == want["N"]
+    assert np.array_equal(got.Lwet, want["Lwet"])
+    assert np.array_equal(got.Lwet3D, want["Lwet3D"])
+    assert np.array_equal(got.wet3D, want["wet3D"])
+    assert got.L[(2, 1, 1)] == 2 and got.C[1] == (1, 1, 1)
+
+
+def test_makeindices_all_dry_and_all_wet():
+    v = np.full((9, 4, 3), np.nan, order="F")
+    ix = otmb_b200.makeindices(v)
+    assert ix.N == 0 and ix.Lwet.size == 0 and not ix.wet3D.any() and (ix.Lwet3D == 0).all()
+    v = np.ones((9, 4, 3), order="F")
+    ix = otmb_b200.makeindices(v)
+    assert ix.N == v.size and np.array_equal(ix.Lwet, np.arange(1, v.size + 1)) and ix.wet3D.all()
+
+
+# ------------------------------------------------------------------------------------------ K2/K3
+@pytest.mark.parametrize("cfg", ["C1", "C1t"])
+def test_gridmetrics_matches_oracle(cfg):
+    oc = synthetic.make_config(cfg, seed=3)
+    f = fields(oc)
+    gm = otmb_b200.makegridmetrics(areacello=f["areacello"], volcello=f["volcello"], lon=f["lon"], lat=f["lat"],
+                                   lev=f["lev"], lon_vertices=f["lon_vertices"], lat_vertices=f["lat_vertices"])
+    v3D, area = O.clean_missing(oc.volcello), O.clean_missing(oc.areacello)
+    assert gm.gridtopology.kind == O.getgridtopology(oc.lon_vertices, oc.lat_vertices) == oc.topology
+    assert np.array_equal(bits(gm.v3D), bits(v3D)) and np.array_equal(bits(gm.area2D), bits(area))
+    want = O.gridmetrics(area, v3D, oc.lon, oc.lat, oc.lon_vertices, oc.lat_vertices, oc.topology)
+    # division / cumsum: IEEE, sequential -> bit-exact
+    assert np.array_equal(bits(gm.thkcello), bits(want["thkcello"]))
+    assert np.array_equal(bits(gm.Z3D), bits(want["Z3D"]))
+    for q, d in enumerate(A.DIRS):
+        for name, key in (("edge_length_2D", "edge"), ("distance_to_edge_2D", "dedge"), ("distance_to_neighbour_2D", "dnbr")):
+            g, w = getattr(gm, name)[d], want[key][:, :, q]
+            assert np.array_equal(np.isnan(g), np.isnan(w)), (name, d)
+            # libm asin/sqrt may differ in the last bits between CUDA and glibc: 1e-13 relative
+            np.testing.assert_allclose(g, w, rtol=1e-13, atol=0, equal_nan=True, err_msg=f"{name}[{d}]")
+    if oc.topology == "bipolar":
+        assert (gm.edge_length_2D["north"][:, -1] == 0.0).all()       # sind/cosd exact at 90 degrees
+        assert np.isnan(gm.distance_to_neighbour_2D["north"][:, -1]).all()
+    assert np.isnan(gm.distance_to_neighbour_2D["south"][:, 0]).all()
+
+
+# ------------------------------------------------------------------------------------------ K4
+@pytest.mark.parametrize("case", SMALL + [(90, 45, 20, "bipolar", 11, {"dirty": True}), (90, 45, 20, "tripolar", 12, {"dirty": True})])
+def test_facefluxes_bit_exact(case):
+    oc = _ocean(*case)
+    f = fields(oc)
+    gm = otmb_b200.makegridmetrics(areacello=f["areacello"], volcello=f["volcello"], lon=f["lon"], lat=f["lat"],
+                                   lev=f["lev"], lon_vertices=f["lon_vertices"], lat_vertices=f["lat_vertices"])
+    ix = otmb_b200.makeindices(gm.v3D)
+    umo0 = oc.umo.copy(order="F")
+    phi = otmb_b200.facefluxesfrommasstransport(umo=f["umo"], vmo=f["vmo"], gridmetrics=gm, indices=ix)
+    want = O.facefluxes(oc.umo, oc.vmo, gm.v3D, oc.topology, oc.fill)
+    for k in A.FACES:
+        assert np.array_equal(bits(getattr(phi, k)), bits(want[k])), k
+    assert np.array_equal(bits(oc.umo), bits(umo0))
+
+
+def test_facefluxes_all_fill_asserts():
+    oc = synthetic.make_ocean(8, 6, 3, "bipolar", seed=0, land_frac=0.0)
+    f = fields(oc)
+    gm = otmb_b200.makegridmetrics(areacello=f["areacello"], volcello=np.where(oc.volcello == 0, 1.0, oc.volcello),
+                                   lon=f["lon"], lat=f["lat"], lev=f["lev"], lon_vertices=f["lon_vertices"],
+                                   lat_vertices=f["lat_vertices"])
+    ix = otmb_b200.makeindices(gm.v3D)
+    allfill = np.full(gm.v3D.shape, oc.fill, order="F")
+    assert ix.N == gm.v3D.size
+    with pytest.raises(A.OTMBError) as e:
+        otmb_b200.facefluxes(allfill, allfill, gm, ix, FillValue=oc.fill)
+    assert e.value.code == 7
+    with pytest.raises(O.OracleError):
+        O.facefluxes(allfill, allfill, gm.v3D, "bipolar", oc.fill)
+
+
+# ------------------------------------------------------------------------------------------ K5-K9, K11
+@pytest.mark.parametrize("path", ["fused", "fused2", "coo"])
+@pytest.mark.parametrize("case", SMALL)
+def test_transportmatrix_small_exact(case, path):
+    oc = _ocean(*case)
+    for upwind, rho in ((True, 1035.0), (False, oc.rho3d)):
+        try:
+            o = oracle_pipeline(oc, rho=rho, upwind=upwind)
+        except O.OracleError as err:
+            with pytest.raises(A.OTMBError) as e:
+                ov = O.clean_missing(oc.volcello)
+                gpu_pipeline(oc, rho=rho, path=path, upwind=upwind)
+            assert e.value.code == err.code
+            continue
+        tm, _ = transport_from_oracle_inputs(o, oc, rho=rho, path=path, upwind=upwind)
+        for oname, gname in NAMES.items():
+            assert_csc_equal(getattr(tm, gname), o["tm"][oname], f"{case} {path} {oname} upwind={upwind}", exact=True)
+
+
+@pytest.mark.parametrize("path", ["fused", "fused2", "coo"])
+@pytest.mark.parametrize("cfg,seed", [("C1", 0), ("C1t", 1)])
+def test_transportmatrix_c1_full_pipeline(cfg, seed, path):
+    """Whole pipeline on the GPU (own geometry and fluxes) against the whole oracle pipeline."""
+    oc = synthetic.make_config(cfg, seed=seed)
+    o = oracle_pipeline(oc)
+    g = gpu_pipeline(oc, path=path)
+    for oname, gname in NAMES.items():
+        # geometry goes through libm on both sides -> TκH (and T) within 1e-12, the rest bit-exact
+        exact = oname in ("Tadv", "TkVML", "TkVdeep")
+        assert_csc_equal(getattr(g["tm"], gname), o["tm"][oname], f"{cfg} {path} {oname}", exact=exact, rtol=1e-12)
+
+
+def test_coincidence_columns_take_generic_branch():
+    """Fold centre (nx/2, ny) <-> (nx/2+1, ny) and seam∩fold (1, ny) <-> (nx, ny) create duplicate
+    (row, col) pairs that sparse() sums in emit order."""
+    oc = synthetic.make_ocean(12, 10, 6, "tripolar", seed=0, land_frac=0.2)
+    o = oracle_pipeline(oc)
+    tr = O.transportmatrix(o["phi"], oc.mlotst, o["v3D"], o["gm"]["thkcello"], o["area"], oc.lev, o["gm"]["edge"],
+                           o["gm"]["dnbr"], o["topo"], 1035.0, keep_triplets=True)["triplets"]["TkH"]
+    I, J, _ = tr
+    off = I != J
+    assert len(set(zip(I[off], J[off]))) < off.sum()        # the oracle really sees duplicates
+    tm, _ = transport_from_oracle_inputs(o, oc)
+    for oname, gname in NAMES.items():
+        assert_csc_equal(getattr(tm, gname), o["tm"][oname], oname, exact=True)
+
+
+def test_zero_diffusivities_drop_zero_entries():
+    """κ = 0: TκH etc. keep explicit zeros (sparse), T drops them (sparse +)."""
+    oc = synthetic.make_ocean(16, 12, 5, "tripolar", seed=9, land_frac=0.2)
+    o = oracle_pipeline(oc, kH=0.0, kVML=0.0, kVdeep=0.0)
+    for path in ("fused", "coo"):
+        tm, _ = transport_from_oracle_inputs(o, oc, path=path, κH=0.0, κVML=0.0, κVdeep=0.0)
+        for oname, gname in NAMES.items():
+            assert_csc_equal(getattr(tm, gname), o["tm"][oname], f"{path} {oname}", exact=True)
+        assert tm.TκH.nnz > 0 and (tm.TκH.data == 0).all()
+        assert tm.T.nnz == (tm.Tadv.data != 0).sum() <= tm.Tadv.nnz
+
+
+def test_prebuilt_operators_are_reused():
+    """The Tadv/TκH/TκVML/TκVdeep kwargs skip construction (src/matrixbuilding.jl:133-143)."""
+    oc = synthetic.make_ocean(20, 14, 6, "tripolar", seed=5, land_frac=0.2)
+    o = oracle_pipeline(oc)
+    tm, gm = transport_from_oracle_inputs(o, oc)
+    phi = A.FaceFluxes(**o["phi"])
+    tm2 = A.transportmatrix(ϕ=phi, mlotst=oc.mlotst, gridmetrics=gm, indices=None, ρ=1035.0, TκH=tm.TκH, TκVdeep=tm.TκVdeep)
+    assert tm2.TκH is tm.TκH and tm2.TκVdeep is tm.TκVdeep
+    for oname, gname in NAMES.items():
+        assert_csc_equal(getattr(tm2, gname), o["tm"][oname], f"preset {oname}", exact=True)
+    tm3 = A.transportmatrix(ϕ=phi, mlotst=oc.mlotst, gridmetrics=gm, indices=None, ρ=1035.0, Tadv=tm.Tadv, TκH=tm.TκH,
+                            TκVML=tm.TκVML, TκVdeep=tm.TκVdeep)
+    assert_csc_equal(tm3.T, o["tm"]["T"], "all preset T", exact=True)
+
+
+# ------------------------------------------------------------------------------------------ errors
+def test_errors_match_reference():
+    oc = synthetic.make_ocean(14, 10, 5, "tripolar", seed=2, land_frac=0.2)
+    o = oracle_pipeline(oc)
+    # ρ contains NaNs (src/matrixbuilding.jl:233)
+    rho = oc.rho3d.copy(order="F")
+    L = int(o["ix"]["Lwet"][3]) - 1
+    rho.ravel(order="F")[L] = np.nan
+    rho = np.asfortranarray(rho)
+    with pytest.raises(A.OTMBError) as e:
+        transport_from_oracle_inputs(o, oc, rho=rho)
+    assert e.value.code == 5 and str(e.value) == "ρ contains NaNs"
+    # a non-zero flux out of a dry cell: the reference dies with a MethodError (:247-250)
+    phi = {k: v.copy(order="F") for k, v in o["phi"].items()}
+    wet = o["ix"]["wet3D"]
+    east_dry = np.roll(wet, -1, axis=0)
+    idx = np.argwhere(wet & ~east_dry)[0]
+    phi["east"][tuple(idx)] = -5.0e6       # inflow "from East" where the east cell is dry
+    o2 = dict(o, phi=phi)
+    with pytest.raises(A.OTMBError) as e:
+        transport_from_oracle_inputs(o2, oc)
+    assert e.value.code == 8
+    with pytest.raises(O.OracleError) as eo:
+        O.transportmatrix(phi, oc.mlotst, o["v3D"], o["gm"]["thkcello"], o["area"], oc.lev, o["gm"]["edge"],
+                          o["gm"]["dnbr"], o["topo"], 1035.0)
+    assert eo.value.code == 8
+    # NaN geometry -> "TκH contains NaNs." (:61)
+    gm_bad = dict(o["gm"])
+    edge = gm_bad["edge"].copy(order="F")
+    i, j, k = np.argwhere(wet)[5]
+    edge[i, j, :] = np.nan
+    gm_bad["edge"] = edge
+    with pytest.raises(A.OTMBError) as e:
+        transport_from_oracle_inputs(dict(o, gm=gm_bad), oc)
+    assert e.value.code == 2 and str(e.value) == "TκH contains NaNs."
+
+
+def test_odd_nx_self_neighbour_errors_like_reference():
+    oc = synthetic.make_ocean(13, 9, 5, "tripolar", seed=1, land_frac=0.2, allow_self_neighbour=True)
+    with pytest.raises(O.OracleError) as eo:
+        oracle_pipeline(oc)
+    with pytest.raises(A.OTMBError) as e:
+        gpu_pipeline(oc)
+    assert e.value.code == eo.value.code == 2
+
+
+def test_unknown_topology_errors():
+    oc = synthetic.make_ocean(12, 8, 4, "tripolar", seed=0)
+    f = fields(oc)
+    lonv = oc.lon_vertices.copy(order="F")
+    lonv[2, 3, -1] += 17.0                                  # break the fold symmetry
+    with pytest.warns(UserWarning):
+        with pytest.raises(A.OTMBError) as e:
+            otmb_b200.makegridmetrics(areacello=f["areacello"], volcello=f["volcello"], lon=f["lon"], lat=f["lat"],
+                                      lev=f["lev"], lon_vertices=lonv, lat_vertices=f["lat_vertices"])
+    assert e.value.code == 6 and str(e.value) == "Unknown grid type"
+
+
+# ------------------------------------------------------------------------------------------ generic sparse / +
+@pytest.mark.parametrize("n,len_,seed", [(50, 400, 0), (7, 600, 1), (1000, 3000, 2), (5, 0, 3), (300, 20000, 4)])
+def test_sparse_and_spadd_match_oracle(n, len_, seed):
+    rng = np.random.default_rng(seed)
+    I, J = rng.integers(1, n + 1, len_), rng.integers(1, n + 1, len_)
+    V = rng.normal(size=len_) * 10.0 ** rng.integers(-8, 8, len_)
+    V[rng.random(len_) < 0.05] = 0.0
+    want = O.sparse(I, J, V, n)
+    cp, rv, nz = otmb_b200.sparse(I, J, V, n)
+    assert np.array_equal(cp, want.colptr) and np.array_equal(rv, want.rowval)
+    assert np.array_equal(bits(nz), bits(want.nzval))
+    I2, J2 = rng.integers(1, n + 1, len_ // 2), rng.integers(1, n + 1, len_ // 2)
+    V2 = rng.normal(size=len_ // 2)
+    # make exact cancellations so that + drops entries
+    B = O.sparse(np.concatenate([I2, I[: len_ // 3]]), np.concatenate([J2, J[: len_ // 3]]),
+                 np.concatenate([V2, np.zeros(len_ // 3)]), n)
+    neg = O.CSC(want.n, want.colptr, want.rowval, -want.nzval)
+    for Bm in (B, neg):
+        wsum = O.spadd(want, Bm)
+        cp, rv, nz = otmb_b200.spadd((want.colptr, want.rowval, want.nzval), (Bm.colptr, Bm.rowval, Bm.nzval), n)
+        assert np.array_equal(cp, wsum.colptr) and np.array_equal(rv, wsum.rowval)
+        assert np.array_equal(bits(nz), bits(wsum.nzval))
+
+
+# ------------------------------------------------------------------------------------------ full size (C2)
+def test_transportmatrix_c2_full_size():
+    """ACCESS-ESM1-5 1° shape (360x300x50, tripolar), all paths vs the oracle, plus the
+    reference's own invariants (test/online.jl:92-123)."""
+    oc = synthetic.make_config("C2", seed=0)
+    o = oracle_pipeline(oc)
+    N = o["ix"]["N"]
+    for path in ("coo", "fused2", "fused"):
+        tm, _ = transport_from_oracle_inputs(o, oc, path=path)
+        for oname, gname in NAMES.items():
+            assert_csc_equal(getattr(tm, gname), o["tm"][oname], f"C2 {path} {oname}", exact=True)
+    T_exact = tm.T
+    g = gpu_pipeline(oc)
+    for oname, gname in NAMES.items():
+        exact = oname in ("Tadv", "TkVML", "TkVdeep")
+        assert_csc_equal(getattr(g["tm"], gname), o["tm"][oname], f"C2 pipeline {oname}", exact=exact, rtol=1e-12)
+    T = g["tm"].T
+    v = o["v3D"].ravel(order="F")[~np.isnan(o["v3D"].ravel(order="F"))]
+    one = np.ones(N)
+    Myr = 365.25 * 86400 * 1e6
+    for name in ("TκH", "TκVML", "TκVdeep"):
+        Tm = getattr(g["tm"], name)
+        assert np.linalg.norm(one) / np.linalg.norm(Tm @ one) / Myr > 1e6, name
+    for name in A.MATRICES:
+        Tm = getattr(g["tm"], name)
+        assert np.linalg.norm(v) / np.linalg.norm(Tm.T @ v) / Myr > 1e6, name
+    d = T.diagonal()
+    assert (d > 0).all()
+    offd = T.copy()
+    offd.setdiag(0)
+    offd.eliminate_zeros()
+    assert (offd.data < 0).all()
+    # T·1 conservation residual must match the oracle's
+    To = o["tm"]["T"].scipy()
+    assert np.array_equal(bits(T_exact @ one), bits(To @ one))
+
+
+# ------------------------------------------------------------------------------------------ K10
+@pytest.mark.parametrize("cfg", ["C1t"])
+def test_redigm_matches_oracle(cfg):
+    oc = synthetic.make_config(cfg, seed=4)
+    o = oracle_pipeline(oc)
+    tm, gm = transport_from_oracle_inputs(o, oc)
+    for d in ("I", "J"):
+        got = A.globalverticalfacetriadderivative(oc.rho3d, gm, None, d)
+        want = O.triad(oc.rho3d, oc.lon, oc.lat, o["gm"]["Z3D"], o["v3D"], oc.topology, d)
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        np.testing.assert_allclose(got, want, rtol=1e-12, atol=0, equal_nan=True)
+    chi = np.asfortranarray(o["gm"]["Z3D"] ** 2)
+    got, want = A.globalverticaldyadderivative(chi, gm, None), O.dyad(chi, o["gm"]["Z3D"], o["v3D"], oc.topology)
+    assert np.array_equal(bits(got), bits(want))
+    u, v = A.bolus_GM_velocity(oc.rho3d, gm, None)
+    uo, vo = O.bolus_gm(oc.rho3d, oc.lon, oc.lat, o["gm"]["Z3D"], o["v3D"], oc.topology)
+    np.testing.assert_allclose(u, uo, rtol=1e-10, atol=1e-300, equal_nan=True)
+    np.testing.assert_allclose(v, vo, rtol=1e-10, atol=1e-300, equal_nan=True)
+
+
+def test_triad_on_bipolar_top_row_throws_like_reference():
+    oc = synthetic.make_ocean(10, 8, 4, "bipolar", seed=3, land_frac=0.0)
+    o = oracle_pipeline(oc)
+    tm, gm = transport_from_oracle_inputs(o, oc)
+    with pytest.raises(O.OracleError):
+        O.triad(oc.rho3d, oc.lon, oc.lat, o["gm"]["Z3D"], o["v3D"], "bipolar", "J")
+    with pytest.raises(A.OTMBError):
+        A.globalverticalfacetriadderivative(oc.rho3d, gm, None, "J")
