@@ -25,8 +25,10 @@ SMALL = [
     (10, 8, 4, "bipolar", 3, {}),
     (37, 11, 7, "tripolar", 6, {"dirty": True}),
     (64, 33, 9, "bipolar", 7, {"dirty": True, "float32_roundtrip": True}),
-    (1, 5, 4, "bipolar", 8, {"land_frac": 0.0}),  # nx = 1: a cell is its own east and west neighbour
 ]
+# nx = 1: a cell is its own east and west neighbour (the reference's makegridmetrics cannot build
+# such a grid — vertexpermutation indexes cell (2,1) — but transportmatrix itself is well defined)
+SMALL_T = SMALL + [(1, 5, 4, "bipolar", 8, {"land_frac": 0.0})]
 
 
 def _ocean(nx, ny, nz, topo, seed, kw):
@@ -119,7 +121,7 @@ def test_facefluxes_all_fill_asserts():
 
 # ------------------------------------------------------------------------------------------ K5-K9, K11
 @pytest.mark.parametrize("path", ["fused", "fused2", "coo"])
-@pytest.mark.parametrize("case", SMALL)
+@pytest.mark.parametrize("case", SMALL_T)
 def test_transportmatrix_small_exact(case, path):
     oc = _ocean(*case)
     for upwind, rho in ((True, 1035.0), (False, oc.rho3d)):
