@@ -1,0 +1,743 @@
+// fused_v2.cu — OTMB_PATH_FUSED: single-pass direct CSC assembly, one thread per WET cell.
+//
+// Same mathematics and ordering rules as fused.cu (read its header first: gather form, emit
+// order, generic branch for coincident neighbours); what changes is the schedule, driven by the
+// ncu profile of the first version (profiles/r1_fused_v1_*: 19 % of executed instructions in the
+// look-back spin, IPC 0.2, 128 registers):
+//   * threads map to wet cells through the compacted Lwet list (no idle dry lanes; a tile of 256
+//     consecutive wet cells owns a contiguous slice of every output array);
+//   * phase 0 derives the sparsity PATTERN of all five matrices from cheap data only (wet bits,
+//     sign of the six face fluxes, mixed-layer test), so the tile aggregate is published a few
+//     hundred cycles after the tile starts and the decoupled look-back never waits on anybody's
+//     floating-point work;
+//   * phase 1 streams operator by operator (Tadv, TκH, TκVML/TκVdeep), each with one batch of
+//     independent loads, writes its entries straight to their final CSC position and folds them
+//     into the running T = ((Tadv + TκH) + TκVML) + TκVdeep accumulators.
+// The pattern of T is the union of the four patterns; sparse `+` additionally drops results that
+// are exactly zero (/root/reference/src/matrixbuilding.jl:147).  Those are counted by a flag and,
+// only when any occurred (e.g. κ = 0), a compaction pass (k_drop_zero_*) removes them.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TILE = 256;
+constexpr int NW = TILE / 32;
+constexpr u64 ST_AGG = 1ull << 62, ST_PRE = 2ull << 62, ST_MASK = (1ull << 62) - 1;
+
+enum { cT = 0, cS = 1, cW = 2, cC = 3, cE = 4, cN = 5, cB = 6 };
+enum { sW = 0, sE = 1, sS = 2, sN = 3, sB = 4, sT = 5 };  // emit-order slots W,E,S,N,B,T
+constexpr unsigned HMASK = (1u << cS) | (1u << cW) | (1u << cE) | (1u << cN);
+constexpr unsigned VMASK = (1u << cT) | (1u << cB);
+
+struct FastDiv {
+    u64 mul;
+    unsigned shift;
+};
+__device__ __forceinline__ unsigned fdiv(unsigned n, FastDiv f) { return (unsigned)((n * f.mul) >> f.shift); }
+
+struct V2Params {
+    GridDims g;
+    FastDiv divP, divNx;
+    const double *v3D, *thk, *area2D, *zt, *edge, *dnbr, *mlotst, *rho3d;
+    const double *pe, *pw, *pn, *ps, *pt, *pb;
+    const u64* mask;
+    const uint32_t* wpre;
+    const int* lwet;
+    double kH, kVML, kVdeep, rho;
+    int upwind, base, build;
+    int ntiles;
+    i64 N;
+    i64* colptr[5];
+    i64* rowval[5];
+    double* nzval[5];
+    DevFlags* flags;
+    u64* tile_state;
+};
+
+__device__ __forceinline__ u64 ld_vol(const u64* p) { return *reinterpret_cast<const volatile u64*>(p); }
+__device__ __forceinline__ void st_vol(u64* p, u64 v) { *reinterpret_cast<volatile u64*>(p) = v; }
+__device__ __forceinline__ u64 warp_sum64(u64 v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+__device__ __forceinline__ double upflux(double x, bool take_max, bool up) {
+    return up ? (take_max ? jl_max(x, 0.0) : jl_min(x, 0.0)) : x / 2;
+}
+
+// ---------------------------------------------------------------------------------------
+// generic branch (coincident neighbours): everything recomputed in local memory, sparse()'s
+// sort + in-order combine reproduced literally.  Rare (a handful of columns per level).
+// ---------------------------------------------------------------------------------------
+struct Ent {
+    int row;
+    i64 key;
+    double val;
+};
+__device__ void ent_sort(Ent* e, int n) {
+    for (int a = 1; a < n; ++a) {
+        Ent x = e[a];
+        int b = a - 1;
+        while (b >= 0 && (e[b].row > x.row || (e[b].row == x.row && e[b].key > x.key))) {
+            e[b + 1] = e[b];
+            --b;
+        }
+        e[b + 1] = x;
+    }
+}
+__device__ int ent_combine(const Ent* e, int n, int* rows, double* vals) {
+    int m = 0;
+    for (int a = 0; a < n; ++a) {
+        if (m > 0 && rows[m - 1] == e[a].row)
+            vals[m - 1] = vals[m - 1] + e[a].val;
+        else {
+            rows[m] = e[a].row;
+            vals[m] = e[a].val;
+            ++m;
+        }
+    }
+    return m;
+}
+__device__ int distinct_rows(unsigned m, const int* r) {
+    int n = 0;
+    for (int c = 0; c < 7; ++c) {
+        if (!(m >> c & 1)) continue;
+        bool dup = false;
+        for (int d = 0; d < c; ++d)
+            if ((m >> d & 1) && r[d] == r[c]) dup = true;
+        n += !dup;
+    }
+    return n;
+}
+
+__device__ __noinline__ void generic_full(const V2Params& P, int L, int i, int j, int k, const int* Lc, const int* r,
+                                          unsigned wetm, bool fold, unsigned act_adv, const double* pmag,
+                                          unsigned act_ml, const i64* off, unsigned* errbits) {
+    const GridDims g = P.g;
+    const int PP = g.P, p2 = L - k * PP;
+    const int emit_slot[7] = {sB, sN, sE, -1, sW, fold ? sN : sS, sT};
+    const int own_slot[7] = {sT, sS, sW, -1, sE, sN, sB};
+    const int rC = r[cC];
+    const double vC = __ldg(P.v3D + L);
+    const double rhoC = P.rho3d ? __ldg(P.rho3d + L) : P.rho;
+    int rows[5][8];
+    double vals[5][8];
+    int cnt[5] = {0, 0, 0, 0, 0};
+    Ent e[16];
+    int n = 0;
+    if (P.build & 2) {
+        for (int c = 0; c < 7; ++c)
+            if (c != cC && (act_adv >> c & 1)) {
+                const double rhoi = P.rho3d ? __ldg(P.rho3d + Lc[c]) : P.rho;
+                const double rb = (rhoi + rhoC) / 2;
+                const double mi = rb * __ldg(P.v3D + Lc[c]), mj = rb * vC;
+                const double a = -pmag[c] / mi, d = pmag[c] / mj;
+                if (isnan(a) || isnan(d)) *errbits |= 2u;
+                const i64 kb = (i64)r[c] * 16 + emit_slot[c] * 2;
+                e[n++] = Ent{r[c], kb, a};
+                e[n++] = Ent{rC, kb + 1, d};
+            }
+        ent_sort(e, n);
+        cnt[1] = ent_combine(e, n, rows[1], vals[1]);
+    }
+    if (P.build & 4) {
+        n = 0;
+        const double thC = __ldg(P.thk + L);
+        for (int c = 0; c < 7; ++c)
+            if ((HMASK >> c & 1) && (wetm >> c & 1)) {
+                const int own = c == cW ? OTMB_DIR_WEST : c == cE ? OTMB_DIR_EAST : c == cS ? OTMB_DIR_SOUTH : OTMB_DIR_NORTH;
+                const int opp = c == cW ? OTMB_DIR_EAST : c == cE ? OTMB_DIR_WEST : c == cS ? OTMB_DIR_NORTH
+                                                                                  : (fold ? OTMB_DIR_NORTH : OTMB_DIR_SOUTH);
+                const int q2 = Lc[c] - k * PP;
+                const double a = jl_min(thC * __ldg(P.edge + own * PP + p2), __ldg(P.thk + Lc[c]) * __ldg(P.edge + opp * PP + q2));
+                const double ka = P.kH * a;
+                const double ts = ka / (__ldg(P.dnbr + own * PP + p2) * vC);
+                const double tn = ka / (__ldg(P.dnbr + opp * PP + q2) * __ldg(P.v3D + Lc[c]));
+                if (isnan(ts) || isnan(tn)) *errbits |= 4u;
+                e[n++] = Ent{rC, (i64)rC * 16 + own_slot[c] * 2, ts};
+                e[n++] = Ent{r[c], (i64)r[c] * 16 + emit_slot[c] * 2 + 1, -tn};
+            }
+        ent_sort(e, n);
+        cnt[2] = ent_combine(e, n, rows[2], vals[2]);
+    }
+    for (int op = 3; op <= 4; ++op) {
+        if (!(P.build >> op & 1)) continue;
+        n = 0;
+        const double area = __ldg(P.area2D + p2), ztC = __ldg(P.zt + k);
+        const double kap = op == 3 ? P.kVML : P.kVdeep;
+        for (int c = 0; c < 7; ++c) {
+            const bool on = op == 3 ? (act_ml >> c & 1) : ((VMASK >> c & 1) && (wetm >> c & 1));
+            if (!on) continue;
+            const int kc = c == cT ? k - 1 : k + 1;
+            const double d = fabs(ztC - __ldg(P.zt + kc));
+            const double ka = kap * area;
+            const double ts = ka / (d * vC), tn = ka / (d * __ldg(P.v3D + Lc[c]));
+            if (isnan(ts) || isnan(tn)) *errbits |= (op == 3 ? 8u : 16u);
+            e[n++] = Ent{rC, (i64)rC * 16 + own_slot[c] * 2, ts};
+            e[n++] = Ent{r[c], (i64)r[c] * 16 + emit_slot[c] * 2 + 1, -tn};
+        }
+        ent_sort(e, n);
+        cnt[op] = ent_combine(e, n, rows[op], vals[op]);
+    }
+    if (P.build & 1) {  // union merge; exact zeros are KEPT here and flagged (the compaction pass drops them)
+        int idx[4] = {0, 0, 0, 0};
+        int m = 0;
+        while (true) {
+            int row = 0x7fffffff;
+            for (int q = 0; q < 4; ++q)
+                if (idx[q] < cnt[q + 1] && rows[q + 1][idx[q]] < row) row = rows[q + 1][idx[q]];
+            if (row == 0x7fffffff) break;
+            double x = 0.0;
+            for (int q = 0; q < 4; ++q) {
+                double v = 0.0;
+                if (idx[q] < cnt[q + 1] && rows[q + 1][idx[q]] == row) {
+                    v = vals[q + 1][idx[q]];
+                    ++idx[q];
+                }
+                x = x + v;
+            }
+            if (x == 0.0) *errbits |= 32u;
+            rows[0][m] = row;
+            vals[0][m] = x;
+            ++m;
+        }
+        cnt[0] = m;
+    }
+    for (int q = 0; q < 5; ++q) {
+        if (!(P.build >> q & 1)) continue;
+        for (int a = 0; a < cnt[q]; ++a) {
+            P.rowval[q][off[q] + a] = (i64)rows[q][a] + P.base;
+            P.nzval[q][off[q] + a] = vals[q][a];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+template <bool RHO3D>
+__global__ void __launch_bounds__(TILE, 3) k_fused_v2(const V2Params P) {
+    __shared__ u64 s_warp[NW];
+    __shared__ u64 s_excl[5];
+    __shared__ u64 s_agg[5];
+    __shared__ int s_tile;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_tile = (int)atomicAdd(&P.flags->ticket, 1ull);
+    __syncthreads();
+    const int tile = s_tile;
+    const GridDims g = P.g;
+    const i64 w64 = (i64)tile * TILE + tid;
+    const bool valid = w64 < P.N;
+    const int rC = (int)w64;
+    const bool up = P.upwind != 0;
+
+    // ================= phase 0: pattern =================
+    int L = 0, i = 0, j = 0, k = 0;
+    int Lc[7];
+    int r[7];
+    unsigned wetm = 0, act = 0, mlm = 0;   // wet neighbours; neighbours whose flux enters this column; ML pairs
+    double pmag[7];
+    unsigned lower[7];
+    bool fold = false, generic = false, natural = true;
+    unsigned m_T = 0, m_adv = 0, m_kh = 0, m_ml = 0, m_dp = 0;
+    unsigned errbits = 0;  // 1 dry nbr, 2 nan adv, 4 nan kh, 8 nan ml, 16 nan deep, 32 zero dropped, 64 nan rho
+    int cnt[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {
+        Lc[c] = 0;
+        r[c] = 0x7fffffff;
+        pmag[c] = 0.0;
+        lower[c] = (1u << c) - 1u;
+    }
+    if (valid) {
+        L = __ldg(P.lwet + rC);
+        k = (int)fdiv((unsigned)L, P.divP);
+        const int p2 = L - k * g.P;
+        j = (int)fdiv((unsigned)p2, P.divNx);
+        i = p2 - j * g.nx;
+        fold = (j == g.ny - 1) && (g.topo == OTMB_TOPO_TRIPOLAR);
+        const bool hasT = k > 0, hasB = k < g.nz - 1, hasS = j > 0, hasN = (j < g.ny - 1) || fold;
+        const bool seamW = i == 0, seamE = i == g.nx - 1;
+        Lc[cC] = L;
+        Lc[cT] = hasT ? L - g.P : L;
+        Lc[cB] = hasB ? L + g.P : L;
+        Lc[cS] = hasS ? L - g.nx : L;
+        Lc[cW] = seamW ? L + (g.nx - 1) : L - 1;
+        Lc[cE] = seamE ? L - (g.nx - 1) : L + 1;
+        Lc[cN] = (j < g.ny - 1) ? L + g.nx : (fold ? k * g.P + (g.ny - 1) * g.nx + (g.nx - 1 - i) : L);
+        r[cC] = rC;
+        const bool ex[7] = {hasT, hasS, true, true, true, hasN, hasB};
+        // wet bits (mask words are L1/L2 resident); W/E ranks follow from linear adjacency
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+            if (c == cC) continue;
+            if (ex[c] && wet_at(P.mask, Lc[c])) wetm |= 1u << c;
+        }
+        r[cW] = (wetm >> cW & 1) ? (seamW ? rank_at(P.mask, P.wpre, Lc[cW]) : rC - 1) : 0x7fffffff;
+        r[cE] = (wetm >> cE & 1) ? (seamE ? rank_at(P.mask, P.wpre, Lc[cE]) : rC + 1) : 0x7fffffff;
+        r[cT] = (wetm >> cT & 1) ? rank_at(P.mask, P.wpre, Lc[cT]) : 0x7fffffff;
+        r[cS] = (wetm >> cS & 1) ? rank_at(P.mask, P.wpre, Lc[cS]) : 0x7fffffff;
+        r[cN] = (wetm >> cN & 1) ? rank_at(P.mask, P.wpre, Lc[cN]) : 0x7fffffff;
+        r[cB] = (wetm >> cB & 1) ? rank_at(P.mask, P.wpre, Lc[cB]) : 0x7fffffff;
+
+        // face flux each neighbour carries through the face it shares with this cell (the value the
+        // reference reads at the neighbour, :244-295); loads are unconditional (index clamped to L)
+        {
+            const double xT = __ldg(P.pb + Lc[cT]);                       // emitter above: its Bottom slot, max
+            const double xS = __ldg(P.pn + Lc[cS]);                       // its North slot, min
+            const double xW = __ldg(P.pe + Lc[cW]);                       // its East slot, min
+            const double xE = __ldg(P.pw + Lc[cE]);                       // its West slot, max
+            const double xN = __ldg((fold ? P.pn : P.ps) + Lc[cN]);       // its South slot (max), or North on the fold (min)
+            const double xB = __ldg(P.pt + Lc[cB]);                       // emitter below: its Top slot, min
+            const double fT = upflux(xT, true, up), fS = upflux(xS, false, up), fW = upflux(xW, false, up),
+                         fE = upflux(xE, true, up), fN = upflux(xN, !fold, up), fB = upflux(xB, false, up);
+            if ((wetm >> cT & 1) && (fT > 0 || fT < 0)) { act |= 1u << cT; pmag[cT] = fT; }
+            if ((wetm >> cS & 1) && (fS > 0 || fS < 0)) { act |= 1u << cS; pmag[cS] = -fS; }
+            if ((wetm >> cW & 1) && (fW > 0 || fW < 0)) { act |= 1u << cW; pmag[cW] = -fW; }
+            if ((wetm >> cE & 1) && (fE > 0 || fE < 0)) { act |= 1u << cE; pmag[cE] = fE; }
+            if ((wetm >> cN & 1) && (fN > 0 || fN < 0)) { act |= 1u << cN; pmag[cN] = fold ? -fN : fN; }
+            if ((wetm >> cB & 1) && (fB > 0 || fB < 0)) { act |= 1u << cB; pmag[cB] = -fB; }
+        }
+        // own faces that point at a dry or absent cell: the reference would push `missing` (:247-250)
+        if (P.build & 2) {
+            const unsigned dry = ~wetm;
+            bool bad = false;
+            if (dry >> cW & 1) { const double f = upflux(__ldg(P.pw + L), true, up); bad |= (f > 0 || f < 0); }
+            if (dry >> cE & 1) { const double f = upflux(__ldg(P.pe + L), false, up); bad |= (f > 0 || f < 0); }
+            if (dry >> cS & 1) { const double f = upflux(__ldg(P.ps + L), true, up); bad |= (f > 0 || f < 0); }
+            if (dry >> cN & 1) { const double f = upflux(__ldg(P.pn + L), false, up); bad |= (f > 0 || f < 0); }
+            if (dry >> cB & 1) { const double f = upflux(__ldg(P.pb + L), true, up); bad |= (f > 0 || f < 0); }
+            if ((dry >> cT & 1) && hasT) { const double f = upflux(__ldg(P.pt + L), false, up); bad |= (f > 0 || f < 0); }
+            if (bad) errbits |= 1u;
+        }
+        // mixed-layer mask Ω = zt[k] < mlotst[i,j] (false for NaN / missing), :85
+        if (P.build & 8) {
+            const double ml = __ldg(P.mlotst + p2);
+            if (__ldg(P.zt + k) < ml) {
+                if ((wetm >> cT & 1) && __ldg(P.zt + (k - 1)) < ml) mlm |= 1u << cT;
+                if ((wetm >> cB & 1) && __ldg(P.zt + (k + 1)) < ml) mlm |= 1u << cB;
+            }
+        }
+        // patterns (bit cC = diagonal)
+        if (P.build & 2) m_adv = act ? (act | (1u << cC)) : 0u;
+        if (P.build & 4) m_kh = (wetm & HMASK) ? ((wetm & HMASK) | (1u << cC)) : 0u;
+        if (P.build & 8) m_ml = mlm ? (mlm | (1u << cC)) : 0u;
+        if (P.build & 16) m_dp = (wetm & VMASK) ? ((wetm & VMASK) | (1u << cC)) : 0u;
+        if (P.build & 1) m_T = m_adv | m_kh | m_ml | m_dp;
+        // rank order of the candidates
+        {
+            int prev = -1;
+            const unsigned present = wetm | (1u << cC);
+#pragma unroll
+            for (int c = 0; c < 7; ++c)
+                if (present >> c & 1) {
+                    if (r[c] <= prev) natural = false;
+                    prev = r[c];
+                }
+            if (!natural) {
+#pragma unroll
+                for (int c = 0; c < 7; ++c) {
+                    unsigned lm = 0;
+#pragma unroll
+                    for (int d = 0; d < 7; ++d)
+                        if (d != c && (present >> d & 1)) {
+                            if (r[d] < r[c]) lm |= 1u << d;
+                            if (r[d] == r[c] && (present >> c & 1)) generic = true;
+                        }
+                    lower[c] = lm;
+                }
+            }
+        }
+        if (!generic) {
+            cnt[0] = __popc(m_T);
+            cnt[1] = __popc(m_adv);
+            cnt[2] = __popc(m_kh);
+            cnt[3] = __popc(m_ml);
+            cnt[4] = __popc(m_dp);
+        } else {
+            cnt[0] = distinct_rows(m_T, r);
+            cnt[1] = distinct_rows(m_adv, r);
+            cnt[2] = distinct_rows(m_kh, r);
+            cnt[3] = distinct_rows(m_ml, r);
+            cnt[4] = distinct_rows(m_dp, r);
+        }
+    }
+
+    // ================= tile scan + decoupled look-back =================
+    u64 packed = 0;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) packed |= (u64)cnt[q] << (12 * q);
+    u64 incl = packed;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const u64 o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    u64 wbase = 0, total = 0;
+#pragma unroll
+    for (int q = 0; q < NW; ++q) {
+        const u64 sw = s_warp[q];
+        if (q < wid) wbase += sw;
+        total += sw;
+    }
+    const u64 excl_packed = wbase + incl - packed;
+    if (tid < 5) {
+        const u64 agg = (total >> (12 * tid)) & 0xfffull;
+        s_agg[tid] = agg;
+        st_vol(P.tile_state + (size_t)tile * 8 + tid, (tile == 0 ? ST_PRE : ST_AGG) | agg);
+    }
+    __syncthreads();
+    if (wid < 5) {
+        const int m = wid;
+        u64 excl = 0;
+        if (tile > 0) {
+            int look = tile - 1;
+            while (true) {
+                const int t = look - lane;
+                u64 wv = ST_PRE;
+                if (t >= 0) {
+                    do {
+                        wv = ld_vol(P.tile_state + (size_t)t * 8 + m);
+                    } while ((wv >> 62) == 0);
+                }
+                const u64 val = wv & ST_MASK;
+                const unsigned pm = __ballot_sync(0xffffffffu, (wv >> 62) == 2);
+                if (pm) {
+                    const int first = __ffs(pm) - 1;
+                    excl += warp_sum64(lane <= first ? val : 0ull);
+                    break;
+                }
+                excl += warp_sum64(val);
+                look -= 32;
+            }
+            if (lane == 0) st_vol(P.tile_state + (size_t)tile * 8 + m, ST_PRE | (excl + s_agg[m]));
+        }
+        if (lane == 0) s_excl[m] = excl;
+    }
+    __syncthreads();
+    if (tile == P.ntiles - 1 && tid < 5) {
+        const u64 nnz = s_excl[tid] + s_agg[tid];
+        P.flags->nnz[tid] = nnz;
+        if (P.build >> tid & 1) P.colptr[tid][P.N] = (i64)nnz + P.base;
+    }
+
+    // ================= phase 1: values, streamed per operator =================
+    if (valid) {
+        i64 off[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            off[q] = (i64)(s_excl[q] + ((excl_packed >> (12 * q)) & 0xfffull));
+            if (P.build >> q & 1) P.colptr[q][rC] = off[q] + P.base;
+        }
+        if (generic) {
+            generic_full(P, L, i, j, k, Lc, r, wetm, fold, act, pmag, mlm, off, &errbits);
+            atomicAdd(&P.flags->generic_columns, 1);
+        } else {
+            const int PP = g.P, p2 = L - k * PP;
+            const double vC = __ldg(P.v3D + L);
+            double vn[7];
+#pragma unroll
+            for (int c = 0; c < 7; ++c) vn[c] = (c == cC) ? vC : __ldg(P.v3D + Lc[c]);   // clamped index: always safe
+            double Tv[7];
+#pragma unroll
+            for (int c = 0; c < 7; ++c) Tv[c] = 0.0;
+
+            // ---- Tadv (:193-204)
+            if (m_adv) {
+                const double rhoC = RHO3D ? __ldg(P.rho3d + L) : P.rho;
+                if (RHO3D && isnan(rhoC)) errbits |= 64u;
+                i64* rv = P.rowval[1] + off[1];
+                double* nv = P.nzval[1] + off[1];
+                double dc[7];
+                bool bad = false;
+#pragma unroll
+                for (int c = 0; c < 7; ++c) {
+                    dc[c] = 0.0;
+                    if (c == cC || !(act >> c & 1)) continue;
+                    const double rhoi = RHO3D ? __ldg(P.rho3d + Lc[c]) : P.rho;
+                    const double rb = (rhoi + rhoC) / 2;
+                    const double a = -pmag[c] / (rb * vn[c]);
+                    dc[c] = pmag[c] / (rb * vC);
+                    bad |= isnan(a) || isnan(dc[c]);
+                    const int pos = __popc(m_adv & lower[c]);
+                    rv[pos] = (i64)r[c] + P.base;
+                    nv[pos] = a;
+                    Tv[c] = a;
+                }
+                if (bad) errbits |= 2u;
+                // diagonal: contributions in ascending emitter rank (sparse! keeps the first, adds the rest)
+                double dsum = 0.0;
+                bool first = true;
+                if (natural) {
+#pragma unroll
+                    for (int c = 0; c < 7; ++c)
+                        if (c != cC && (act >> c & 1)) {
+                            dsum = first ? dc[c] : dsum + dc[c];
+                            first = false;
+                        }
+                } else {
+                    const unsigned present = wetm | (1u << cC);
+                    for (int t = 0; t < 7; ++t) {
+#pragma unroll
+                        for (int c = 0; c < 7; ++c)
+                            if (c != cC && (act >> c & 1) && __popc(present & lower[c]) == t) {
+                                dsum = first ? dc[c] : dsum + dc[c];
+                                first = false;
+                            }
+                    }
+                }
+                const int pos = __popc(m_adv & lower[cC]);
+                rv[pos] = (i64)rC + P.base;
+                nv[pos] = dsum;
+                Tv[cC] = dsum;
+            } else if (RHO3D && (P.build & 2)) {
+                if (isnan(__ldg(P.rho3d + L))) errbits |= 64u;
+            }
+
+            // ---- TκH (:348-415, :426-435); own slots in emit order W,E,S,N
+            if (m_kh) {
+                const double thC = __ldg(P.thk + L);
+                i64* rv = P.rowval[2] + off[2];
+                double* nv = P.nzval[2] + off[2];
+                double dsum = 0.0;
+                bool first = true, bad = false;
+                const int ord[4] = {cW, cE, cS, cN};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int c = ord[q];
+                    if (!(wetm >> c & 1)) continue;
+                    const int own = c == cW ? OTMB_DIR_WEST : c == cE ? OTMB_DIR_EAST : c == cS ? OTMB_DIR_SOUTH : OTMB_DIR_NORTH;
+                    const int opp = c == cW ? OTMB_DIR_EAST : c == cE ? OTMB_DIR_WEST : c == cS ? OTMB_DIR_NORTH
+                                                                                      : (fold ? OTMB_DIR_NORTH : OTMB_DIR_SOUTH);
+                    const int q2 = Lc[c] - k * PP;
+                    const double a_own = thC * __ldg(P.edge + own * PP + p2);
+                    const double a_nbr = __ldg(P.thk + Lc[c]) * __ldg(P.edge + opp * PP + q2);
+                    const double ka = P.kH * jl_min(a_own, a_nbr);
+                    const double ts = ka / (__ldg(P.dnbr + own * PP + p2) * vC);      // row 𝑗 seen from 𝑗
+                    const double tn = ka / (__ldg(P.dnbr + opp * PP + q2) * vn[c]);   // row 𝑖 seen from 𝑖
+                    bad |= isnan(ts) || isnan(tn);
+                    dsum = first ? ts : dsum + ts;
+                    first = false;
+                    const int pos = __popc(m_kh & lower[c]);
+                    rv[pos] = (i64)r[c] + P.base;
+                    nv[pos] = -tn;
+                    Tv[c] = Tv[c] + (-tn);
+                }
+                if (bad) errbits |= 4u;
+                const int pos = __popc(m_kh & lower[cC]);
+                rv[pos] = (i64)rC + P.base;
+                nv[pos] = dsum;
+                Tv[cC] = Tv[cC] + dsum;
+            }
+
+            // ---- TκVML and TκVdeep (:450-477); own slots in emit order B, T
+            if (m_dp | m_ml) {
+                const double area = __ldg(P.area2D + p2), ztC = __ldg(P.zt + k);
+                double mls = 0.0, dps = 0.0, mlT = 0.0, mlB = 0.0, dpT = 0.0, dpB = 0.0;
+                bool firstm = true, firstd = true, badm = false, badd = false;
+                const int ord[2] = {cB, cT};
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int c = ord[q];
+                    if (!(wetm >> c & 1)) continue;
+                    const int kc = c == cT ? k - 1 : k + 1;
+                    const double d = fabs(ztC - __ldg(P.zt + kc));
+                    const double qs = d * vC, qn = d * vn[c];
+                    if (m_dp) {
+                        const double ka = P.kVdeep * area;
+                        const double ts = ka / qs, tn = ka / qn;
+                        badd |= isnan(ts) || isnan(tn);
+                        dps = firstd ? ts : dps + ts;
+                        firstd = false;
+                        if (c == cT) dpT = -tn; else dpB = -tn;
+                    }
+                    if (mlm >> c & 1) {
+                        const double ka = P.kVML * area;
+                        const double ts = ka / qs, tn = ka / qn;
+                        badm |= isnan(ts) || isnan(tn);
+                        mls = firstm ? ts : mls + ts;
+                        firstm = false;
+                        if (c == cT) mlT = -tn; else mlB = -tn;
+                    }
+                }
+                if (badm) errbits |= 8u;
+                if (badd) errbits |= 16u;
+                // T folds TκVML before TκVdeep
+                if (m_ml) {
+                    i64* rv = P.rowval[3] + off[3];
+                    double* nv = P.nzval[3] + off[3];
+                    if (mlm >> cT & 1) { const int pos = __popc(m_ml & lower[cT]); rv[pos] = (i64)r[cT] + P.base; nv[pos] = mlT; Tv[cT] = Tv[cT] + mlT; }
+                    if (mlm >> cB & 1) { const int pos = __popc(m_ml & lower[cB]); rv[pos] = (i64)r[cB] + P.base; nv[pos] = mlB; Tv[cB] = Tv[cB] + mlB; }
+                    const int pos = __popc(m_ml & lower[cC]);
+                    rv[pos] = (i64)rC + P.base;
+                    nv[pos] = mls;
+                    Tv[cC] = Tv[cC] + mls;
+                }
+                if (m_dp) {
+                    i64* rv = P.rowval[4] + off[4];
+                    double* nv = P.nzval[4] + off[4];
+                    if (wetm >> cT & 1) { const int pos = __popc(m_dp & lower[cT]); rv[pos] = (i64)r[cT] + P.base; nv[pos] = dpT; Tv[cT] = Tv[cT] + dpT; }
+                    if (wetm >> cB & 1) { const int pos = __popc(m_dp & lower[cB]); rv[pos] = (i64)r[cB] + P.base; nv[pos] = dpB; Tv[cB] = Tv[cB] + dpB; }
+                    const int pos = __popc(m_dp & lower[cC]);
+                    rv[pos] = (i64)rC + P.base;
+                    nv[pos] = dps;
+                    Tv[cC] = Tv[cC] + dps;
+                }
+            }
+
+            // ---- T: union pattern; exact zeros are flagged and removed by the compaction pass
+            if (m_T) {
+                i64* rv = P.rowval[0] + off[0];
+                double* nv = P.nzval[0] + off[0];
+                bool zero = false;
+#pragma unroll
+                for (int c = 0; c < 7; ++c) {
+                    if (!(m_T >> c & 1)) continue;
+                    const int pos = __popc(m_T & lower[c]);
+                    rv[pos] = (i64)r[c] + P.base;
+                    nv[pos] = Tv[c];
+                    zero |= (Tv[c] == 0.0);
+                }
+                if (zero) errbits |= 32u;
+            }
+        }
+    }
+
+    // ---- flags: one atomic per warp and kind
+#pragma unroll
+    for (int b = 0; b < 7; ++b) {
+        const unsigned any = __ballot_sync(0xffffffffu, (errbits >> b) & 1u);
+        if (lane == 0 && any) {
+            int* dst = b == 0 ? &P.flags->err_dry_neighbour : b == 1 ? &P.flags->nan_adv : b == 2 ? &P.flags->nan_kh
+                     : b == 3 ? &P.flags->nan_kvml : b == 4 ? &P.flags->nan_kvdeep : b == 5 ? &P.flags->zero_dropped
+                                                                                            : &P.flags->nan_rho;
+            atomicOr(dst, 1);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// zero-dropping compaction of one CSC matrix (only runs when the flag says a zero was stored)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_count_nonzero(const i64* __restrict__ colptr, const double* __restrict__ nz, i64 n,
+                                                       int base, uint32_t* __restrict__ cnt) {
+    const i64 col = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col > n) return;
+    uint32_t m = 0;
+    if (col < n)
+        for (i64 p = colptr[col] - base; p < colptr[col + 1] - base; ++p) m += (nz[p] != 0.0);
+    cnt[col] = m;
+}
+__global__ void __launch_bounds__(256) k_copy_nonzero(const i64* __restrict__ colptr, const i64* __restrict__ rv,
+                                                      const double* __restrict__ nz, i64 n, int base,
+                                                      const i64* __restrict__ ncp0, i64* __restrict__ ncp,
+                                                      i64* __restrict__ nrv, double* __restrict__ nnz_) {
+    const i64 col = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col > n) return;
+    i64 o = ncp0[col];
+    ncp[col] = o + base;
+    if (col == n) return;
+    for (i64 p = colptr[col] - base; p < colptr[col + 1] - base; ++p)
+        if (nz[p] != 0.0) {
+            nrv[o] = rv[p];
+            nnz_[o] = nz[p];
+            ++o;
+        }
+}
+
+FastDiv make_fastdiv(unsigned d) {
+    unsigned s = 0;
+    while ((1ull << s) < d) ++s;
+    FastDiv f;
+    f.shift = 32 + s;
+    f.mul = ((1ull << f.shift) + d - 1) / d;
+    return f;
+}
+
+}  // namespace
+
+int otmb_drop_zeros(otmb_ctx* c, int m, int base) {
+    const i64 n = c->N;
+    DevBuf &cnt = c->coo[3], &cp0 = c->coo[11];
+    CU_TRY(c, cnt.ensure((size_t)(n + 1) * 4));
+    CU_TRY(c, cp0.ensure((size_t)(n + 1) * 8));
+    k_count_nonzero<<<grid_for(n + 1, 256), 256, 0, c->stream>>>(c->colptr[m].as<i64>(), c->nzval[m].as<double>(), n, base,
+                                                                  cnt.as<uint32_t>());
+    LAUNCHED(c);
+    OT_TRY(otmb_scan_u32_to_i64(c, cnt.as<uint32_t>(), cp0.as<i64>(), n + 1, &c->flags.as<DevFlags>()->nnz[m]));
+    CU_TRY(c, c->add_tmp[0].ensure(c->colptr[m].cap));
+    CU_TRY(c, c->add_tmp[1].ensure(c->rowval[m].cap));
+    CU_TRY(c, c->add_tmp[2].ensure(c->nzval[m].cap));
+    k_copy_nonzero<<<grid_for(n + 1, 256), 256, 0, c->stream>>>(c->colptr[m].as<i64>(), c->rowval[m].as<i64>(),
+                                                                 c->nzval[m].as<double>(), n, base, cp0.as<i64>(),
+                                                                 c->add_tmp[0].as<i64>(), c->add_tmp[1].as<i64>(),
+                                                                 c->add_tmp[2].as<double>());
+    LAUNCHED(c);
+    CU_TRY(c, cudaGetLastError());
+    OT_TRY(otmb_fetch_flags(c));
+    std::swap(c->colptr[m], c->add_tmp[0]);
+    std::swap(c->rowval[m], c->add_tmp[1]);
+    std::swap(c->nzval[m], c->add_tmp[2]);
+    c->nnz[m] = (i64)c->h_flags->nnz[m];
+    return OTMB_OK;
+}
+
+int otmb_fused_v2_build(otmb_ctx* c, const otmb_tm_params* prm, int build) {
+    V2Params P;
+    P.g = GridDims{(int)c->nx, (int)c->ny, (int)c->nz, c->topo, (int)c->P, (int)c->M};
+    P.divP = make_fastdiv((unsigned)c->P);
+    P.divNx = make_fastdiv((unsigned)c->nx);
+    P.v3D = c->v3D.as<double>();
+    P.thk = c->thk.as<double>();
+    P.area2D = c->area2D.as<double>();
+    P.zt = c->zt.as<double>();
+    P.edge = c->edge.as<double>();
+    P.dnbr = c->dnbr.as<double>();
+    P.mlotst = c->mlotst.as<double>();
+    P.rho3d = c->have_rho3d ? c->rho3d.as<double>() : nullptr;
+    P.pe = c->phi[OTMB_FACE_EAST].as<double>();
+    P.pw = c->phi[OTMB_FACE_WEST].as<double>();
+    P.pn = c->phi[OTMB_FACE_NORTH].as<double>();
+    P.ps = c->phi[OTMB_FACE_SOUTH].as<double>();
+    P.pt = c->phi[OTMB_FACE_TOP].as<double>();
+    P.pb = c->phi[OTMB_FACE_BOTTOM].as<double>();
+    P.mask = c->mask.as<u64>();
+    P.wpre = c->wpre.as<uint32_t>();
+    P.lwet = c->lwet.as<int>();
+    P.kH = prm->kH;
+    P.kVML = prm->kVML;
+    P.kVdeep = prm->kVdeep;
+    P.rho = prm->rho;
+    P.upwind = prm->upwind;
+    P.base = prm->index_base;
+    P.build = build;
+    P.N = c->N;
+    P.flags = c->flags.as<DevFlags>();
+    const int ntiles = (int)((c->N + TILE - 1) / TILE);
+    P.ntiles = ntiles;
+    const int cap_per_col[5] = {7, 7, 5, 3, 3};
+    for (int m = 0; m < 5; ++m) {
+        P.colptr[m] = nullptr;
+        P.rowval[m] = nullptr;
+        P.nzval[m] = nullptr;
+        if (!(build >> m & 1)) continue;
+        const size_t cap = (size_t)c->N * cap_per_col[m] + 8;
+        CU_TRY(c, c->colptr[m].ensure((size_t)(c->N + 1) * 8));
+        CU_TRY(c, c->rowval[m].ensure(cap * 8));
+        CU_TRY(c, c->nzval[m].ensure(cap * 8));
+        P.colptr[m] = c->colptr[m].as<i64>();
+        P.rowval[m] = c->rowval[m].as<i64>();
+        P.nzval[m] = c->nzval[m].as<double>();
+    }
+    CU_TRY(c, c->tile_state.ensure((size_t)ntiles * 8 * sizeof(u64)));
+    P.tile_state = c->tile_state.as<u64>();
+    CU_TRY(c, cudaMemsetAsync(P.tile_state, 0, (size_t)ntiles * 8 * sizeof(u64), c->stream));
+    if (c->have_rho3d)
+        k_fused_v2<true><<<ntiles, TILE, 0, c->stream>>>(P);
+    else
+        k_fused_v2<false><<<ntiles, TILE, 0, c->stream>>>(P);
+    LAUNCHED(c);
+    CU_TRY(c, cudaGetLastError());
+    return OTMB_OK;
+}

@@ -76,7 +76,7 @@ int otmb_transportmatrix_build(otmb_ctx* c, const otmb_tm_params* prm, int64_t n
         OT_TRY(otmb_sum_operators(c, prm->index_base));
     } else {
         const int build = ops | (all4 ? 1 : 0);
-        st = otmb_fused_build(c, prm, build, prm->path == OTMB_PATH_FUSED2);
+        st = prm->path == OTMB_PATH_FUSED2 ? otmb_fused_build(c, prm, build, true) : otmb_fused_v2_build(c, prm, build);
         if (st != OTMB_OK) return st;
         CU_TRY(c, cudaEventRecord(c->ev_b1, c->stream));
         OT_TRY(otmb_fetch_flags(c));
@@ -86,6 +86,11 @@ int otmb_transportmatrix_build(otmb_ctx* c, const otmb_tm_params* prm, int64_t n
                 c->nnz[m] = (i64)c->h_flags->nnz[m];
                 c->have_mat[m] = true;
             }
+        if ((build & 1) && c->h_flags->zero_dropped) {
+            // sparse + does not store results equal to zero (:147): rare, handled by a compaction pass
+            OT_TRY(otmb_drop_zeros(c, 0, prm->index_base));
+            CU_TRY(c, cudaEventRecord(c->ev_b1, c->stream));
+        }
         if (!all4) {
             for (int m = 1; m <= 4; ++m) c->have_mat[m] = true;
             OT_TRY(otmb_sum_operators(c, prm->index_base));
