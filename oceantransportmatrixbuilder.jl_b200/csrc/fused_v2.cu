@@ -2,32 +2,41 @@
 //
 // Same mathematics and ordering rules as fused.cu (read its header first: gather form, emit
 // order, generic branch for coincident neighbours); what changes is the schedule, driven by the
-// ncu profile of the first version (profiles/r1_fused_v1_*: 19 % of executed instructions in the
-// look-back spin, IPC 0.2, 128 registers):
-//   * threads map to wet cells through the compacted Lwet list (no idle dry lanes; a tile of 256
-//     consecutive wet cells owns a contiguous slice of every output array);
+// ncu profiles under profiles/ (first version: 19 % of executed instructions in the look-back
+// spin, IPC 0.2, 128 registers; second: L1/LSU-bound on scattered 8-byte stores, 2.2x DRAM write
+// amplification):
+//   * threads map to wet cells through the compacted Lwet list (no idle dry lanes; a tile of
+//     TILE consecutive wet cells owns a contiguous slice of every output array);
 //   * phase 0 derives the sparsity PATTERN of all five matrices from cheap data only (wet bits,
 //     sign of the six face fluxes, mixed-layer test), so the tile aggregate is published a few
 //     hundred cycles after the tile starts and the decoupled look-back never waits on anybody's
 //     floating-point work;
 //   * phase 1 streams operator by operator (Tadv, TκH, TκVML/TκVdeep), each with one batch of
-//     independent loads, writes its entries straight to their final CSC position and folds them
-//     into the running T = ((Tadv + TκH) + TκVML) + TκVdeep accumulators.
+//     independent loads, folds the entries into the running
+//     T = ((Tadv + TκH) + TκVML) + TκVdeep accumulators and stages (row, value) pairs of the
+//     whole tile in shared memory at their final in-tile position;
+//   * phase 2 flushes the staged tile to the five CSC arrays with fully coalesced stores.
 // The pattern of T is the union of the four patterns; sparse `+` additionally drops results that
 // are exactly zero (/root/reference/src/matrixbuilding.jl:147).  Those are counted by a flag and,
-// only when any occurred (e.g. κ = 0), a compaction pass (k_drop_zero_*) removes them.
+// only when any occurred (e.g. κ = 0), a compaction pass (k_count_nonzero / k_copy_nonzero)
+// removes them.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
 
-constexpr int TILE = 256;
-constexpr int NW = TILE / 32;
 constexpr u64 ST_AGG = 1ull << 62, ST_PRE = 2ull << 62, ST_MASK = (1ull << 62) - 1;
 
 enum { cT = 0, cS = 1, cW = 2, cC = 3, cE = 4, cN = 5, cB = 6 };
 enum { sW = 0, sE = 1, sS = 2, sN = 3, sB = 4, sT = 5 };  // emit-order slots W,E,S,N,B,T
 constexpr unsigned HMASK = (1u << cS) | (1u << cW) | (1u << cE) | (1u << cN);
 constexpr unsigned VMASK = (1u << cT) | (1u << cB);
+// staging capacity per column and matrix (T, Tadv, TκH, TκVML, TκVdeep) and their prefix
+constexpr int CAP0 = 7, CAP1 = 7, CAP2 = 5, CAP3 = 3, CAP4 = 3, CAPSUM = 25;
+__host__ __device__ constexpr int ebase(int q) {
+    return q == 0 ? 0 : q == 1 ? CAP0 : q == 2 ? CAP0 + CAP1 : q == 3 ? CAP0 + CAP1 + CAP2 : CAP0 + CAP1 + CAP2 + CAP3;
+}
 
 struct FastDiv {
     u64 mul;
@@ -64,6 +73,7 @@ __device__ __forceinline__ u64 warp_sum64(u64 v) {
 __device__ __forceinline__ double upflux(double x, bool take_max, bool up) {
     return up ? (take_max ? jl_max(x, 0.0) : jl_min(x, 0.0)) : x / 2;
 }
+__device__ __forceinline__ bool nz(double f) { return f > 0 || f < 0; }
 
 // ---------------------------------------------------------------------------------------
 // generic branch (coincident neighbours): everything recomputed in local memory, sparse()'s
@@ -98,7 +108,7 @@ __device__ int ent_combine(const Ent* e, int n, int* rows, double* vals) {
     }
     return m;
 }
-__device__ int distinct_rows(unsigned m, const int* r) {
+__device__ __noinline__ int distinct_rows(unsigned m, const int* r) {
     int n = 0;
     for (int c = 0; c < 7; ++c) {
         if (!(m >> c & 1)) continue;
@@ -110,9 +120,11 @@ __device__ int distinct_rows(unsigned m, const int* r) {
     return n;
 }
 
-__device__ __noinline__ void generic_full(const V2Params& P, int L, int i, int j, int k, const int* Lc, const int* r,
-                                          unsigned wetm, bool fold, unsigned act_adv, const double* pmag,
-                                          unsigned act_ml, const i64* off, unsigned* errbits) {
+// stages the column's entries of all five matrices at srow/sval[sidx[q] + ...]
+__device__ __noinline__ void generic_full(const V2Params& P, int L, int k, const int* Lc, const int* r, unsigned wetm,
+                                          bool fold, unsigned act_adv, const double* pmag, unsigned act_ml,
+                                          const int* sidx /*[5] smem index of the column's first entry*/, int* srow,
+                                          double* sval, unsigned* errbits) {
     const GridDims g = P.g;
     const int PP = g.P, p2 = L - k * PP;
     const int emit_slot[7] = {sB, sN, sE, -1, sW, fold ? sN : sS, sT};
@@ -206,15 +218,19 @@ __device__ __noinline__ void generic_full(const V2Params& P, int L, int i, int j
     for (int q = 0; q < 5; ++q) {
         if (!(P.build >> q & 1)) continue;
         for (int a = 0; a < cnt[q]; ++a) {
-            P.rowval[q][off[q] + a] = (i64)rows[q][a] + P.base;
-            P.nzval[q][off[q] + a] = vals[q][a];
+            srow[sidx[q] + a] = rows[q][a];
+            sval[sidx[q] + a] = vals[q][a];
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------
-template <bool RHO3D>
-__global__ void __launch_bounds__(TILE, 3) k_fused_v2(const V2Params P) {
+template <bool RHO3D, int TILE, int MINB>
+__global__ void __launch_bounds__(TILE, MINB) k_fused_v2(const V2Params P) {
+    constexpr int NW = TILE / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* sval = reinterpret_cast<double*>(smem_raw);            // CAPSUM*TILE doubles
+    int* srow = reinterpret_cast<int*>(sval + CAPSUM * TILE);      // CAPSUM*TILE ints
     __shared__ u64 s_warp[NW];
     __shared__ u64 s_excl[5];
     __shared__ u64 s_agg[5];
@@ -231,12 +247,12 @@ __global__ void __launch_bounds__(TILE, 3) k_fused_v2(const V2Params P) {
     const bool up = P.upwind != 0;
 
     // ================= phase 0: pattern =================
-    int L = 0, i = 0, j = 0, k = 0;
+    int L = 0, k = 0, p2 = 0;
     int Lc[7];
     int r[7];
     unsigned wetm = 0, act = 0, mlm = 0;   // wet neighbours; neighbours whose flux enters this column; ML pairs
     double pmag[7];
-    unsigned lower[7];
+    u64 lowpack = 0;   // non-natural order only: 7-bit "candidates with a smaller rank" mask per candidate
     bool fold = false, generic = false, natural = true;
     unsigned m_T = 0, m_adv = 0, m_kh = 0, m_ml = 0, m_dp = 0;
     unsigned errbits = 0;  // 1 dry nbr, 2 nan adv, 4 nan kh, 8 nan ml, 16 nan deep, 32 zero dropped, 64 nan rho
@@ -246,14 +262,13 @@ __global__ void __launch_bounds__(TILE, 3) k_fused_v2(const V2Params P) {
         Lc[c] = 0;
         r[c] = 0x7fffffff;
         pmag[c] = 0.0;
-        lower[c] = (1u << c) - 1u;
     }
     if (valid) {
         L = __ldg(P.lwet + rC);
         k = (int)fdiv((unsigned)L, P.divP);
-        const int p2 = L - k * g.P;
-        j = (int)fdiv((unsigned)p2, P.divNx);
-        i = p2 - j * g.nx;
+        p2 = L - k * g.P;
+        const int j = (int)fdiv((unsigned)p2, P.divNx);
+        const int i = p2 - j * g.nx;
         fold = (j == g.ny - 1) && (g.topo == OTMB_TOPO_TRIPOLAR);
         const bool hasT = k > 0, hasB = k < g.nz - 1, hasS = j > 0, hasN = (j < g.ny - 1) || fold;
         const bool seamW = i == 0, seamE = i == g.nx - 1;
@@ -266,18 +281,22 @@ __global__ void __launch_bounds__(TILE, 3) k_fused_v2(const V2Params P) {
         Lc[cN] = (j < g.ny - 1) ? L + g.nx : (fold ? k * g.P + (g.ny - 1) * g.nx + (g.nx - 1 - i) : L);
         r[cC] = rC;
         const bool ex[7] = {hasT, hasS, true, true, true, hasN, hasB};
-        // wet bits (mask words are L1/L2 resident); W/E ranks follow from linear adjacency
+        // wet bits and ranks: mask word + word prefix of every candidate, loaded unconditionally in one
+        // batch (L1/L2 resident, 12 bytes per 64 cells); W/E ranks follow from linear adjacency off the seam
 #pragma unroll
         for (int c = 0; c < 7; ++c) {
             if (c == cC) continue;
-            if (ex[c] && wet_at(P.mask, Lc[c])) wetm |= 1u << c;
+            const u64 word = __ldg(P.mask + (Lc[c] >> 6));
+            const int pre = (int)__ldg(P.wpre + (Lc[c] >> 6));
+            const bool wet = ex[c] && ((word >> (Lc[c] & 63)) & 1ull);
+            int rk = pre + __popcll(word & ((1ull << (Lc[c] & 63)) - 1ull));
+            if (c == cW && !seamW) rk = rC - 1;
+            if (c == cE && !seamE) rk = rC + 1;
+            if (wet) {
+                wetm |= 1u << c;
+                r[c] = rk;
+            }
         }
-        r[cW] = (wetm >> cW & 1) ? (seamW ? rank_at(P.mask, P.wpre, Lc[cW]) : rC - 1) : 0x7fffffff;
-        r[cE] = (wetm >> cE & 1) ? (seamE ? rank_at(P.mask, P.wpre, Lc[cE]) : rC + 1) : 0x7fffffff;
-        r[cT] = (wetm >> cT & 1) ? rank_at(P.mask, P.wpre, Lc[cT]) : 0x7fffffff;
-        r[cS] = (wetm >> cS & 1) ? rank_at(P.mask, P.wpre, Lc[cS]) : 0x7fffffff;
-        r[cN] = (wetm >> cN & 1) ? rank_at(P.mask, P.wpre, Lc[cN]) : 0x7fffffff;
-        r[cB] = (wetm >> cB & 1) ? rank_at(P.mask, P.wpre, Lc[cB]) : 0x7fffffff;
 
         // face flux each neighbour carries through the face it shares with this cell (the value the
         // reference reads at the neighbour, :244-295); loads are unconditional (index clamped to L)
@@ -290,31 +309,32 @@ __global__ void __launch_bounds__(TILE, 3) k_fused_v2(const V2Params P) {
             const double xB = __ldg(P.pt + Lc[cB]);                       // emitter below: its Top slot, min
             const double fT = upflux(xT, true, up), fS = upflux(xS, false, up), fW = upflux(xW, false, up),
                          fE = upflux(xE, true, up), fN = upflux(xN, !fold, up), fB = upflux(xB, false, up);
-            if ((wetm >> cT & 1) && (fT > 0 || fT < 0)) { act |= 1u << cT; pmag[cT] = fT; }
-            if ((wetm >> cS & 1) && (fS > 0 || fS < 0)) { act |= 1u << cS; pmag[cS] = -fS; }
-            if ((wetm >> cW & 1) && (fW > 0 || fW < 0)) { act |= 1u << cW; pmag[cW] = -fW; }
-            if ((wetm >> cE & 1) && (fE > 0 || fE < 0)) { act |= 1u << cE; pmag[cE] = fE; }
-            if ((wetm >> cN & 1) && (fN > 0 || fN < 0)) { act |= 1u << cN; pmag[cN] = fold ? -fN : fN; }
-            if ((wetm >> cB & 1) && (fB > 0 || fB < 0)) { act |= 1u << cB; pmag[cB] = -fB; }
+            if ((wetm >> cT & 1) && nz(fT)) { act |= 1u << cT; pmag[cT] = fT; }
+            if ((wetm >> cS & 1) && nz(fS)) { act |= 1u << cS; pmag[cS] = -fS; }
+            if ((wetm >> cW & 1) && nz(fW)) { act |= 1u << cW; pmag[cW] = -fW; }
+            if ((wetm >> cE & 1) && nz(fE)) { act |= 1u << cE; pmag[cE] = fE; }
+            if ((wetm >> cN & 1) && nz(fN)) { act |= 1u << cN; pmag[cN] = fold ? -fN : fN; }
+            if ((wetm >> cB & 1) && nz(fB)) { act |= 1u << cB; pmag[cB] = -fB; }
         }
         // own faces that point at a dry or absent cell: the reference would push `missing` (:247-250)
         if (P.build & 2) {
             const unsigned dry = ~wetm;
             bool bad = false;
-            if (dry >> cW & 1) { const double f = upflux(__ldg(P.pw + L), true, up); bad |= (f > 0 || f < 0); }
-            if (dry >> cE & 1) { const double f = upflux(__ldg(P.pe + L), false, up); bad |= (f > 0 || f < 0); }
-            if (dry >> cS & 1) { const double f = upflux(__ldg(P.ps + L), true, up); bad |= (f > 0 || f < 0); }
-            if (dry >> cN & 1) { const double f = upflux(__ldg(P.pn + L), false, up); bad |= (f > 0 || f < 0); }
-            if (dry >> cB & 1) { const double f = upflux(__ldg(P.pb + L), true, up); bad |= (f > 0 || f < 0); }
-            if ((dry >> cT & 1) && hasT) { const double f = upflux(__ldg(P.pt + L), false, up); bad |= (f > 0 || f < 0); }
+            if (dry >> cW & 1) bad |= nz(upflux(__ldg(P.pw + L), true, up));
+            if (dry >> cE & 1) bad |= nz(upflux(__ldg(P.pe + L), false, up));
+            if (dry >> cS & 1) bad |= nz(upflux(__ldg(P.ps + L), true, up));
+            if (dry >> cN & 1) bad |= nz(upflux(__ldg(P.pn + L), false, up));
+            if (dry >> cB & 1) bad |= nz(upflux(__ldg(P.pb + L), true, up));
+            if ((dry >> cT & 1) && hasT) bad |= nz(upflux(__ldg(P.pt + L), false, up));
             if (bad) errbits |= 1u;
         }
         // mixed-layer mask Ω = zt[k] < mlotst[i,j] (false for NaN / missing), :85
         if (P.build & 8) {
             const double ml = __ldg(P.mlotst + p2);
-            if (__ldg(P.zt + k) < ml) {
-                if ((wetm >> cT & 1) && __ldg(P.zt + (k - 1)) < ml) mlm |= 1u << cT;
-                if ((wetm >> cB & 1) && __ldg(P.zt + (k + 1)) < ml) mlm |= 1u << cB;
+            const double z0 = __ldg(P.zt + k), zT = __ldg(P.zt + (hasT ? k - 1 : k)), zB = __ldg(P.zt + (hasB ? k + 1 : k));
+            if (z0 < ml) {
+                if ((wetm >> cT & 1) && zT < ml) mlm |= 1u << cT;
+                if ((wetm >> cB & 1) && zB < ml) mlm |= 1u << cB;
             }
         }
         // patterns (bit cC = diagonal)
@@ -343,7 +363,7 @@ __global__ void __launch_bounds__(TILE, 3) k_fused_v2(const V2Params P) {
                             if (r[d] < r[c]) lm |= 1u << d;
                             if (r[d] == r[c] && (present >> c & 1)) generic = true;
                         }
-                    lower[c] = lm;
+                    lowpack |= (u64)lm << (7 * c);
                 }
             }
         }
@@ -354,13 +374,21 @@ __global__ void __launch_bounds__(TILE, 3) k_fused_v2(const V2Params P) {
             cnt[3] = __popc(m_ml);
             cnt[4] = __popc(m_dp);
         } else {
-            cnt[0] = distinct_rows(m_T, r);
-            cnt[1] = distinct_rows(m_adv, r);
-            cnt[2] = distinct_rows(m_kh, r);
-            cnt[3] = distinct_rows(m_ml, r);
-            cnt[4] = distinct_rows(m_dp, r);
+            int g_r[7];   // local copy: distinct_rows indexes dynamically
+#pragma unroll
+            for (int c = 0; c < 7; ++c) g_r[c] = r[c];
+            cnt[0] = distinct_rows(m_T, g_r);
+            cnt[1] = distinct_rows(m_adv, g_r);
+            cnt[2] = distinct_rows(m_kh, g_r);
+            cnt[3] = distinct_rows(m_ml, g_r);
+            cnt[4] = distinct_rows(m_dp, g_r);
         }
     }
+    // position of candidate c inside a column whose pattern is m: number of present candidates of smaller rank
+    auto pos_of = [&](unsigned m, int c) -> int {
+        const unsigned lm = natural ? ((1u << c) - 1u) : (unsigned)((lowpack >> (7 * c)) & 0x7full);
+        return __popc(m & lm);
+    };
 
     // ================= tile scan + decoupled look-back =================
     u64 packed = 0;
@@ -381,125 +409,144 @@ __global__ void __launch_bounds__(TILE, 3) k_fused_v2(const V2Params P) {
         if (q < wid) wbase += sw;
         total += sw;
     }
-    const u64 excl_packed = wbase + incl - packed;
+    const u64 excl_packed = wbase + incl - packed;   // in-tile exclusive offsets of this column, 12 bits each
     if (tid < 5) {
         const u64 agg = (total >> (12 * tid)) & 0xfffull;
         s_agg[tid] = agg;
         st_vol(P.tile_state + (size_t)tile * 8 + tid, (tile == 0 ? ST_PRE : ST_AGG) | agg);
     }
     __syncthreads();
-    if (wid < 5) {
-        const int m = wid;
-        u64 excl = 0;
-        if (tile > 0) {
-            int look = tile - 1;
-            while (true) {
-                const int t = look - lane;
-                u64 wv = ST_PRE;
-                if (t >= 0) {
-                    do {
-                        wv = ld_vol(P.tile_state + (size_t)t * 8 + m);
-                    } while ((wv >> 62) == 0);
+    if (wid < (NW < 5 ? NW : 5)) {   // one warp per counter; the other warps go straight to phase 1
+        for (int m = wid; m < 5; m += NW) {
+            u64 excl = 0;
+            if (tile > 0) {
+                int look = tile - 1;
+                while (true) {
+                    const int t = look - lane;
+                    u64 wv = ST_PRE;
+                    if (t >= 0) {
+                        do {
+                            wv = ld_vol(P.tile_state + (size_t)t * 8 + m);
+                        } while ((wv >> 62) == 0);
+                    }
+                    const u64 val = wv & ST_MASK;
+                    const unsigned pm = __ballot_sync(0xffffffffu, (wv >> 62) == 2);
+                    if (pm) {
+                        const int first = __ffs(pm) - 1;
+                        excl += warp_sum64(lane <= first ? val : 0ull);
+                        break;
+                    }
+                    excl += warp_sum64(val);
+                    look -= 32;
                 }
-                const u64 val = wv & ST_MASK;
-                const unsigned pm = __ballot_sync(0xffffffffu, (wv >> 62) == 2);
-                if (pm) {
-                    const int first = __ffs(pm) - 1;
-                    excl += warp_sum64(lane <= first ? val : 0ull);
-                    break;
-                }
-                excl += warp_sum64(val);
-                look -= 32;
+                if (lane == 0) st_vol(P.tile_state + (size_t)tile * 8 + m, ST_PRE | (excl + s_agg[m]));
             }
-            if (lane == 0) st_vol(P.tile_state + (size_t)tile * 8 + m, ST_PRE | (excl + s_agg[m]));
+            if (lane == 0) s_excl[m] = excl;
         }
-        if (lane == 0) s_excl[m] = excl;
-    }
-    __syncthreads();
-    if (tile == P.ntiles - 1 && tid < 5) {
-        const u64 nnz = s_excl[tid] + s_agg[tid];
-        P.flags->nnz[tid] = nnz;
-        if (P.build >> tid & 1) P.colptr[tid][P.N] = (i64)nnz + P.base;
     }
 
-    // ================= phase 1: values, streamed per operator =================
+    // ================= phase 1: values, streamed per operator, staged in shared memory =================
     if (valid) {
-        i64 off[5];
+        int sidx[5];   // smem index of this column's first entry, per matrix
 #pragma unroll
-        for (int q = 0; q < 5; ++q) {
-            off[q] = (i64)(s_excl[q] + ((excl_packed >> (12 * q)) & 0xfffull));
-            if (P.build >> q & 1) P.colptr[q][rC] = off[q] + P.base;
-        }
+        for (int q = 0; q < 5; ++q) sidx[q] = ebase(q) * TILE + (int)((excl_packed >> (12 * q)) & 0xfffull);
         if (generic) {
-            generic_full(P, L, i, j, k, Lc, r, wetm, fold, act, pmag, mlm, off, &errbits);
+            // copies: only these escape to the out-of-line routine, so Lc/r/pmag stay in registers
+            int g_Lc[7], g_r[7], g_s[5];
+            double g_p[7];
+            unsigned g_err = 0;
+#pragma unroll
+            for (int c = 0; c < 7; ++c) {
+                g_Lc[c] = Lc[c];
+                g_r[c] = r[c];
+                g_p[c] = pmag[c];
+            }
+#pragma unroll
+            for (int q = 0; q < 5; ++q) g_s[q] = sidx[q];
+            generic_full(P, L, k, g_Lc, g_r, wetm, fold, act, g_p, mlm, g_s, srow, sval, &g_err);
+            errbits |= g_err;
             atomicAdd(&P.flags->generic_columns, 1);
         } else {
-            const int PP = g.P, p2 = L - k * PP;
-            const double vC = __ldg(P.v3D + L);
-            double vn[7];
+            const int PP = g.P;
+            // ---- ONE batch of independent loads.  Every index is clamped to a valid cell, so the loads
+            // are unconditional and all in flight together: one memory round trip for the whole column
+            // instead of one per direction (the first version serialised ~12 of them).
+            double vn[7], rh[7];
 #pragma unroll
-            for (int c = 0; c < 7; ++c) vn[c] = (c == cC) ? vC : __ldg(P.v3D + Lc[c]);   // clamped index: always safe
+            for (int c = 0; c < 7; ++c) {
+                vn[c] = __ldg(P.v3D + Lc[c]);
+                rh[c] = RHO3D ? __ldg(P.rho3d + Lc[c]) : P.rho;
+            }
+            const double vC = vn[cC];
+            // horizontal neighbours S,W,E,N: thickness, own/opposite edge length, own/opposite centre distance
+            double thn[7], e_own[7], e_opp[7], d_own[7], d_opp[7];
+#pragma unroll
+            for (int c = 0; c < 7; ++c) {
+                thn[c] = e_own[c] = e_opp[c] = d_own[c] = d_opp[c] = 0.0;
+                if (!(HMASK >> c & 1)) continue;
+                const int own = c == cW ? OTMB_DIR_WEST : c == cE ? OTMB_DIR_EAST : c == cS ? OTMB_DIR_SOUTH : OTMB_DIR_NORTH;
+                const int opp = c == cW ? OTMB_DIR_EAST : c == cE ? OTMB_DIR_WEST : c == cS ? OTMB_DIR_NORTH
+                                                                                  : (fold ? OTMB_DIR_NORTH : OTMB_DIR_SOUTH);
+                const int q2 = Lc[c] - k * PP;
+                thn[c] = __ldg(P.thk + Lc[c]);
+                e_own[c] = __ldg(P.edge + own * PP + p2);
+                e_opp[c] = __ldg(P.edge + opp * PP + q2);
+                d_own[c] = __ldg(P.dnbr + own * PP + p2);
+                d_opp[c] = __ldg(P.dnbr + opp * PP + q2);
+            }
+            const double thC = __ldg(P.thk + L);
+            const double area = __ldg(P.area2D + p2), ztC = __ldg(P.zt + k);
+            const double ztT = __ldg(P.zt + (k > 0 ? k - 1 : k)), ztB = __ldg(P.zt + (k < g.nz - 1 ? k + 1 : k));
             double Tv[7];
 #pragma unroll
             for (int c = 0; c < 7; ++c) Tv[c] = 0.0;
 
             // ---- Tadv (:193-204)
             if (m_adv) {
-                const double rhoC = RHO3D ? __ldg(P.rho3d + L) : P.rho;
+                const double rhoC = rh[cC];
                 if (RHO3D && isnan(rhoC)) errbits |= 64u;
-                i64* rv = P.rowval[1] + off[1];
-                double* nv = P.nzval[1] + off[1];
-                double dc[7];
-                bool bad = false;
+                double dsum = 0.0;
+                bool first = true, bad = false;
 #pragma unroll
                 for (int c = 0; c < 7; ++c) {
-                    dc[c] = 0.0;
                     if (c == cC || !(act >> c & 1)) continue;
-                    const double rhoi = RHO3D ? __ldg(P.rho3d + Lc[c]) : P.rho;
+                    const double rhoi = rh[c];
                     const double rb = (rhoi + rhoC) / 2;
                     const double a = -pmag[c] / (rb * vn[c]);
-                    dc[c] = pmag[c] / (rb * vC);
-                    bad |= isnan(a) || isnan(dc[c]);
-                    const int pos = __popc(m_adv & lower[c]);
-                    rv[pos] = (i64)r[c] + P.base;
-                    nv[pos] = a;
+                    const double d = pmag[c] / (rb * vC);
+                    bad |= isnan(a) || isnan(d);
+                    const int s = sidx[1] + pos_of(m_adv, c);
+                    srow[s] = r[c];
+                    sval[s] = a;
                     Tv[c] = a;
+                    // diagonal: contributions in ascending emitter rank; candidate order IS rank order when natural
+                    dsum = first ? d : dsum + d;
+                    first = false;
                 }
-                if (bad) errbits |= 2u;
-                // diagonal: contributions in ascending emitter rank (sparse! keeps the first, adds the rest)
-                double dsum = 0.0;
-                bool first = true;
-                if (natural) {
-#pragma unroll
-                    for (int c = 0; c < 7; ++c)
-                        if (c != cC && (act >> c & 1)) {
-                            dsum = first ? dc[c] : dsum + dc[c];
-                            first = false;
-                        }
-                } else {
+                if (!natural) {   // seam / fold columns: redo the diagonal sum in true rank order
                     const unsigned present = wetm | (1u << cC);
+                    first = true;
                     for (int t = 0; t < 7; ++t) {
 #pragma unroll
                         for (int c = 0; c < 7; ++c)
-                            if (c != cC && (act >> c & 1) && __popc(present & lower[c]) == t) {
-                                dsum = first ? dc[c] : dsum + dc[c];
+                            if (c != cC && (act >> c & 1) && pos_of(present, c) == t) {
+                                const double d = pmag[c] / (((rh[c] + rhoC) / 2) * vC);
+                                dsum = first ? d : dsum + d;
                                 first = false;
                             }
                     }
                 }
-                const int pos = __popc(m_adv & lower[cC]);
-                rv[pos] = (i64)rC + P.base;
-                nv[pos] = dsum;
+                if (bad) errbits |= 2u;
+                const int s = sidx[1] + pos_of(m_adv, cC);
+                srow[s] = rC;
+                sval[s] = dsum;
                 Tv[cC] = dsum;
             } else if (RHO3D && (P.build & 2)) {
-                if (isnan(__ldg(P.rho3d + L))) errbits |= 64u;
+                if (isnan(rh[cC])) errbits |= 64u;
             }
 
             // ---- TκH (:348-415, :426-435); own slots in emit order W,E,S,N
             if (m_kh) {
-                const double thC = __ldg(P.thk + L);
-                i64* rv = P.rowval[2] + off[2];
-                double* nv = P.nzval[2] + off[2];
                 double dsum = 0.0;
                 bool first = true, bad = false;
                 const int ord[4] = {cW, cE, cS, cN};
@@ -507,33 +554,28 @@ __global__ void __launch_bounds__(TILE, 3) k_fused_v2(const V2Params P) {
                 for (int q = 0; q < 4; ++q) {
                     const int c = ord[q];
                     if (!(wetm >> c & 1)) continue;
-                    const int own = c == cW ? OTMB_DIR_WEST : c == cE ? OTMB_DIR_EAST : c == cS ? OTMB_DIR_SOUTH : OTMB_DIR_NORTH;
-                    const int opp = c == cW ? OTMB_DIR_EAST : c == cE ? OTMB_DIR_WEST : c == cS ? OTMB_DIR_NORTH
-                                                                                      : (fold ? OTMB_DIR_NORTH : OTMB_DIR_SOUTH);
-                    const int q2 = Lc[c] - k * PP;
-                    const double a_own = thC * __ldg(P.edge + own * PP + p2);
-                    const double a_nbr = __ldg(P.thk + Lc[c]) * __ldg(P.edge + opp * PP + q2);
+                    const double a_own = thC * e_own[c];
+                    const double a_nbr = thn[c] * e_opp[c];
                     const double ka = P.kH * jl_min(a_own, a_nbr);
-                    const double ts = ka / (__ldg(P.dnbr + own * PP + p2) * vC);      // row 𝑗 seen from 𝑗
-                    const double tn = ka / (__ldg(P.dnbr + opp * PP + q2) * vn[c]);   // row 𝑖 seen from 𝑖
+                    const double ts = ka / (d_own[c] * vC);       // row 𝑗 seen from 𝑗
+                    const double tn = ka / (d_opp[c] * vn[c]);    // row 𝑖 seen from 𝑖
                     bad |= isnan(ts) || isnan(tn);
                     dsum = first ? ts : dsum + ts;
                     first = false;
-                    const int pos = __popc(m_kh & lower[c]);
-                    rv[pos] = (i64)r[c] + P.base;
-                    nv[pos] = -tn;
+                    const int s = sidx[2] + pos_of(m_kh, c);
+                    srow[s] = r[c];
+                    sval[s] = -tn;
                     Tv[c] = Tv[c] + (-tn);
                 }
                 if (bad) errbits |= 4u;
-                const int pos = __popc(m_kh & lower[cC]);
-                rv[pos] = (i64)rC + P.base;
-                nv[pos] = dsum;
+                const int s = sidx[2] + pos_of(m_kh, cC);
+                srow[s] = rC;
+                sval[s] = dsum;
                 Tv[cC] = Tv[cC] + dsum;
             }
 
             // ---- TκVML and TκVdeep (:450-477); own slots in emit order B, T
             if (m_dp | m_ml) {
-                const double area = __ldg(P.area2D + p2), ztC = __ldg(P.zt + k);
                 double mls = 0.0, dps = 0.0, mlT = 0.0, mlB = 0.0, dpT = 0.0, dpB = 0.0;
                 bool firstm = true, firstd = true, badm = false, badd = false;
                 const int ord[2] = {cB, cT};
@@ -541,8 +583,7 @@ __global__ void __launch_bounds__(TILE, 3) k_fused_v2(const V2Params P) {
                 for (int q = 0; q < 2; ++q) {
                     const int c = ord[q];
                     if (!(wetm >> c & 1)) continue;
-                    const int kc = c == cT ? k - 1 : k + 1;
-                    const double d = fabs(ztC - __ldg(P.zt + kc));
+                    const double d = fabs(ztC - (c == cT ? ztT : ztB));
                     const double qs = d * vC, qn = d * vn[c];
                     if (m_dp) {
                         const double ka = P.kVdeep * area;
@@ -565,42 +606,63 @@ __global__ void __launch_bounds__(TILE, 3) k_fused_v2(const V2Params P) {
                 if (badd) errbits |= 16u;
                 // T folds TκVML before TκVdeep
                 if (m_ml) {
-                    i64* rv = P.rowval[3] + off[3];
-                    double* nv = P.nzval[3] + off[3];
-                    if (mlm >> cT & 1) { const int pos = __popc(m_ml & lower[cT]); rv[pos] = (i64)r[cT] + P.base; nv[pos] = mlT; Tv[cT] = Tv[cT] + mlT; }
-                    if (mlm >> cB & 1) { const int pos = __popc(m_ml & lower[cB]); rv[pos] = (i64)r[cB] + P.base; nv[pos] = mlB; Tv[cB] = Tv[cB] + mlB; }
-                    const int pos = __popc(m_ml & lower[cC]);
-                    rv[pos] = (i64)rC + P.base;
-                    nv[pos] = mls;
+                    if (mlm >> cT & 1) { const int s = sidx[3] + pos_of(m_ml, cT); srow[s] = r[cT]; sval[s] = mlT; Tv[cT] = Tv[cT] + mlT; }
+                    if (mlm >> cB & 1) { const int s = sidx[3] + pos_of(m_ml, cB); srow[s] = r[cB]; sval[s] = mlB; Tv[cB] = Tv[cB] + mlB; }
+                    const int s = sidx[3] + pos_of(m_ml, cC);
+                    srow[s] = rC;
+                    sval[s] = mls;
                     Tv[cC] = Tv[cC] + mls;
                 }
                 if (m_dp) {
-                    i64* rv = P.rowval[4] + off[4];
-                    double* nv = P.nzval[4] + off[4];
-                    if (wetm >> cT & 1) { const int pos = __popc(m_dp & lower[cT]); rv[pos] = (i64)r[cT] + P.base; nv[pos] = dpT; Tv[cT] = Tv[cT] + dpT; }
-                    if (wetm >> cB & 1) { const int pos = __popc(m_dp & lower[cB]); rv[pos] = (i64)r[cB] + P.base; nv[pos] = dpB; Tv[cB] = Tv[cB] + dpB; }
-                    const int pos = __popc(m_dp & lower[cC]);
-                    rv[pos] = (i64)rC + P.base;
-                    nv[pos] = dps;
+                    if (wetm >> cT & 1) { const int s = sidx[4] + pos_of(m_dp, cT); srow[s] = r[cT]; sval[s] = dpT; Tv[cT] = Tv[cT] + dpT; }
+                    if (wetm >> cB & 1) { const int s = sidx[4] + pos_of(m_dp, cB); srow[s] = r[cB]; sval[s] = dpB; Tv[cB] = Tv[cB] + dpB; }
+                    const int s = sidx[4] + pos_of(m_dp, cC);
+                    srow[s] = rC;
+                    sval[s] = dps;
                     Tv[cC] = Tv[cC] + dps;
                 }
             }
 
             // ---- T: union pattern; exact zeros are flagged and removed by the compaction pass
             if (m_T) {
-                i64* rv = P.rowval[0] + off[0];
-                double* nv = P.nzval[0] + off[0];
                 bool zero = false;
 #pragma unroll
                 for (int c = 0; c < 7; ++c) {
                     if (!(m_T >> c & 1)) continue;
-                    const int pos = __popc(m_T & lower[c]);
-                    rv[pos] = (i64)r[c] + P.base;
-                    nv[pos] = Tv[c];
+                    const int s = sidx[0] + pos_of(m_T, c);
+                    srow[s] = r[c];
+                    sval[s] = Tv[c];
                     zero |= (Tv[c] == 0.0);
                 }
                 if (zero) errbits |= 32u;
             }
+        }
+    }
+    __syncthreads();   // staged tile complete, s_excl published
+
+    // ================= phase 2: coalesced flush =================
+    if (valid) {
+#pragma unroll
+        for (int q = 0; q < 5; ++q)
+            if (P.build >> q & 1)
+                P.colptr[q][rC] = (i64)(s_excl[q] + ((excl_packed >> (12 * q)) & 0xfffull)) + P.base;
+    }
+    if (tile == P.ntiles - 1 && tid < 5) {
+        const u64 nnz = s_excl[tid] + s_agg[tid];
+        P.flags->nnz[tid] = nnz;
+        if (P.build >> tid & 1) P.colptr[tid][P.N] = (i64)nnz + P.base;
+    }
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        if (!(P.build >> q & 1)) continue;
+        const int n = (int)s_agg[q];
+        i64* __restrict__ rv = P.rowval[q] + s_excl[q];
+        double* __restrict__ nv = P.nzval[q] + s_excl[q];
+        const int* sr = srow + ebase(q) * TILE;
+        const double* sv = sval + ebase(q) * TILE;
+        for (int idx = tid; idx < n; idx += TILE) {
+            rv[idx] = (i64)sr[idx] + P.base;
+            nv[idx] = sv[idx];
         }
     }
 
@@ -620,17 +682,17 @@ __global__ void __launch_bounds__(TILE, 3) k_fused_v2(const V2Params P) {
 // ---------------------------------------------------------------------------------------
 // zero-dropping compaction of one CSC matrix (only runs when the flag says a zero was stored)
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_count_nonzero(const i64* __restrict__ colptr, const double* __restrict__ nz, i64 n,
+__global__ void __launch_bounds__(256) k_count_nonzero(const i64* __restrict__ colptr, const double* __restrict__ nzv, i64 n,
                                                        int base, uint32_t* __restrict__ cnt) {
     const i64 col = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (col > n) return;
     uint32_t m = 0;
     if (col < n)
-        for (i64 p = colptr[col] - base; p < colptr[col + 1] - base; ++p) m += (nz[p] != 0.0);
+        for (i64 p = colptr[col] - base; p < colptr[col + 1] - base; ++p) m += (nzv[p] != 0.0);
     cnt[col] = m;
 }
 __global__ void __launch_bounds__(256) k_copy_nonzero(const i64* __restrict__ colptr, const i64* __restrict__ rv,
-                                                      const double* __restrict__ nz, i64 n, int base,
+                                                      const double* __restrict__ nzv, i64 n, int base,
                                                       const i64* __restrict__ ncp0, i64* __restrict__ ncp,
                                                       i64* __restrict__ nrv, double* __restrict__ nnz_) {
     const i64 col = (i64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -639,9 +701,9 @@ __global__ void __launch_bounds__(256) k_copy_nonzero(const i64* __restrict__ co
     ncp[col] = o + base;
     if (col == n) return;
     for (i64 p = colptr[col] - base; p < colptr[col + 1] - base; ++p)
-        if (nz[p] != 0.0) {
+        if (nzv[p] != 0.0) {
             nrv[o] = rv[p];
-            nnz_[o] = nz[p];
+            nnz_[o] = nzv[p];
             ++o;
         }
 }
@@ -653,6 +715,22 @@ FastDiv make_fastdiv(unsigned d) {
     f.shift = 32 + s;
     f.mul = ((1ull << f.shift) + d - 1) / d;
     return f;
+}
+
+template <bool RHO3D, int TILE, int MINB>
+int launch_v2(otmb_ctx* c, V2Params& P) {
+    const int ntiles = (int)((c->N + TILE - 1) / TILE);
+    P.ntiles = ntiles;
+    CU_TRY(c, c->tile_state.ensure((size_t)ntiles * 8 * sizeof(u64)));
+    P.tile_state = c->tile_state.as<u64>();
+    CU_TRY(c, cudaMemsetAsync(P.tile_state, 0, (size_t)ntiles * 8 * sizeof(u64), c->stream));
+    const size_t smem = (size_t)CAPSUM * TILE * (sizeof(double) + sizeof(int));
+    // per device (a process may hold one context per GPU); the call is cheap
+    CU_TRY(c, cudaFuncSetAttribute(k_fused_v2<RHO3D, TILE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_fused_v2<RHO3D, TILE, MINB><<<ntiles, TILE, smem, c->stream>>>(P);
+    LAUNCHED(c);
+    CU_TRY(c, cudaGetLastError());
+    return OTMB_OK;
 }
 
 }  // namespace
@@ -714,9 +792,7 @@ int otmb_fused_v2_build(otmb_ctx* c, const otmb_tm_params* prm, int build) {
     P.build = build;
     P.N = c->N;
     P.flags = c->flags.as<DevFlags>();
-    const int ntiles = (int)((c->N + TILE - 1) / TILE);
-    P.ntiles = ntiles;
-    const int cap_per_col[5] = {7, 7, 5, 3, 3};
+    const int cap_per_col[5] = {CAP0, CAP1, CAP2, CAP3, CAP4};
     for (int m = 0; m < 5; ++m) {
         P.colptr[m] = nullptr;
         P.rowval[m] = nullptr;
@@ -730,14 +806,9 @@ int otmb_fused_v2_build(otmb_ctx* c, const otmb_tm_params* prm, int build) {
         P.rowval[m] = c->rowval[m].as<i64>();
         P.nzval[m] = c->nzval[m].as<double>();
     }
-    CU_TRY(c, c->tile_state.ensure((size_t)ntiles * 8 * sizeof(u64)));
-    P.tile_state = c->tile_state.as<u64>();
-    CU_TRY(c, cudaMemsetAsync(P.tile_state, 0, (size_t)ntiles * 8 * sizeof(u64), c->stream));
-    if (c->have_rho3d)
-        k_fused_v2<true><<<ntiles, TILE, 0, c->stream>>>(P);
-    else
-        k_fused_v2<false><<<ntiles, TILE, 0, c->stream>>>(P);
-    LAUNCHED(c);
-    CU_TRY(c, cudaGetLastError());
-    return OTMB_OK;
+    static const int variant = getenv("OTMB_V2_VARIANT") ? atoi(getenv("OTMB_V2_VARIANT")) : 0;
+    if (c->have_rho3d) return launch_v2<true, 256, 2>(c, P);
+    if (variant == 1) return launch_v2<false, 128, 4>(c, P);
+    if (variant == 2) return launch_v2<false, 128, 5>(c, P);
+    return launch_v2<false, 256, 2>(c, P);
 }
