@@ -2,20 +2,29 @@
 //
 // Same mathematics and ordering rules as fused.cu (read its header first: gather form, emit
 // order, generic branch for coincident neighbours); what changes is the schedule, driven by the
-// ncu profiles under profiles/ (first version: 19 % of executed instructions in the look-back
-// spin, IPC 0.2, 128 registers; second: L1/LSU-bound on scattered 8-byte stores, 2.2x DRAM write
-// amplification):
+// ncu profiles under profiles/ (v1: 19 % of executed instructions in the look-back spin, IPC 0.2,
+// 128 registers; v2a/b: L1/LSU-bound on scattered 8-byte stores and spill traffic; v2d: latency
+// chain per tile, 85 % integer/control instructions):
 //   * threads map to wet cells through the compacted Lwet list (no idle dry lanes; a tile of
 //     TILE consecutive wet cells owns a contiguous slice of every output array);
 //   * phase 0 derives the sparsity PATTERN of all five matrices from cheap data only (wet bits,
 //     sign of the six face fluxes, mixed-layer test), so the tile aggregate is published a few
 //     hundred cycles after the tile starts and the decoupled look-back never waits on anybody's
 //     floating-point work;
-//   * phase 1 streams operator by operator (Tadv, TκH, TκVML/TκVdeep), each with one batch of
-//     independent loads, folds the entries into the running
-//     T = ((Tadv + TκH) + TκVML) + TκVdeep accumulators and stages (row, value) pairs of the
-//     whole tile in shared memory at their final in-tile position;
-//   * phase 2 flushes the staged tile to the five CSC arrays with fully coalesced stores.
+//   * every load of a column is unconditional (indices clamped to a valid cell) and issued in two
+//     batches (pattern inputs, value inputs): two memory round trips per column, not one per
+//     direction;
+//   * phase 1 computes operator by operator (Tadv, TκH, TκVML/TκVdeep), folds the entries into the
+//     running T = ((Tadv + TκH) + TκVML) + TκVdeep accumulators and stages (row, value) pairs of
+//     the whole tile in shared memory at their final in-tile position;
+//   * phase 2 flushes the staged tile to the five CSC arrays with coalesced 16-byte stores.
+//
+// Row order inside a column.  Wet rank is monotone in the linear index, so the candidates always
+// sort as  [top] [south] {west, self, east, north-if-on-the-fold} [north-if-regular] [bottom]:
+// only the members of the braces (all in grid row j) can permute (periodic seam, tripolar fold),
+// and only they can coincide.  Six integer comparisons settle the order; a coincidence sends the
+// column to the generic sort-and-combine branch.
+//
 // The pattern of T is the union of the four patterns; sparse `+` additionally drops results that
 // are exactly zero (/root/reference/src/matrixbuilding.jl:147).  Those are counted by a flag and,
 // only when any occurred (e.g. κ = 0), a compaction pass (k_count_nonzero / k_copy_nonzero)
@@ -30,8 +39,9 @@ constexpr u64 ST_AGG = 1ull << 62, ST_PRE = 2ull << 62, ST_MASK = (1ull << 62) -
 
 enum { cT = 0, cS = 1, cW = 2, cC = 3, cE = 4, cN = 5, cB = 6 };
 enum { sW = 0, sE = 1, sS = 2, sN = 3, sB = 4, sT = 5 };  // emit-order slots W,E,S,N,B,T
-constexpr unsigned HMASK = (1u << cS) | (1u << cW) | (1u << cE) | (1u << cN);
-constexpr unsigned VMASK = (1u << cT) | (1u << cB);
+constexpr unsigned bT = 1u << cT, bS = 1u << cS, bW = 1u << cW, bC = 1u << cC, bE = 1u << cE, bN = 1u << cN, bB = 1u << cB;
+constexpr unsigned HMASK = bS | bW | bE | bN;
+constexpr unsigned VMASK = bT | bB;
 // staging capacity per column and matrix (T, Tadv, TκH, TκVML, TκVdeep) and their prefix
 constexpr int CAP0 = 7, CAP1 = 7, CAP2 = 5, CAP3 = 3, CAP4 = 3, CAPSUM = 25;
 __host__ __device__ constexpr int ebase(int q) {
@@ -224,9 +234,19 @@ __device__ __noinline__ void generic_full(const V2Params& P, int L, int k, const
     }
 }
 
+// compare-exchange of (rank, value) pairs, ascending rank
+__device__ __forceinline__ void cex(int& ka, double& va, int& kb, double& vb) {
+    const bool sw = kb < ka;
+    const int k0 = sw ? kb : ka, k1 = sw ? ka : kb;
+    const double v0 = sw ? vb : va, v1 = sw ? va : vb;
+    ka = k0; kb = k1; va = v0; vb = v1;
+}
+
 // ---------------------------------------------------------------------------------------
 template <bool RHO3D, int TILE, int MINB>
-__global__ void __launch_bounds__(TILE, MINB) k_fused_v2(const V2Params P) {
+// __grid_constant__: the generic branch takes the address of P; without it every thread would copy
+// the whole parameter block to local memory at kernel entry (measured: 1.2 GB of local stores)
+__global__ void __launch_bounds__(TILE, MINB) k_fused_v2(const __grid_constant__ V2Params P) {
     constexpr int NW = TILE / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* sval = reinterpret_cast<double*>(smem_raw);            // CAPSUM*TILE doubles
@@ -234,12 +254,11 @@ __global__ void __launch_bounds__(TILE, MINB) k_fused_v2(const V2Params P) {
     __shared__ u64 s_warp[NW];
     __shared__ u64 s_excl[5];
     __shared__ u64 s_agg[5];
-    __shared__ int s_tile;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) s_tile = (int)atomicAdd(&P.flags->ticket, 1ull);
-    __syncthreads();
-    const int tile = s_tile;
+    // tile id = block id: blocks are dispatched in index order, so every tile this one waits on in
+    // the look-back is already resident or finished (the same assumption CUB's scan makes)
+    const int tile = blockIdx.x;
     const GridDims g = P.g;
     const i64 w64 = (i64)tile * TILE + tid;
     const bool valid = w64 < P.N;
@@ -250,10 +269,10 @@ __global__ void __launch_bounds__(TILE, MINB) k_fused_v2(const V2Params P) {
     int L = 0, k = 0, p2 = 0;
     int Lc[7];
     int r[7];
+    unsigned low[7];   // low[c]: present candidates with a smaller wet rank than c
     unsigned wetm = 0, act = 0, mlm = 0;   // wet neighbours; neighbours whose flux enters this column; ML pairs
     double pmag[7];
-    u64 lowpack = 0;   // non-natural order only: 7-bit "candidates with a smaller rank" mask per candidate
-    bool fold = false, generic = false, natural = true;
+    bool fold = false, generic = false, irregular = false;
     unsigned m_T = 0, m_adv = 0, m_kh = 0, m_ml = 0, m_dp = 0;
     unsigned errbits = 0;  // 1 dry nbr, 2 nan adv, 4 nan kh, 8 nan ml, 16 nan deep, 32 zero dropped, 64 nan rho
     int cnt[5] = {0, 0, 0, 0, 0};
@@ -262,6 +281,7 @@ __global__ void __launch_bounds__(TILE, MINB) k_fused_v2(const V2Params P) {
         Lc[c] = 0;
         r[c] = 0x7fffffff;
         pmag[c] = 0.0;
+        low[c] = 0;
     }
     if (valid) {
         L = __ldg(P.lwet + rC);
@@ -272,6 +292,7 @@ __global__ void __launch_bounds__(TILE, MINB) k_fused_v2(const V2Params P) {
         fold = (j == g.ny - 1) && (g.topo == OTMB_TOPO_TRIPOLAR);
         const bool hasT = k > 0, hasB = k < g.nz - 1, hasS = j > 0, hasN = (j < g.ny - 1) || fold;
         const bool seamW = i == 0, seamE = i == g.nx - 1;
+        irregular = seamW || seamE || fold;
         Lc[cC] = L;
         Lc[cT] = hasT ? L - g.P : L;
         Lc[cB] = hasB ? L + g.P : L;
@@ -281,15 +302,30 @@ __global__ void __launch_bounds__(TILE, MINB) k_fused_v2(const V2Params P) {
         Lc[cN] = (j < g.ny - 1) ? L + g.nx : (fold ? k * g.P + (g.ny - 1) * g.nx + (g.nx - 1 - i) : L);
         r[cC] = rC;
         const bool ex[7] = {hasT, hasS, true, true, true, hasN, hasB};
-        // wet bits and ranks: mask word + word prefix of every candidate, loaded unconditionally in one
-        // batch (L1/L2 resident, 12 bytes per 64 cells); W/E ranks follow from linear adjacency off the seam
+        // ---- batch 1 of loads (all unconditional): mask word + word prefix of every candidate
+        // (L1/L2 resident, 12 bytes per 64 cells), the six face fluxes, the mixed-layer inputs
+        u64 word[7];
+        int pre[7];
 #pragma unroll
         for (int c = 0; c < 7; ++c) {
             if (c == cC) continue;
-            const u64 word = __ldg(P.mask + (Lc[c] >> 6));
-            const int pre = (int)__ldg(P.wpre + (Lc[c] >> 6));
-            const bool wet = ex[c] && ((word >> (Lc[c] & 63)) & 1ull);
-            int rk = pre + __popcll(word & ((1ull << (Lc[c] & 63)) - 1ull));
+            word[c] = __ldg(P.mask + (Lc[c] >> 6));
+            pre[c] = (int)__ldg(P.wpre + (Lc[c] >> 6));
+        }
+        const double xT = __ldg(P.pb + Lc[cT]);                       // emitter above: its Bottom slot, max
+        const double xS = __ldg(P.pn + Lc[cS]);                       // its North slot, min
+        const double xW = __ldg(P.pe + Lc[cW]);                       // its East slot, min
+        const double xE = __ldg(P.pw + Lc[cE]);                       // its West slot, max
+        const double xN = __ldg((fold ? P.pn : P.ps) + Lc[cN]);       // its South slot (max), or North on the fold (min)
+        const double xB = __ldg(P.pt + Lc[cB]);                       // emitter below: its Top slot, min
+        const double ml = __ldg(P.mlotst + p2);
+        const double z0 = __ldg(P.zt + k), zT = __ldg(P.zt + (hasT ? k - 1 : k)), zB = __ldg(P.zt + (hasB ? k + 1 : k));
+        // wet bits and ranks; W/E ranks follow from linear adjacency off the seam
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+            if (c == cC) continue;
+            const bool wet = ex[c] && ((word[c] >> (Lc[c] & 63)) & 1ull);
+            int rk = pre[c] + __popcll(word[c] & ((1ull << (Lc[c] & 63)) - 1ull));
             if (c == cW && !seamW) rk = rC - 1;
             if (c == cE && !seamE) rk = rC + 1;
             if (wet) {
@@ -297,74 +333,69 @@ __global__ void __launch_bounds__(TILE, MINB) k_fused_v2(const V2Params P) {
                 r[c] = rk;
             }
         }
-
         // face flux each neighbour carries through the face it shares with this cell (the value the
-        // reference reads at the neighbour, :244-295); loads are unconditional (index clamped to L)
+        // reference reads at the neighbour, :244-295)
         {
-            const double xT = __ldg(P.pb + Lc[cT]);                       // emitter above: its Bottom slot, max
-            const double xS = __ldg(P.pn + Lc[cS]);                       // its North slot, min
-            const double xW = __ldg(P.pe + Lc[cW]);                       // its East slot, min
-            const double xE = __ldg(P.pw + Lc[cE]);                       // its West slot, max
-            const double xN = __ldg((fold ? P.pn : P.ps) + Lc[cN]);       // its South slot (max), or North on the fold (min)
-            const double xB = __ldg(P.pt + Lc[cB]);                       // emitter below: its Top slot, min
             const double fT = upflux(xT, true, up), fS = upflux(xS, false, up), fW = upflux(xW, false, up),
                          fE = upflux(xE, true, up), fN = upflux(xN, !fold, up), fB = upflux(xB, false, up);
-            if ((wetm >> cT & 1) && nz(fT)) { act |= 1u << cT; pmag[cT] = fT; }
-            if ((wetm >> cS & 1) && nz(fS)) { act |= 1u << cS; pmag[cS] = -fS; }
-            if ((wetm >> cW & 1) && nz(fW)) { act |= 1u << cW; pmag[cW] = -fW; }
-            if ((wetm >> cE & 1) && nz(fE)) { act |= 1u << cE; pmag[cE] = fE; }
-            if ((wetm >> cN & 1) && nz(fN)) { act |= 1u << cN; pmag[cN] = fold ? -fN : fN; }
-            if ((wetm >> cB & 1) && nz(fB)) { act |= 1u << cB; pmag[cB] = -fB; }
+            if ((wetm & bT) && nz(fT)) { act |= bT; pmag[cT] = fT; }
+            if ((wetm & bS) && nz(fS)) { act |= bS; pmag[cS] = -fS; }
+            if ((wetm & bW) && nz(fW)) { act |= bW; pmag[cW] = -fW; }
+            if ((wetm & bE) && nz(fE)) { act |= bE; pmag[cE] = fE; }
+            if ((wetm & bN) && nz(fN)) { act |= bN; pmag[cN] = fold ? -fN : fN; }
+            if ((wetm & bB) && nz(fB)) { act |= bB; pmag[cB] = -fB; }
         }
         // own faces that point at a dry or absent cell: the reference would push `missing` (:247-250)
         if (P.build & 2) {
             const unsigned dry = ~wetm;
             bool bad = false;
-            if (dry >> cW & 1) bad |= nz(upflux(__ldg(P.pw + L), true, up));
-            if (dry >> cE & 1) bad |= nz(upflux(__ldg(P.pe + L), false, up));
-            if (dry >> cS & 1) bad |= nz(upflux(__ldg(P.ps + L), true, up));
-            if (dry >> cN & 1) bad |= nz(upflux(__ldg(P.pn + L), false, up));
-            if (dry >> cB & 1) bad |= nz(upflux(__ldg(P.pb + L), true, up));
-            if ((dry >> cT & 1) && hasT) bad |= nz(upflux(__ldg(P.pt + L), false, up));
+            if (dry & bW) bad |= nz(upflux(__ldg(P.pw + L), true, up));
+            if (dry & bE) bad |= nz(upflux(__ldg(P.pe + L), false, up));
+            if (dry & bS) bad |= nz(upflux(__ldg(P.ps + L), true, up));
+            if (dry & bN) bad |= nz(upflux(__ldg(P.pn + L), false, up));
+            if (dry & bB) bad |= nz(upflux(__ldg(P.pb + L), true, up));
+            if ((dry & bT) && hasT) bad |= nz(upflux(__ldg(P.pt + L), false, up));
             if (bad) errbits |= 1u;
         }
         // mixed-layer mask Ω = zt[k] < mlotst[i,j] (false for NaN / missing), :85
-        if (P.build & 8) {
-            const double ml = __ldg(P.mlotst + p2);
-            const double z0 = __ldg(P.zt + k), zT = __ldg(P.zt + (hasT ? k - 1 : k)), zB = __ldg(P.zt + (hasB ? k + 1 : k));
-            if (z0 < ml) {
-                if ((wetm >> cT & 1) && zT < ml) mlm |= 1u << cT;
-                if ((wetm >> cB & 1) && zB < ml) mlm |= 1u << cB;
-            }
+        if ((P.build & 8) && z0 < ml) {
+            if ((wetm & bT) && zT < ml) mlm |= bT;
+            if ((wetm & bB) && zB < ml) mlm |= bB;
         }
         // patterns (bit cC = diagonal)
-        if (P.build & 2) m_adv = act ? (act | (1u << cC)) : 0u;
-        if (P.build & 4) m_kh = (wetm & HMASK) ? ((wetm & HMASK) | (1u << cC)) : 0u;
-        if (P.build & 8) m_ml = mlm ? (mlm | (1u << cC)) : 0u;
-        if (P.build & 16) m_dp = (wetm & VMASK) ? ((wetm & VMASK) | (1u << cC)) : 0u;
+        if (P.build & 2) m_adv = act ? (act | bC) : 0u;
+        if (P.build & 4) m_kh = (wetm & HMASK) ? ((wetm & HMASK) | bC) : 0u;
+        if (P.build & 8) m_ml = mlm ? (mlm | bC) : 0u;
+        if (P.build & 16) m_dp = (wetm & VMASK) ? ((wetm & VMASK) | bC) : 0u;
         if (P.build & 1) m_T = m_adv | m_kh | m_ml | m_dp;
-        // rank order of the candidates
+        // ---- row order: [T] [S] {W, C, E, N-on-fold} [N-regular] [B]; only the braces can permute
         {
-            int prev = -1;
-            const unsigned present = wetm | (1u << cC);
-#pragma unroll
-            for (int c = 0; c < 7; ++c)
-                if (present >> c & 1) {
-                    if (r[c] <= prev) natural = false;
-                    prev = r[c];
+            const unsigned present = wetm | bC;
+            const unsigned before = present & (bT | bS);
+            low[cT] = 0;
+            low[cS] = present & bT;
+            low[cB] = present & ~bB;
+            if (!irregular) {
+                low[cW] = before;
+                low[cC] = before | (present & bW);
+                low[cE] = before | (present & (bW | bC));
+                low[cN] = before | (present & (bW | bC | bE));
+            } else {
+                const bool pW = present & bW, pE = present & bE, pNf = fold && (present & bN);
+                unsigned lW = 0, lC = 0, lE = 0, lN = 0;
+                if (pW) { if (r[cW] < rC) lC |= bW; else lW |= bC; generic |= r[cW] == rC; }
+                if (pE) { if (r[cE] < rC) lC |= bE; else lE |= bC; generic |= r[cE] == rC; }
+                if (pW && pE) { if (r[cW] < r[cE]) lE |= bW; else lW |= bE; generic |= r[cW] == r[cE]; }
+                if (pNf) {
+                    if (r[cN] < rC) lC |= bN; else lN |= bC;
+                    generic |= r[cN] == rC;
+                    if (pW) { if (r[cN] < r[cW]) lW |= bN; else lN |= bW; generic |= r[cN] == r[cW]; }
+                    if (pE) { if (r[cN] < r[cE]) lE |= bN; else lN |= bE; generic |= r[cN] == r[cE]; }
                 }
-            if (!natural) {
-#pragma unroll
-                for (int c = 0; c < 7; ++c) {
-                    unsigned lm = 0;
-#pragma unroll
-                    for (int d = 0; d < 7; ++d)
-                        if (d != c && (present >> d & 1)) {
-                            if (r[d] < r[c]) lm |= 1u << d;
-                            if (r[d] == r[c] && (present >> c & 1)) generic = true;
-                        }
-                    lowpack |= (u64)lm << (7 * c);
-                }
+                low[cW] = before | lW;
+                low[cC] = before | lC;
+                low[cE] = before | lE;
+                low[cN] = fold ? (before | lN) : (before | (present & (bW | bC | bE)));
             }
         }
         if (!generic) {
@@ -384,11 +415,6 @@ __global__ void __launch_bounds__(TILE, MINB) k_fused_v2(const V2Params P) {
             cnt[4] = distinct_rows(m_dp, g_r);
         }
     }
-    // position of candidate c inside a column whose pattern is m: number of present candidates of smaller rank
-    auto pos_of = [&](unsigned m, int c) -> int {
-        const unsigned lm = natural ? ((1u << c) - 1u) : (unsigned)((lowpack >> (7 * c)) & 0x7full);
-        return __popc(m & lm);
-    };
 
     // ================= tile scan + decoupled look-back =================
     u64 packed = 0;
@@ -410,14 +436,13 @@ __global__ void __launch_bounds__(TILE, MINB) k_fused_v2(const V2Params P) {
         total += sw;
     }
     const u64 excl_packed = wbase + incl - packed;   // in-tile exclusive offsets of this column, 12 bits each
-    if (tid < 5) {
-        const u64 agg = (total >> (12 * tid)) & 0xfffull;
-        s_agg[tid] = agg;
-        st_vol(P.tile_state + (size_t)tile * 8 + tid, (tile == 0 ? ST_PRE : ST_AGG) | agg);
-    }
-    __syncthreads();
     if (wid < (NW < 5 ? NW : 5)) {   // one warp per counter; the other warps go straight to phase 1
         for (int m = wid; m < 5; m += NW) {
+            const u64 agg = (total >> (12 * m)) & 0xfffull;
+            if (lane == 0) {
+                s_agg[m] = agg;
+                st_vol(P.tile_state + (size_t)tile * 8 + m, (tile == 0 ? ST_PRE : ST_AGG) | agg);
+            }
             u64 excl = 0;
             if (tile > 0) {
                 int look = tile - 1;
@@ -439,13 +464,13 @@ __global__ void __launch_bounds__(TILE, MINB) k_fused_v2(const V2Params P) {
                     excl += warp_sum64(val);
                     look -= 32;
                 }
-                if (lane == 0) st_vol(P.tile_state + (size_t)tile * 8 + m, ST_PRE | (excl + s_agg[m]));
+                if (lane == 0) st_vol(P.tile_state + (size_t)tile * 8 + m, ST_PRE | (excl + agg));
             }
             if (lane == 0) s_excl[m] = excl;
         }
     }
 
-    // ================= phase 1: values, streamed per operator, staged in shared memory =================
+    // ================= phase 1: values, staged in shared memory =================
     if (valid) {
         int sidx[5];   // smem index of this column's first entry, per matrix
 #pragma unroll
@@ -468,9 +493,7 @@ __global__ void __launch_bounds__(TILE, MINB) k_fused_v2(const V2Params P) {
             atomicAdd(&P.flags->generic_columns, 1);
         } else {
             const int PP = g.P;
-            // ---- ONE batch of independent loads.  Every index is clamped to a valid cell, so the loads
-            // are unconditional and all in flight together: one memory round trip for the whole column
-            // instead of one per direction (the first version serialised ~12 of them).
+            // ---- batch 2 of loads: every value input of the column, unconditional, one round trip
             double vn[7], rh[7];
 #pragma unroll
             for (int c = 0; c < 7; ++c) {
@@ -505,39 +528,51 @@ __global__ void __launch_bounds__(TILE, MINB) k_fused_v2(const V2Params P) {
             if (m_adv) {
                 const double rhoC = rh[cC];
                 if (RHO3D && isnan(rhoC)) errbits |= 64u;
-                double dsum = 0.0;
-                bool first = true, bad = false;
+                double dd[7];
+                bool bad = false;
 #pragma unroll
                 for (int c = 0; c < 7; ++c) {
+                    dd[c] = 0.0;
                     if (c == cC || !(act >> c & 1)) continue;
-                    const double rhoi = rh[c];
-                    const double rb = (rhoi + rhoC) / 2;
+                    const double rb = (rh[c] + rhoC) / 2;
                     const double a = -pmag[c] / (rb * vn[c]);
-                    const double d = pmag[c] / (rb * vC);
-                    bad |= isnan(a) || isnan(d);
-                    const int s = sidx[1] + pos_of(m_adv, c);
+                    dd[c] = pmag[c] / (rb * vC);
+                    bad |= isnan(a) || isnan(dd[c]);
+                    const int s = sidx[1] + __popc(m_adv & low[c]);
                     srow[s] = r[c];
                     sval[s] = a;
                     Tv[c] = a;
-                    // diagonal: contributions in ascending emitter rank; candidate order IS rank order when natural
-                    dsum = first ? d : dsum + d;
-                    first = false;
-                }
-                if (!natural) {   // seam / fold columns: redo the diagonal sum in true rank order
-                    const unsigned present = wetm | (1u << cC);
-                    first = true;
-                    for (int t = 0; t < 7; ++t) {
-#pragma unroll
-                        for (int c = 0; c < 7; ++c)
-                            if (c != cC && (act >> c & 1) && pos_of(present, c) == t) {
-                                const double d = pmag[c] / (((rh[c] + rhoC) / 2) * vC);
-                                dsum = first ? d : dsum + d;
-                                first = false;
-                            }
-                    }
                 }
                 if (bad) errbits |= 2u;
-                const int s = sidx[1] + pos_of(m_adv, cC);
+                // diagonal: emitter contributions in ascending wet rank; sparse! keeps the first value and
+                // adds the later ones.  Order: T, S, the row group {W, E, N-on-fold} by rank, N-regular, B.
+                double dsum = 0.0;
+                bool first = true;
+                auto add = [&](bool on, double d) {
+                    if (on) {
+                        dsum = first ? d : dsum + d;
+                        first = false;
+                    }
+                };
+                add(act & bT, dd[cT]);
+                add(act & bS, dd[cS]);
+                if (!irregular) {
+                    add(act & bW, dd[cW]);
+                    add(act & bE, dd[cE]);
+                } else {
+                    int k0 = (act & bW) ? r[cW] : 0x7fffffff, k1 = (act & bE) ? r[cE] : 0x7fffffff,
+                        k2 = (fold && (act & bN)) ? r[cN] : 0x7fffffff;
+                    double v0 = dd[cW], v1 = dd[cE], v2 = dd[cN];
+                    cex(k0, v0, k1, v1);
+                    cex(k1, v1, k2, v2);
+                    cex(k0, v0, k1, v1);
+                    add(k0 != 0x7fffffff, v0);
+                    add(k1 != 0x7fffffff, v1);
+                    add(k2 != 0x7fffffff, v2);
+                }
+                add(!fold && (act & bN), dd[cN]);
+                add(act & bB, dd[cB]);
+                const int s = sidx[1] + __popc(m_adv & low[cC]);
                 srow[s] = rC;
                 sval[s] = dsum;
                 Tv[cC] = dsum;
@@ -562,13 +597,13 @@ __global__ void __launch_bounds__(TILE, MINB) k_fused_v2(const V2Params P) {
                     bad |= isnan(ts) || isnan(tn);
                     dsum = first ? ts : dsum + ts;
                     first = false;
-                    const int s = sidx[2] + pos_of(m_kh, c);
+                    const int s = sidx[2] + __popc(m_kh & low[c]);
                     srow[s] = r[c];
                     sval[s] = -tn;
                     Tv[c] = Tv[c] + (-tn);
                 }
                 if (bad) errbits |= 4u;
-                const int s = sidx[2] + pos_of(m_kh, cC);
+                const int s = sidx[2] + __popc(m_kh & low[cC]);
                 srow[s] = rC;
                 sval[s] = dsum;
                 Tv[cC] = Tv[cC] + dsum;
@@ -606,17 +641,17 @@ __global__ void __launch_bounds__(TILE, MINB) k_fused_v2(const V2Params P) {
                 if (badd) errbits |= 16u;
                 // T folds TκVML before TκVdeep
                 if (m_ml) {
-                    if (mlm >> cT & 1) { const int s = sidx[3] + pos_of(m_ml, cT); srow[s] = r[cT]; sval[s] = mlT; Tv[cT] = Tv[cT] + mlT; }
-                    if (mlm >> cB & 1) { const int s = sidx[3] + pos_of(m_ml, cB); srow[s] = r[cB]; sval[s] = mlB; Tv[cB] = Tv[cB] + mlB; }
-                    const int s = sidx[3] + pos_of(m_ml, cC);
+                    if (mlm & bT) { const int s = sidx[3] + __popc(m_ml & low[cT]); srow[s] = r[cT]; sval[s] = mlT; Tv[cT] = Tv[cT] + mlT; }
+                    if (mlm & bB) { const int s = sidx[3] + __popc(m_ml & low[cB]); srow[s] = r[cB]; sval[s] = mlB; Tv[cB] = Tv[cB] + mlB; }
+                    const int s = sidx[3] + __popc(m_ml & low[cC]);
                     srow[s] = rC;
                     sval[s] = mls;
                     Tv[cC] = Tv[cC] + mls;
                 }
                 if (m_dp) {
-                    if (wetm >> cT & 1) { const int s = sidx[4] + pos_of(m_dp, cT); srow[s] = r[cT]; sval[s] = dpT; Tv[cT] = Tv[cT] + dpT; }
-                    if (wetm >> cB & 1) { const int s = sidx[4] + pos_of(m_dp, cB); srow[s] = r[cB]; sval[s] = dpB; Tv[cB] = Tv[cB] + dpB; }
-                    const int s = sidx[4] + pos_of(m_dp, cC);
+                    if (wetm & bT) { const int s = sidx[4] + __popc(m_dp & low[cT]); srow[s] = r[cT]; sval[s] = dpT; Tv[cT] = Tv[cT] + dpT; }
+                    if (wetm & bB) { const int s = sidx[4] + __popc(m_dp & low[cB]); srow[s] = r[cB]; sval[s] = dpB; Tv[cB] = Tv[cB] + dpB; }
+                    const int s = sidx[4] + __popc(m_dp & low[cC]);
                     srow[s] = rC;
                     sval[s] = dps;
                     Tv[cC] = Tv[cC] + dps;
@@ -629,7 +664,7 @@ __global__ void __launch_bounds__(TILE, MINB) k_fused_v2(const V2Params P) {
 #pragma unroll
                 for (int c = 0; c < 7; ++c) {
                     if (!(m_T >> c & 1)) continue;
-                    const int s = sidx[0] + pos_of(m_T, c);
+                    const int s = sidx[0] + __popc(m_T & low[c]);
                     srow[s] = r[c];
                     sval[s] = Tv[c];
                     zero |= (Tv[c] == 0.0);
@@ -638,7 +673,7 @@ __global__ void __launch_bounds__(TILE, MINB) k_fused_v2(const V2Params P) {
             }
         }
     }
-    __syncthreads();   // staged tile complete, s_excl published
+    __syncthreads();   // staged tile complete, s_excl / s_agg published
 
     // ================= phase 2: coalesced flush =================
     if (valid) {
@@ -656,25 +691,45 @@ __global__ void __launch_bounds__(TILE, MINB) k_fused_v2(const V2Params P) {
     for (int q = 0; q < 5; ++q) {
         if (!(P.build >> q & 1)) continue;
         const int n = (int)s_agg[q];
-        i64* __restrict__ rv = P.rowval[q] + s_excl[q];
-        double* __restrict__ nv = P.nzval[q] + s_excl[q];
+        const u64 g0 = s_excl[q];
+        i64* __restrict__ rv = P.rowval[q] + g0;
+        double* __restrict__ nv = P.nzval[q] + g0;
         const int* sr = srow + ebase(q) * TILE;
         const double* sv = sval + ebase(q) * TILE;
-        for (int idx = tid; idx < n; idx += TILE) {
-            rv[idx] = (i64)sr[idx] + P.base;
-            nv[idx] = sv[idx];
+        const int head = (int)(g0 & 1ull) < n ? (int)(g0 & 1ull) : n;   // make the global side 16-byte aligned
+        if (tid == 0 && head) {
+            rv[0] = (i64)sr[0] + P.base;
+            nv[0] = sv[0];
+        }
+        const int npair = (n - head) >> 1;
+        for (int pidx = tid; pidx < npair; pidx += TILE) {
+            const int idx = head + 2 * pidx;
+            longlong2 rr;
+            rr.x = (i64)sr[idx] + P.base;
+            rr.y = (i64)sr[idx + 1] + P.base;
+            double2 vv;
+            vv.x = sv[idx];
+            vv.y = sv[idx + 1];
+            *reinterpret_cast<longlong2*>(rv + idx) = rr;
+            *reinterpret_cast<double2*>(nv + idx) = vv;
+        }
+        if (tid == 0 && ((n - head) & 1)) {
+            rv[n - 1] = (i64)sr[n - 1] + P.base;
+            nv[n - 1] = sv[n - 1];
         }
     }
 
     // ---- flags: one atomic per warp and kind
+    if (__any_sync(0xffffffffu, errbits != 0)) {
 #pragma unroll
-    for (int b = 0; b < 7; ++b) {
-        const unsigned any = __ballot_sync(0xffffffffu, (errbits >> b) & 1u);
-        if (lane == 0 && any) {
-            int* dst = b == 0 ? &P.flags->err_dry_neighbour : b == 1 ? &P.flags->nan_adv : b == 2 ? &P.flags->nan_kh
-                     : b == 3 ? &P.flags->nan_kvml : b == 4 ? &P.flags->nan_kvdeep : b == 5 ? &P.flags->zero_dropped
-                                                                                            : &P.flags->nan_rho;
-            atomicOr(dst, 1);
+        for (int b = 0; b < 7; ++b) {
+            const unsigned any = __ballot_sync(0xffffffffu, (errbits >> b) & 1u);
+            if (lane == 0 && any) {
+                int* dst = b == 0 ? &P.flags->err_dry_neighbour : b == 1 ? &P.flags->nan_adv : b == 2 ? &P.flags->nan_kh
+                         : b == 3 ? &P.flags->nan_kvml : b == 4 ? &P.flags->nan_kvdeep : b == 5 ? &P.flags->zero_dropped
+                                                                                                : &P.flags->nan_rho;
+                atomicOr(dst, 1);
+            }
         }
     }
 }
@@ -809,6 +864,6 @@ int otmb_fused_v2_build(otmb_ctx* c, const otmb_tm_params* prm, int build) {
     static const int variant = getenv("OTMB_V2_VARIANT") ? atoi(getenv("OTMB_V2_VARIANT")) : 0;
     if (c->have_rho3d) return launch_v2<true, 256, 2>(c, P);
     if (variant == 1) return launch_v2<false, 128, 4>(c, P);
-    if (variant == 2) return launch_v2<false, 128, 5>(c, P);
+    if (variant == 2) return launch_v2<false, 128, 3>(c, P);
     return launch_v2<false, 256, 2>(c, P);
 }
