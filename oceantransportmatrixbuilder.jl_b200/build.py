@@ -11,8 +11,8 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 INCLUDE = HERE.parent / "include"
 LIB = HERE / "libotmb.so"
-SOURCES = ["ctx.cu", "scan.cu", "geometry.cu", "faceflux.cu", "fused.cu", "fused_v2.cu", "coo.cu", "transport.cu", "redigm.cu"]
-HEADERS = ["common.cuh", "sphere.cuh"]
+SOURCES = ["ctx.cu", "scan.cu", "geometry.cu", "faceflux.cu", "fused.cu", "fused_v2.cu", "fused_v3.cu", "fused_v4.cu", "coo.cu", "transport.cu", "redigm.cu"]
+HEADERS = ["common.cuh", "sphere.cuh", "fused_generic.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

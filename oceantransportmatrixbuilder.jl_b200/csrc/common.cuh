@@ -64,7 +64,7 @@ struct otmb_ctx {
     bool have_grid = false, have_indices = false, have_metrics = false, have_phi = false, have_mlotst = false,
          have_rho3d = false, have_z3d = false, have_lonlat = false;
 
-    DevBuf v3D, mask, wcount, wpre, lwet, area2D, thk, Z3D, zt, edge, dnbr, dedge, lon, lat, lonv, latv, mlotst, rho3d;
+    DevBuf v3D, mask, wcount, wpre, lwet, rank3d, area2D, thk, Z3D, zt, edge, dnbr, dedge, lon, lat, lonv, latv, mlotst, rho3d;
     DevBuf phi[6];
     DevBuf stage_a, stage_b;  // generic staging (uploads for facefluxes / Redi-GM inputs)
 
@@ -155,6 +155,8 @@ int otmb_scan_u32_to_i64(otmb_ctx* ctx, const uint32_t* in, i64* out, i64 n, u64
 int otmb_need(otmb_ctx* ctx, bool cond, const char* what);
 int otmb_fused_build(otmb_ctx* ctx, const otmb_tm_params* prm, int mask, bool two_pass);
 int otmb_fused_v2_build(otmb_ctx* ctx, const otmb_tm_params* prm, int mask);
+int otmb_fused_v3_build(otmb_ctx* ctx, const otmb_tm_params* prm, int mask);
+int otmb_fused_v4_build(otmb_ctx* ctx, const otmb_tm_params* prm, int mask);
 int otmb_drop_zeros(otmb_ctx* ctx, int m, int base);
 int otmb_coo_build(otmb_ctx* ctx, const otmb_tm_params* prm, int mask);
 int otmb_sum_operators(otmb_ctx* ctx, int base);

@@ -40,10 +40,13 @@ __global__ void __launch_bounds__(256) k_fill_indices(const u64* __restrict__ ma
 }
 
 __global__ void __launch_bounds__(256) k_fill_lwet32(const u64* __restrict__ mask, const uint32_t* __restrict__ wpre,
-                                                     i64 M, int* __restrict__ lwet) {
+                                                     i64 M, int* __restrict__ lwet, int* __restrict__ rank3d) {
     const i64 L = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (L >= M) return;
-    if (wet_at(mask, (int)L)) lwet[rank_at(mask, wpre, (int)L)] = (int)L;
+    const bool wet = wet_at(mask, (int)L);
+    const int r = rank_at(mask, wpre, (int)L);
+    rank3d[L] = wet ? r : -1;     // the reference's Lwet3D (0-based, -1 = missing), src/matrixbuilding.jl:18-20
+    if (wet) lwet[r] = (int)L;
 }
 
 __global__ void k_l2_flush(uint4* __restrict__ buf, i64 n) {
@@ -143,7 +146,7 @@ int otmb_destroy(otmb_ctx* c) {
     if (!c) return OTMB_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf* bufs[] = {&c->v3D, &c->mask, &c->wcount, &c->wpre, &c->lwet, &c->area2D, &c->thk, &c->Z3D, &c->zt, &c->edge, &c->dnbr,
+    DevBuf* bufs[] = {&c->v3D, &c->mask, &c->wcount, &c->wpre, &c->lwet, &c->rank3d, &c->area2D, &c->thk, &c->Z3D, &c->zt, &c->edge, &c->dnbr,
                       &c->dedge, &c->lon, &c->lat, &c->lonv, &c->latv, &c->mlotst, &c->rho3d, &c->stage_a, &c->stage_b,
                       &c->flags, &c->tile_state, &c->scan_tmp, &c->sp_colptr, &c->sp_rowval, &c->sp_nzval, &c->l2};
     for (DevBuf* b : bufs) b->release();
@@ -224,8 +227,9 @@ int otmb_makeindices(otmb_ctx* c, const double* v3D, int64_t* N) {
     c->N = (i64)c->h_flags->nnz[0];
     // compacted wet list (0-based linear index per wet rank) for the thread-per-wet-cell kernels
     CU_TRY(c, c->lwet.ensure((size_t)(c->N + 1) * 4));
+    CU_TRY(c, c->rank3d.ensure((size_t)(c->M + 1) * 4));
     k_fill_lwet32<<<grid_for(c->M, 256), 256, 0, c->stream>>>(c->mask.as<u64>(), c->wpre.as<uint32_t>(), c->M,
-                                                               c->lwet.as<int>());
+                                                               c->lwet.as<int>(), c->rank3d.as<int>());
     LAUNCHED(c);
     CU_TRY(c, cudaGetLastError());
     c->have_indices = true;

@@ -1,0 +1,643 @@
+// fused_v4.cu — OTMB_PATH_FUSED: single-pass direct CSC assembly, one thread per WET cell,
+// written as ROLLED loops over a column's candidates so that the hot code stays inside the
+// instruction caches and the per-thread state stays inside 64 registers.
+//
+// Same mathematics and ordering rules as fused.cu (read its header first: gather form, emit
+// order, generic branch for coincident neighbours).  Why this shape (ncu profiles under
+// profiles/): the fully unrolled v2/v3 kernels were 8 000-10 000 SASS instructions of straight-line
+// code, each executed once per warp — instruction-cache hit rate 83-95 %, the GPC-level instruction
+// cache at 60-80 % of its request peak, 128 registers (16 warps per SM) or heavy spilling below
+// that; DRAM sat at 20-30 % with traffic equal to the algorithmic bytes.  The kernel was bound by
+// instruction supply and exposed latency, not by bandwidth.  Here:
+//   * per-thread candidate arrays (neighbour linear index, row index, running T value) live in
+//     shared memory, [candidate][thread] so that every access is conflict-free, and are indexed by
+//     a loop variable: the advection, horizontal-diffusion and T "walks" are 7-iteration loops;
+//   * a walk visits the candidates in ascending ROW order, which is a function of the cell's class
+//     only (regular T S W C E N B; west seam T S C E W N B; east seam T S E W C N B; right half
+//     of the tripolar fold row T S N W C E B) — one packed order word per class.  Ascending row
+//     order is also the reference's emit order of Tadv's diagonal contributions, so the walk
+//     accumulates the diagonal in passing; entries are appended to the staging buffer with a
+//     running position (absent entries go to a per-lane dump slot: no branches);
+//   * neighbours are resolved through `rank3d` (Int32 wet rank per grid cell, -1 = dry — the
+//     reference's own Lwet3D, /root/reference/src/matrixbuilding.jl:18-20);
+//   * staging is warp-private and reused matrix by matrix; each warp flushes its own contiguous
+//     slice of rowval/nzval with coalesced stores as soon as it is staged.
+//
+// Launch geometry: one tile of TILE consecutive wet cells per block, tiles in block-index order
+// (the decoupled look-back only waits on lower-numbered tiles, which are resident or finished).
+// A launch covers the wet ranks [w0, w0 + ncols): the whole matrix on one GPU, or the columns of
+// one k-slab when a matrix is sharded across GPUs (rows are global wet ranks either way).
+#include <cstdlib>
+#include <type_traits>
+
+#include "fused_generic.cuh"
+
+using namespace fusedg;
+
+namespace {
+
+constexpr u64 ST_AGG = 1ull << 62, ST_PRE = 2ull << 62, ST_MASK = (1ull << 62) - 1;
+constexpr int WDATA = 7 * 32;       // staged entries per warp: 7 per column
+constexpr int WCAP = WDATA + 32;    // + one dump slot per lane for absent entries (branch-free staging)
+// candidates in ascending row order, one nibble each, per class
+constexpr unsigned ORD0 = 0x6543210u;   // T S W C E N B
+constexpr unsigned ORD1 = 0x6524310u;   // T S C E W N B   (west seam: W wraps to the end of the row)
+constexpr unsigned ORD2 = 0x6532410u;   // T S E W C N B   (east seam: E wraps to the start of the row)
+constexpr unsigned ORD3 = 0x6432510u;   // T S N W C E B   (fold row, right half: N mirrors to the left of W)
+// own-side direction (OTMB_DIR_*) of the horizontal candidates: S -> south 0, W -> west 3, E -> east 1, N -> north 2
+constexpr unsigned OWNDIR = 0x00210300u;
+
+struct FastDiv {
+    u64 mul;
+    unsigned shift;
+};
+__device__ __forceinline__ unsigned fdiv(unsigned n, FastDiv f) { return (unsigned)((n * f.mul) >> f.shift); }
+
+struct V4Params {
+    GridDims g;
+    FastDiv divP, divNx;
+    const double *v3D, *thk, *area2D, *zt, *edge, *dnbr, *mlotst, *rho3d;
+    const double *pe, *pw, *pn, *ps, *pt, *pb;
+    // flux array read at candidate c (the slot of the neighbour that points back at this cell):
+    // T -> its bottom, S -> its north, W -> its east, (C unused), E -> its west, N -> its south, B -> its top,
+    // [7] = north again, used for N on the tripolar fold
+    const double* phi_nb[8];
+    const int* rank3d;   // (M) global wet rank, -1 = dry
+    const int* lwet;     // (ncols) linear index of the launch's wet cells
+    double kH, kVML, kVdeep, rho;
+    int upwind, base, build;
+    int ntiles;
+    int opt;             // experiment switches (OTMB_V4_OPT): 1 compact tile-state layout, 2 unrolled flush
+    int w0;              // global wet rank of the launch's first column
+    int ncols;
+    i64* colptr[5];
+    i64* rowval[5];
+    double* nzval[5];
+    DevFlags* flags;
+    u64* tile_state;
+};
+
+__device__ __forceinline__ size_t ts_index(int opt, int ntiles, int tile, int m) {
+    return (opt & 1) ? (size_t)m * ntiles + tile : (size_t)tile * 8 + m;
+}
+__device__ __forceinline__ u64 ld_vol(const u64* p) { return *reinterpret_cast<const volatile u64*>(p); }
+__device__ __forceinline__ void st_vol(u64* p, u64 v) { *reinterpret_cast<volatile u64*>(p) = v; }
+__device__ __forceinline__ u64 warp_sum64(u64 v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+__device__ __forceinline__ double upflux(double x, bool take_max, bool up) {
+    return up ? (take_max ? jl_max(x, 0.0) : jl_min(x, 0.0)) : x / 2;
+}
+__device__ __forceinline__ bool nz(double f) { return f > 0 || f < 0; }
+
+template <int TILE>
+struct Smem {
+    double val[TILE / 32][WCAP];   // warp-private staging: values
+    double Tv[7][TILE];            // running T = ((Tadv + TκH) + TκVML) + TκVdeep, by candidate
+    int row[TILE / 32][WCAP];      // warp-private staging: row indices (+ index base)
+    int Lc[7][TILE];               // linear index of candidate c (clamped to a valid cell)
+    int rk[7][TILE];               // row index (+ index base) of candidate c
+    u64 warp[TILE / 32];
+    u64 excl[5];
+};
+
+// ---------------------------------------------------------------------------------------
+template <bool RHO3D, int TILE, int MINB>
+// __grid_constant__: P is indexed dynamically and its address is taken by the generic branch
+__global__ void __launch_bounds__(TILE, MINB) k_fused_v4(const __grid_constant__ V4Params P) {
+    constexpr int NW = TILE / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem<TILE>& S = *reinterpret_cast<Smem<TILE>*>(smem_raw);
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tile = blockIdx.x;
+    const GridDims g = P.g;
+    const int PP = g.P;
+    const int w = tile * TILE + tid;       // column of this launch
+    const bool valid = w < P.ncols;
+    const int rC = P.w0 + w;               // global wet rank = row/column index
+    const bool up = P.upwind != 0;
+
+    // ================= phase 0: pattern =================
+    int L = 0, k = 0, p2 = 0;
+    unsigned wetm = 0, act = 0, mlm = 0;
+    unsigned ord = ORD0;
+    bool fold = false, generic = false;
+    unsigned m_T = 0, m_adv = 0, m_kh = 0, m_ml = 0, m_dp = 0;
+    unsigned errbits = 0;  // 1 dry nbr, 2 nan adv, 4 nan kh, 8 nan ml, 16 nan deep, 32 zero dropped, 64 nan rho
+    u64 packed = 0;        // 5 counts, 12 bits each
+    if (valid) {
+        int Lc[7], r[7];
+        L = __ldg(P.lwet + w);
+        k = (int)fdiv((unsigned)L, P.divP);
+        p2 = L - k * PP;
+        const int j = (int)fdiv((unsigned)p2, P.divNx);
+        const int i = p2 - j * g.nx;
+        fold = (j == g.ny - 1) && (g.topo == OTMB_TOPO_TRIPOLAR);
+        const bool hasT = k > 0, hasB = k < g.nz - 1, hasS = j > 0, hasN = (j < g.ny - 1) || fold;
+        const bool seamW = i == 0, seamE = i == g.nx - 1;
+        ord = seamW ? ORD1 : seamE ? ORD2 : (fold && (g.nx - 1 - i < i)) ? ORD3 : ORD0;
+        Lc[cC] = L;
+        Lc[cT] = hasT ? L - PP : L;
+        Lc[cB] = hasB ? L + PP : L;
+        Lc[cS] = hasS ? L - g.nx : L;
+        Lc[cW] = seamW ? L + (g.nx - 1) : L - 1;
+        Lc[cE] = seamE ? L - (g.nx - 1) : L + 1;
+        Lc[cN] = (j < g.ny - 1) ? L + g.nx : (fold ? L + (g.nx - 1 - 2 * i) : L);
+        // ---- loads: neighbour ranks, the six face fluxes the neighbours carry, mixed-layer inputs
+        const int qT = __ldg(P.rank3d + Lc[cT]), qS = __ldg(P.rank3d + Lc[cS]), qW = __ldg(P.rank3d + Lc[cW]),
+                  qE = __ldg(P.rank3d + Lc[cE]), qN = __ldg(P.rank3d + Lc[cN]), qB = __ldg(P.rank3d + Lc[cB]);
+        const double xT = __ldg(P.pb + Lc[cT]);                       // emitter above: its Bottom slot, max
+        const double xS = __ldg(P.pn + Lc[cS]);                       // its North slot, min
+        const double xW = __ldg(P.pe + Lc[cW]);                       // its East slot, min
+        const double xE = __ldg(P.pw + Lc[cE]);                       // its West slot, max
+        const double xN = __ldg((fold ? P.pn : P.ps) + Lc[cN]);       // its South slot (max), or North on the fold (min)
+        const double xB = __ldg(P.pt + Lc[cB]);                       // emitter below: its Top slot, min
+        const double ml = __ldg(P.mlotst + p2);
+        const double z0 = __ldg(P.zt + k), zT = __ldg(P.zt + (hasT ? k - 1 : k)), zB = __ldg(P.zt + (hasB ? k + 1 : k));
+        r[cC] = rC;
+        r[cT] = hasT ? qT : -1;
+        r[cS] = hasS ? qS : -1;
+        r[cW] = qW;
+        r[cE] = qE;
+        r[cN] = hasN ? qN : -1;
+        r[cB] = hasB ? qB : -1;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+            if (c != cC && r[c] >= 0) wetm |= 1u << c;
+            S.Lc[c][tid] = Lc[c];
+            S.rk[c][tid] = r[c] + P.base;
+        }
+        // face flux each neighbour carries through the face it shares with this cell (the value the
+        // reference reads at the neighbour, :244-295): only the sign pattern is needed here
+        if (P.build & 2) {
+            if ((wetm & bT) && nz(upflux(xT, true, up))) act |= bT;
+            if ((wetm & bS) && nz(upflux(xS, false, up))) act |= bS;
+            if ((wetm & bW) && nz(upflux(xW, false, up))) act |= bW;
+            if ((wetm & bE) && nz(upflux(xE, true, up))) act |= bE;
+            if ((wetm & bN) && nz(upflux(xN, !fold, up))) act |= bN;
+            if ((wetm & bB) && nz(upflux(xB, false, up))) act |= bB;
+            // own faces that point at a dry or absent cell: the reference would push `missing` (:247-250)
+            const unsigned dry = ~wetm;
+            bool bad = false;
+            if (dry & bW) bad |= nz(upflux(__ldg(P.pw + L), true, up));
+            if (dry & bE) bad |= nz(upflux(__ldg(P.pe + L), false, up));
+            if (dry & bS) bad |= nz(upflux(__ldg(P.ps + L), true, up));
+            if (dry & bN) bad |= nz(upflux(__ldg(P.pn + L), false, up));
+            if (dry & bB) bad |= nz(upflux(__ldg(P.pb + L), true, up));
+            if ((dry & bT) && hasT) bad |= nz(upflux(__ldg(P.pt + L), false, up));
+            if (bad) errbits |= 1u;
+        }
+        // mixed-layer mask Ω = zt[k] < mlotst[i,j] (false for NaN / missing), :85
+        if ((P.build & 8) && z0 < ml) {
+            if ((wetm & bT) && zT < ml) mlm |= bT;
+            if ((wetm & bB) && zB < ml) mlm |= bB;
+        }
+        // patterns (bit cC = diagonal)
+        if (P.build & 2) m_adv = act ? (act | bC) : 0u;
+        if (P.build & 4) m_kh = (wetm & HMASK) ? ((wetm & HMASK) | bC) : 0u;
+        if (P.build & 8) m_ml = mlm ? (mlm | bC) : 0u;
+        if (P.build & 16) m_dp = (wetm & VMASK) ? ((wetm & VMASK) | bC) : 0u;
+        if (P.build & 1) m_T = m_adv | m_kh | m_ml | m_dp;
+        // coincident neighbours inside the grid row (seam, fold, nx <= 2): generic branch
+        if (ord != ORD0 || fold) {
+            const bool pW = wetm & bW, pE = wetm & bE, pNf = fold && (wetm & bN);
+            generic = (pW && r[cW] == rC) || (pE && r[cE] == rC) || (pW && pE && r[cW] == r[cE]) ||
+                      (pNf && (r[cN] == rC || (pW && r[cN] == r[cW]) || (pE && r[cN] == r[cE])));
+        }
+        int c0, c1, c2, c3, c4;
+        if (!generic) {
+            c0 = __popc(m_T), c1 = __popc(m_adv), c2 = __popc(m_kh), c3 = __popc(m_ml), c4 = __popc(m_dp);
+        } else {
+            int g_r[7];
+#pragma unroll
+            for (int c = 0; c < 7; ++c) g_r[c] = r[c];
+            c0 = distinct_rows(m_T, g_r), c1 = distinct_rows(m_adv, g_r), c2 = distinct_rows(m_kh, g_r),
+            c3 = distinct_rows(m_ml, g_r), c4 = distinct_rows(m_dp, g_r);
+        }
+        packed = (u64)c0 | ((u64)c1 << 12) | ((u64)c2 << 24) | ((u64)c3 << 36) | ((u64)c4 << 48);
+    } else {
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+            S.Lc[c][tid] = 0;
+            S.rk[c][tid] = 0;
+        }
+    }
+
+    // ================= tile scan + decoupled look-back =================
+    u64 incl = packed;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const u64 o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) S.warp[wid] = incl;
+    const u64 lane_excl = incl - packed;                       // in-warp exclusive offsets of this column
+    const u64 warp_tot = __shfl_sync(0xffffffffu, incl, 31);   // entries of this warp, per matrix
+    __syncthreads();
+    u64 wbase = 0, total = 0;                                  // in-tile offset of this warp, tile totals
+#pragma unroll
+    for (int q = 0; q < NW; ++q) {
+        const u64 sw = S.warp[q];
+        if (q < wid) wbase += sw;
+        total += sw;
+    }
+    if (wid < (NW < 5 ? NW : 5)) {   // one warp per counter; the other warps go straight to the values
+        for (int m = wid; m < 5; m += NW) {
+            const u64 agg = (total >> (12 * m)) & 0xfffull;
+            if (lane == 0) st_vol(P.tile_state + ts_index(P.opt, P.ntiles, tile, m), (tile == 0 ? ST_PRE : ST_AGG) | agg);
+            u64 excl = 0;
+            if (P.opt & 8) excl = (u64)tile * TILE * 7;
+            if (tile > 0 && !(P.opt & 8)) {
+                int look = tile - 1;
+                while (true) {
+                    const int t = look - lane;
+                    u64 wv = ST_PRE;
+                    if (t >= 0) {
+                        // one counter's descriptors are contiguous: a poll of 32 tiles touches 8 sectors
+                        while (((wv = ld_vol(P.tile_state + ts_index(P.opt, P.ntiles, t, m))) >> 62) == 0) {}
+                    }
+                    const u64 val = wv & ST_MASK;
+                    const unsigned pm = __ballot_sync(0xffffffffu, (wv >> 62) == 2);
+                    if (pm) {
+                        const int first = __ffs(pm) - 1;
+                        excl += warp_sum64(lane <= first ? val : 0ull);
+                        break;
+                    }
+                    excl += warp_sum64(val);
+                    look -= 32;
+                }
+                if (lane == 0) st_vol(P.tile_state + ts_index(P.opt, P.ntiles, tile, m), ST_PRE | (excl + agg));
+            }
+            if (lane == 0) {
+                S.excl[m] = excl;
+                if (tile == P.ntiles - 1) {
+                    const u64 nnz = excl + agg;
+                    P.flags->nnz[m] = nnz;
+                    if (P.build >> m & 1) P.colptr[m][P.ncols] = (i64)nnz + P.base;
+                }
+            }
+        }
+    }
+
+    // ================= phase 1: operator by operator: walk -> warp staging -> flush =================
+    int* const srow = S.row[wid];
+    double* const sval = S.val[wid];
+    const int dump = WDATA + lane;
+    const double vC = __ldg(P.v3D + L);
+    const int rkC = rC + P.base;
+    GenOut gen;      // local memory, only touched by generic columns
+
+    if (valid && generic) {
+        double g_p[7];
+        int g_Lc[7], g_r[7];
+        unsigned g_err = 0;
+        for (int c = 0; c < 7; ++c) {
+            g_Lc[c] = S.Lc[c][tid];
+            g_r[c] = S.rk[c][tid] - P.base;
+            const bool mx = c == cT || c == cE || (c == cN && !fold);
+            const double f = c == cC ? 0.0 : upflux(__ldg(P.phi_nb[(c == cN && fold) ? 7 : c] + g_Lc[c]), mx, up);
+            g_p[c] = mx ? f : -f;
+        }
+        generic_full(P, L, k, g_Lc, g_r, wetm, fold, act, g_p, mlm, &gen, &g_err);
+        errbits |= g_err;
+        atomicAdd(&P.flags->generic_columns, 1);
+        m_T = m_adv = m_kh = m_ml = m_dp = 0;   // the walks stage nothing for this column
+        wetm = act = mlm = 0;
+    }
+
+    // copies a generic column's entries of matrix q behind the regular ones
+    auto stage_generic = [&](const int q, const int off) {
+        if (generic)
+            for (int a = 0; a < gen.cnt[q]; ++a) {
+                srow[off + a] = gen.rows[q][a] + P.base;
+                sval[off + a] = gen.vals[q][a];
+            }
+    };
+    // flush of the staged slice: colptr of the 32 columns, then rowval / nzval, coalesced
+    // (iters = compile-time bound on ceil(entries of a warp / 32): the matrix's maximum entries per column)
+    auto flush = [&](auto iters, const int q, const int off) {
+        constexpr int IT = decltype(iters)::value;
+        const u64 g0 = S.excl[q] + ((wbase >> (12 * q)) & 0xfffull);
+        const int n = (int)((warp_tot >> (12 * q)) & 0xfffull);
+        if (valid) P.colptr[q][w] = (i64)(g0 + (u64)off) + P.base;
+        __syncwarp();
+        i64* __restrict__ rv = P.rowval[q] + g0 + lane;
+        double* __restrict__ nv = P.nzval[q] + g0 + lane;
+        const int* sr = srow + lane;
+        const double* sv = sval + lane;
+        if (P.opt & 4) {
+        } else if (P.opt & 2) {
+#pragma unroll
+            for (int it = 0; it < IT; ++it) {
+                if (lane + 32 * it < n) {
+                    rv[32 * it] = (i64)(unsigned)sr[32 * it];
+                    nv[32 * it] = sv[32 * it];
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int e = lane; e < n; e += 32) {
+                rv[e - lane] = (i64)(unsigned)sr[e - lane];
+                nv[e - lane] = sv[e - lane];
+            }
+        }
+        __syncwarp();   // the staging buffer may be overwritten by the next matrix
+    };
+    auto offset_of = [&](const int q) { return (int)((lane_excl >> (12 * q)) & 0xfffull); };
+
+    // ---- Tadv walk (:193-204, :237-297): candidates in ascending row order = ascending emitter rank.
+    // Off-diagonal (𝑖, 𝑗) = -p/m𝑖 as the emitter 𝑖 computes it; the diagonal adds p/m𝑗 per emitter,
+    // sparse! keeping the first value and adding the later ones in that order.
+    const int off1 = offset_of(1);
+    if (P.build & 2) {
+        const double rhoC = RHO3D ? __ldg(P.rho3d + L) : P.rho;
+        if (RHO3D && valid && isnan(rhoC)) errbits |= 64u;
+        const unsigned MX = bT | bE | (fold ? 0u : bN);
+        double dsum = 0.0;
+        bool first = true, bad = false;
+        int pos = off1, posC = dump;
+#pragma unroll 1
+        for (int t = 0; t < 7; ++t) {
+            const int c = (ord >> (4 * t)) & 7;
+            const bool on = (m_adv >> c) & 1;
+            if (c == cC) {
+                posC = on ? pos : dump;
+                pos += on;
+                continue;
+            }
+            const int Lc = S.Lc[c][tid];
+            const bool mx = (MX >> c) & 1;
+            const double f = upflux(__ldg(P.phi_nb[(c == cN && fold) ? 7 : c] + Lc), mx, up);
+            const double p = mx ? f : -f;     // pushed magnitude: ϕ for W,S,B slots of the emitter, -ϕ for E,N,T
+            const double rb = ((RHO3D ? __ldg(P.rho3d + Lc) : P.rho) + rhoC) / 2;
+            // absent entries divide 1/1: a zero / NaN operand would send the whole warp through the
+            // slow path of the IEEE division
+            const double pn = on ? p : 1.0;
+            const double a = -pn / (on ? rb * __ldg(P.v3D + Lc) : 1.0);
+            const double d = pn / (on ? rb * vC : 1.0);
+            if (on) {
+                bad |= isnan(a) || isnan(d);
+                dsum = first ? d : dsum + d;
+                first = false;
+            }
+            const int pp = on ? pos : dump;
+            srow[pp] = S.rk[c][tid];
+            sval[pp] = a;
+            pos += on;
+            S.Tv[c][tid] = on ? a : 0.0;
+        }
+        if (bad) errbits |= 2u;
+        srow[posC] = rkC;
+        sval[posC] = dsum;
+        S.Tv[cC][tid] = (m_adv & bC) ? dsum : 0.0;
+        stage_generic(1, off1);
+    } else {
+#pragma unroll
+        for (int c = 0; c < 7; ++c) S.Tv[c][tid] = 0.0;
+    }
+
+    __syncthreads();   // look-back results (S.excl) published
+
+    if (tile * TILE + wid * 32 < P.ncols) {
+        if (P.build & 2) flush(std::integral_constant<int, 7>{}, 1, off1);
+
+        // ---- TκH walk (:348-415, :426-435).  Off-diagonal (𝑖, 𝑗) = -t as 𝑖 computes it; the diagonal sums
+        // 𝑗's own slots in emit order W,E,S,N.
+        if (P.build & 4) {
+            const int off2 = offset_of(2);
+            const double thC = __ldg(P.thk + L);
+            double tsW = 0.0, tsE = 0.0, tsS = 0.0, tsN = 0.0;
+            bool bad = false;
+            int pos = off2, posC = dump;
+#pragma unroll 1
+            for (int t = 1; t < 6; ++t) {      // T and B sit at both ends of every order word
+                const int c = (ord >> (4 * t)) & 7;
+                const bool on = (m_kh >> c) & 1;
+                if (c == cC) {
+                    posC = on ? pos : dump;
+                    pos += on;
+                    continue;
+                }
+                const int Lc = S.Lc[c][tid];
+                const int own = (OWNDIR >> (4 * c)) & 3;
+                const int opp = (c == cN && fold) ? own : own ^ 2;   // the neighbour's side of the shared face (:407)
+                const int q2 = Lc - k * PP;
+                const double a_own = thC * __ldg(P.edge + own * PP + p2);
+                const double a_nbr = __ldg(P.thk + Lc) * __ldg(P.edge + opp * PP + q2);
+                const double ka = on ? P.kH * jl_min(a_own, a_nbr) : 1.0;   // absent: 1/1, see the Tadv walk
+                const double ts = ka / (on ? __ldg(P.dnbr + own * PP + p2) * vC : 1.0);                   // row 𝑗 seen from 𝑗
+                const double tn = ka / (on ? __ldg(P.dnbr + opp * PP + q2) * __ldg(P.v3D + Lc) : 1.0);    // row 𝑖 seen from 𝑖
+                if (on) {
+                    bad |= isnan(ts) || isnan(tn);
+                    tsW = c == cW ? ts : tsW;
+                    tsE = c == cE ? ts : tsE;
+                    tsS = c == cS ? ts : tsS;
+                    tsN = c == cN ? ts : tsN;
+                    S.Tv[c][tid] = S.Tv[c][tid] + (-tn);
+                }
+                const int pp = on ? pos : dump;
+                srow[pp] = S.rk[c][tid];
+                sval[pp] = -tn;
+                pos += on;
+            }
+            if (bad) errbits |= 4u;
+            double dsum = 0.0;
+            bool first = true;
+            if (m_kh & bW) { dsum = tsW; first = false; }
+            if (m_kh & bE) { dsum = first ? tsE : dsum + tsE; first = false; }
+            if (m_kh & bS) { dsum = first ? tsS : dsum + tsS; first = false; }
+            if (m_kh & bN) { dsum = first ? tsN : dsum + tsN; first = false; }
+            srow[posC] = rkC;
+            sval[posC] = dsum;
+            if (m_kh & bC) S.Tv[cC][tid] = S.Tv[cC][tid] + dsum;
+            stage_generic(2, off2);
+            flush(std::integral_constant<int, 5>{}, 2, off2);
+        }
+
+        // ---- TκVML and TκVdeep (:450-477); own slots in emit order B, T; T folds TκVML before TκVdeep
+        if (P.build & 24) {
+            double dpT = 0.0, dpB = 0.0, dps = 0.0, mlT = 0.0, mlB = 0.0, mls = 0.0;
+            if (m_dp | m_ml) {
+                const double area = __ldg(P.area2D + p2), ztC = __ldg(P.zt + k);
+                bool firstm = true, firstd = true, badm = false, badd = false;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int c = q == 0 ? cB : cT;
+                    if (!(wetm >> c & 1)) continue;
+                    const double d = fabs(ztC - __ldg(P.zt + (c == cT ? k - 1 : k + 1)));
+                    const double qs = d * vC, qn = d * __ldg(P.v3D + S.Lc[c][tid]);
+                    if (m_dp) {
+                        const double ka = P.kVdeep * area;
+                        const double ts = ka / qs, tn = ka / qn;
+                        badd |= isnan(ts) || isnan(tn);
+                        dps = firstd ? ts : dps + ts;
+                        firstd = false;
+                        if (c == cT) dpT = -tn; else dpB = -tn;
+                    }
+                    if (mlm >> c & 1) {
+                        const double ka = P.kVML * area;
+                        const double ts = ka / qs, tn = ka / qn;
+                        badm |= isnan(ts) || isnan(tn);
+                        mls = firstm ? ts : mls + ts;
+                        firstm = false;
+                        if (c == cT) mlT = -tn; else mlB = -tn;
+                    }
+                }
+                if (badm) errbits |= 8u;
+                if (badd) errbits |= 16u;
+            }
+            // rows of a vertical operator: T, C, B in every class
+            auto emit_vertical = [&](const int q, const unsigned m, const double vT, const double vCd, const double vB) {
+                const int off = offset_of(q);
+                int pos = off;
+                int pp = (m & bT) ? pos : dump;
+                srow[pp] = S.rk[cT][tid];
+                sval[pp] = vT;
+                pos += (m & bT) ? 1 : 0;
+                pp = (m & bC) ? pos : dump;
+                srow[pp] = rkC;
+                sval[pp] = vCd;
+                pos += (m & bC) ? 1 : 0;
+                pp = (m & bB) ? pos : dump;
+                srow[pp] = S.rk[cB][tid];
+                sval[pp] = vB;
+                if (m & bT) S.Tv[cT][tid] = S.Tv[cT][tid] + vT;
+                if (m & bC) S.Tv[cC][tid] = S.Tv[cC][tid] + vCd;
+                if (m & bB) S.Tv[cB][tid] = S.Tv[cB][tid] + vB;
+                stage_generic(q, off);
+                flush(std::integral_constant<int, 3>{}, q, off);
+            };
+            if (P.build & 8) emit_vertical(3, m_ml, mlT, mls, mlB);
+            if (P.build & 16) emit_vertical(4, m_dp, dpT, dps, dpB);
+        }
+
+        // ---- T walk: union pattern; exact zeros are flagged and removed by the compaction pass
+        if (P.build & 1) {
+            const int off0 = offset_of(0);
+            int pos = off0;
+            bool zero = false;
+#pragma unroll 1
+            for (int t = 0; t < 7; ++t) {
+                const int c = (ord >> (4 * t)) & 7;
+                const bool on = (m_T >> c) & 1;
+                const double v = S.Tv[c][tid];
+                zero |= on && (v == 0.0);
+                const int pp = on ? pos : dump;
+                srow[pp] = S.rk[c][tid];
+                sval[pp] = v;
+                pos += on;
+            }
+            if (zero) errbits |= 32u;
+            stage_generic(0, off0);
+            flush(std::integral_constant<int, 7>{}, 0, off0);
+        }
+    }
+
+    // ---- flags: one atomic per warp and kind
+    if (__any_sync(0xffffffffu, errbits != 0)) {
+#pragma unroll
+        for (int b = 0; b < 7; ++b) {
+            const unsigned any = __ballot_sync(0xffffffffu, (errbits >> b) & 1u);
+            if (lane == 0 && any) {
+                int* dst = b == 0 ? &P.flags->err_dry_neighbour : b == 1 ? &P.flags->nan_adv : b == 2 ? &P.flags->nan_kh
+                         : b == 3 ? &P.flags->nan_kvml : b == 4 ? &P.flags->nan_kvdeep : b == 5 ? &P.flags->zero_dropped
+                                                                                                : &P.flags->nan_rho;
+                atomicOr(dst, 1);
+            }
+        }
+    }
+}
+
+FastDiv make_fastdiv(unsigned d) {
+    unsigned s = 0;
+    while ((1ull << s) < d) ++s;
+    FastDiv f;
+    f.shift = 32 + s;
+    f.mul = ((1ull << f.shift) + d - 1) / d;
+    return f;
+}
+
+template <bool RHO3D, int TILE, int MINB>
+int launch_v4(otmb_ctx* c, V4Params& P) {
+    const int ntiles = (int)(((i64)P.ncols + TILE - 1) / TILE);
+    P.ntiles = ntiles;
+    CU_TRY(c, c->tile_state.ensure((size_t)ntiles * 8 * sizeof(u64)));
+    P.tile_state = c->tile_state.as<u64>();
+    CU_TRY(c, cudaMemsetAsync(P.tile_state, 0, (size_t)ntiles * 8 * sizeof(u64), c->stream));
+    const size_t smem = sizeof(Smem<TILE>);
+    CU_TRY(c, cudaFuncSetAttribute(k_fused_v4<RHO3D, TILE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_fused_v4<RHO3D, TILE, MINB><<<ntiles, TILE, smem, c->stream>>>(P);
+    LAUNCHED(c);
+    CU_TRY(c, cudaGetLastError());
+    return OTMB_OK;
+}
+
+}  // namespace
+
+int otmb_fused_v4_build(otmb_ctx* c, const otmb_tm_params* prm, int build) {
+    V4Params P;
+    P.g = GridDims{(int)c->nx, (int)c->ny, (int)c->nz, c->topo, (int)c->P, (int)c->M};
+    P.divP = make_fastdiv((unsigned)c->P);
+    P.divNx = make_fastdiv((unsigned)c->nx);
+    P.v3D = c->v3D.as<double>();
+    P.thk = c->thk.as<double>();
+    P.area2D = c->area2D.as<double>();
+    P.zt = c->zt.as<double>();
+    P.edge = c->edge.as<double>();
+    P.dnbr = c->dnbr.as<double>();
+    P.mlotst = c->mlotst.as<double>();
+    P.rho3d = c->have_rho3d ? c->rho3d.as<double>() : nullptr;
+    P.pe = c->phi[OTMB_FACE_EAST].as<double>();
+    P.pw = c->phi[OTMB_FACE_WEST].as<double>();
+    P.pn = c->phi[OTMB_FACE_NORTH].as<double>();
+    P.ps = c->phi[OTMB_FACE_SOUTH].as<double>();
+    P.pt = c->phi[OTMB_FACE_TOP].as<double>();
+    P.pb = c->phi[OTMB_FACE_BOTTOM].as<double>();
+    P.phi_nb[cT] = P.pb;
+    P.phi_nb[cS] = P.pn;
+    P.phi_nb[cW] = P.pe;
+    P.phi_nb[cC] = P.pe;
+    P.phi_nb[cE] = P.pw;
+    P.phi_nb[cN] = P.ps;
+    P.phi_nb[cB] = P.pt;
+    P.phi_nb[7] = P.pn;
+    P.rank3d = c->rank3d.as<int>();
+    P.lwet = c->lwet.as<int>();
+    P.kH = prm->kH;
+    P.kVML = prm->kVML;
+    P.kVdeep = prm->kVdeep;
+    P.rho = prm->rho;
+    P.upwind = prm->upwind;
+    P.base = prm->index_base;
+    P.build = build;
+    P.w0 = 0;
+    P.opt = getenv("OTMB_V4_OPT") ? atoi(getenv("OTMB_V4_OPT")) : 0;
+    P.ncols = (int)c->N;
+    P.flags = c->flags.as<DevFlags>();
+    const int cap_per_col[5] = {7, 7, 5, 3, 3};
+    for (int m = 0; m < 5; ++m) {
+        P.colptr[m] = nullptr;
+        P.rowval[m] = nullptr;
+        P.nzval[m] = nullptr;
+        if (!(build >> m & 1)) continue;
+        const size_t cap = (size_t)c->N * cap_per_col[m] + 8;
+        CU_TRY(c, c->colptr[m].ensure((size_t)(c->N + 1) * 8));
+        CU_TRY(c, c->rowval[m].ensure(cap * 8));
+        CU_TRY(c, c->nzval[m].ensure(cap * 8));
+        P.colptr[m] = c->colptr[m].as<i64>();
+        P.rowval[m] = c->rowval[m].as<i64>();
+        P.nzval[m] = c->nzval[m].as<double>();
+    }
+    static const int variant = getenv("OTMB_V4_VARIANT") ? atoi(getenv("OTMB_V4_VARIANT")) : 0;
+    if (c->have_rho3d) return launch_v4<true, 256, 4>(c, P);
+    switch (variant) {
+        case 1: return launch_v4<false, 256, 3>(c, P);
+        case 2: return launch_v4<false, 256, 2>(c, P);
+        case 3: return launch_v4<false, 128, 8>(c, P);
+        case 4: return launch_v4<false, 128, 6>(c, P);
+        default: return launch_v4<false, 256, 4>(c, P);
+    }
+}
