@@ -110,6 +110,29 @@ int otmb_set_gridmetrics(otmb_ctx* ctx, const double* area2D, const double* thkc
  * NamedTuple (east, west, north, south, top, bottom); they also stay resident as ϕ. */
 int otmb_facefluxes(otmb_ctx* ctx, const double* umo, const double* vmo, double fill_value,
                     double* east, double* west, double* north, double* south, double* top, double* bottom);
+/* ---- k-slab sharding of ONE matrix across GPUs (one context per GPU / rank) -----------------------
+ * Wet ranks are ordered k-slowest, so a contiguous range of levels [k_begin, k_end) is a contiguous
+ * block of rows/columns of every matrix.  A slab context keeps those levels plus one halo level on
+ * either side resident, assembles the CSC COLUMNS of its owned cells (rows stay global wet ranks)
+ * and returns them with local colptr offsets; the host concatenates the ranks' segments.
+ * Call order: otmb_set_grid, otmb_set_slab, otmb_makeindices, [otmb_slab_counts on every rank ->
+ * exclusive sum over lower ranks], otmb_set_rank_offset, metrics / fluxes / build / fetch as usual.
+ * Every function still takes the FULL (nx,ny,nz) host arrays; only the slab's window is copied.
+ * The reference has no counterpart (single process); this shards its loop `for 𝑖 in eachindex(Lwet)`
+ * (src/matrixbuilding.jl:237, 348, 450). */
+int otmb_set_slab(otmb_ctx* ctx, int64_t k_begin, int64_t k_end);   /* 0-based levels; (0, nz) = unsharded */
+int otmb_slab_counts(otmb_ctx* ctx, int64_t* n_owned, int64_t* n_halo_above);
+int otmb_set_rank_offset(otmb_ctx* ctx, int64_t w0);   /* global wet rank (0-based) of the first owned cell */
+/* facefluxes on a slab.  The continuity scan (src/velocities.jl:234-243) runs bottom-up and is not
+ * associative in floating point, so the slabs form a chain: carry_in = ϕtop of level k_end computed by
+ * the slab below (NULL for the deepest slab), carry_out = ϕtop of level k_begin for the slab above.
+ * carry_on_device != 0: both are DEVICE pointers of nx*ny doubles (e.g. the buffers an NCCL send/recv
+ * works on).  valid_uv[0..1]: whether this slab saw any valid umo / vmo value; the caller combines the
+ * ranks and raises the reference's assertion (:199-200).  Outputs: owned levels of the full-size arrays. */
+int otmb_facefluxes_slab(otmb_ctx* ctx, const double* umo, const double* vmo, double fill_value,
+                         const double* carry_in, double* carry_out, int32_t carry_on_device, int32_t valid_uv[2],
+                         double* east, double* west, double* north, double* south, double* top, double* bottom);
+
 /* upload caller-held ϕ (order OTMB_FACE_*) */
 int otmb_set_facefluxes(otmb_ctx* ctx, const double* const phi[6]);
 int otmb_set_mlotst(otmb_ctx* ctx, const double* mlotst /* (nx,ny), NaN = missing */);

@@ -60,12 +60,19 @@ struct otmb_ctx {
     int sm_count = OTMB_SM_COUNT_HINT;
 
     i64 nx = 0, ny = 0, nz = 0, P = 0, M = 0, N = 0, nwords = 0;
+    // k-slab sharding (otmb_set_slab): this context owns the levels [k_own0, k_own1) and keeps one halo
+    // level on either side resident, [k_win0, k_win1).  Unsharded: own = window = [0, nz).
+    // N = wet cells in the window (local ranks 0..N), ncols = owned wet cells = columns this context
+    // assembles, h_up = wet cells of the upper halo level, w0 = global wet rank of the first owned cell.
+    bool sharded = false, have_rank_offset = false;
+    i64 k_own0 = 0, k_own1 = 0, k_win0 = 0, k_win1 = 0, ncols = 0, h_up = 0, w0 = 0;
     int topo = OTMB_TOPO_UNKNOWN;
     bool have_grid = false, have_indices = false, have_metrics = false, have_phi = false, have_mlotst = false,
          have_rho3d = false, have_z3d = false, have_lonlat = false;
 
     DevBuf v3D, mask, wcount, wpre, lwet, rank3d, area2D, thk, Z3D, zt, edge, dnbr, dedge, lon, lat, lonv, latv, mlotst, rho3d;
     DevBuf phi[6];
+    DevBuf carry[2];          // (nx,ny) planes handed between k-slabs by the continuity scan
     DevBuf stage_a, stage_b;  // generic staging (uploads for facefluxes / Redi-GM inputs)
 
     // results
@@ -153,6 +160,7 @@ int otmb_scan_u32_to_i64(otmb_ctx* ctx, const uint32_t* in, i64* out, i64 n, u64
 
 // internal entry points across translation units
 int otmb_need(otmb_ctx* ctx, bool cond, const char* what);
+int otmb_upload3d(otmb_ctx* ctx, DevBuf& buf, const double* host);   // whole (nx,ny,nz) array, or only the slab window
 int otmb_fused_build(otmb_ctx* ctx, const otmb_tm_params* prm, int mask, bool two_pass);
 int otmb_fused_v2_build(otmb_ctx* ctx, const otmb_tm_params* prm, int mask);
 int otmb_fused_v3_build(otmb_ctx* ctx, const otmb_tm_params* prm, int mask);

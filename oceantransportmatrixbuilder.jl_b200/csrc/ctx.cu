@@ -40,12 +40,14 @@ __global__ void __launch_bounds__(256) k_fill_indices(const u64* __restrict__ ma
 }
 
 __global__ void __launch_bounds__(256) k_fill_lwet32(const u64* __restrict__ mask, const uint32_t* __restrict__ wpre,
-                                                     i64 M, int* __restrict__ lwet, int* __restrict__ rank3d) {
+                                                     i64 M, int rank_offset, int* __restrict__ lwet,
+                                                     int* __restrict__ rank3d) {
     const i64 L = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (L >= M) return;
     const bool wet = wet_at(mask, (int)L);
     const int r = rank_at(mask, wpre, (int)L);
-    rank3d[L] = wet ? r : -1;     // the reference's Lwet3D (0-based, -1 = missing), src/matrixbuilding.jl:18-20
+    // the reference's Lwet3D (0-based, -1 = missing), src/matrixbuilding.jl:18-20; global rank when sharded
+    rank3d[L] = wet ? r + rank_offset : -1;
     if (wet) lwet[r] = (int)L;
 }
 
@@ -62,6 +64,39 @@ int upload(otmb_ctx* ctx, DevBuf& buf, const void* host, size_t bytes) {
 }
 
 }  // namespace
+
+int otmb_upload3d(otmb_ctx* c, DevBuf& buf, const double* host) {
+    CU_TRY(c, buf.ensure((size_t)c->M * 8));
+    const size_t a = (size_t)c->k_win0 * c->P, b = (size_t)c->k_win1 * c->P;
+    CU_TRY(c, cudaMemcpyAsync((double*)buf.p + a, host + a, (b - a) * 8, cudaMemcpyHostToDevice, c->stream));
+    return OTMB_OK;
+}
+
+// number of wet cells with linear index < X (two small reads of the resident mask / prefix)
+static int wet_below(otmb_ctx* c, i64 X, i64* out) {
+    if (X >= c->M) {
+        *out = c->N;
+        return OTMB_OK;
+    }
+    u64 word = 0;
+    uint32_t pre = 0;
+    CU_TRY(c, cudaMemcpyAsync(&word, c->mask.as<u64>() + (X >> 6), 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(&pre, c->wpre.as<uint32_t>() + (X >> 6), 4, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    *out = (i64)pre + __builtin_popcountll(word & ((1ull << (X & 63)) - 1ull));
+    return OTMB_OK;
+}
+
+static int fill_ranks(otmb_ctx* c) {
+    CU_TRY(c, c->lwet.ensure((size_t)(c->N + 1) * 4));
+    CU_TRY(c, c->rank3d.ensure((size_t)(c->M + 1) * 4));
+    k_fill_lwet32<<<grid_for(c->M, 256), 256, 0, c->stream>>>(c->mask.as<u64>(), c->wpre.as<uint32_t>(), c->M,
+                                                               (int)(c->w0 - c->h_up), c->lwet.as<int>(), c->rank3d.as<int>());
+    LAUNCHED(c);
+    CU_TRY(c, cudaGetLastError());
+    c->have_rank_offset = true;
+    return OTMB_OK;
+}
 
 int otmb_need(otmb_ctx* ctx, bool cond, const char* what) {
     if (cond) return OTMB_OK;
@@ -151,6 +186,7 @@ int otmb_destroy(otmb_ctx* c) {
                       &c->flags, &c->tile_state, &c->scan_tmp, &c->sp_colptr, &c->sp_rowval, &c->sp_nzval, &c->l2};
     for (DevBuf* b : bufs) b->release();
     for (int q = 0; q < 6; ++q) c->phi[q].release();
+    for (int q = 0; q < 2; ++q) c->carry[q].release();
     for (int q = 0; q < 6; ++q) c->add_tmp[q].release();
     for (int q = 0; q < 12; ++q) c->coo[q].release();
     for (int q = 0; q < 5; ++q) {
@@ -204,6 +240,45 @@ int otmb_set_grid(otmb_ctx* c, int64_t nx, int64_t ny, int64_t nz, int topology)
     c->have_indices = c->have_metrics = c->have_phi = c->have_mlotst = c->have_rho3d = c->have_z3d = c->have_lonlat = false;
     for (int q = 0; q < 5; ++q) c->have_mat[q] = c->preset[q] = false;
     c->N = 0;
+    c->sharded = c->have_rank_offset = false;
+    c->k_own0 = c->k_win0 = 0;
+    c->k_own1 = c->k_win1 = nz;
+    c->ncols = c->h_up = c->w0 = 0;
+    return OTMB_OK;
+}
+
+int otmb_set_slab(otmb_ctx* c, int64_t k_begin, int64_t k_end) {
+    if (!c) return OTMB_ERR_BADARG;
+    OT_TRY(otmb_need(c, c->have_grid, "otmb_set_grid"));
+    if (k_begin < 0 || k_end > c->nz || k_begin >= k_end) return otmb_fail(c, OTMB_ERR_BADARG, "slab must be a non-empty level range");
+    c->k_own0 = k_begin;
+    c->k_own1 = k_end;
+    c->k_win0 = k_begin > 0 ? k_begin - 1 : 0;
+    c->k_win1 = k_end < c->nz ? k_end + 1 : c->nz;
+    c->sharded = !(k_begin == 0 && k_end == c->nz);
+    c->have_indices = c->have_metrics = c->have_phi = c->have_mlotst = c->have_rho3d = c->have_z3d = c->have_lonlat = false;
+    c->have_rank_offset = false;
+    for (int q = 0; q < 5; ++q) c->have_mat[q] = c->preset[q] = false;
+    c->N = c->ncols = c->h_up = c->w0 = 0;
+    return OTMB_OK;
+}
+
+int otmb_slab_counts(otmb_ctx* c, int64_t* n_owned, int64_t* n_halo_above) {
+    if (!c) return OTMB_ERR_BADARG;
+    OT_TRY(otmb_need(c, c->have_indices, "otmb_makeindices"));
+    if (n_owned) *n_owned = c->ncols;
+    if (n_halo_above) *n_halo_above = c->h_up;
+    return OTMB_OK;
+}
+
+int otmb_set_rank_offset(otmb_ctx* c, int64_t w0) {
+    if (!c || w0 < 0) return OTMB_ERR_BADARG;
+    OT_TRY(otmb_need(c, c->have_indices, "otmb_makeindices"));
+    if (w0 < c->h_up) return otmb_fail(c, OTMB_ERR_BADARG, "rank offset smaller than the wet count of the halo level above");
+    CU_TRY(c, cudaSetDevice(c->device));
+    c->w0 = w0;
+    OT_TRY(fill_ranks(c));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
     return OTMB_OK;
 }
 
@@ -211,7 +286,12 @@ int otmb_makeindices(otmb_ctx* c, const double* v3D, int64_t* N) {
     if (!c || !v3D) return OTMB_ERR_BADARG;
     OT_TRY(otmb_need(c, c->have_grid, "otmb_set_grid"));
     CU_TRY(c, cudaSetDevice(c->device));
-    OT_TRY(upload(c, c->v3D, v3D, (size_t)c->M * 8));
+    if (c->sharded) {
+        // cells outside the window read as dry (all-ones bytes are a NaN): their data never reaches this GPU
+        CU_TRY(c, c->v3D.ensure((size_t)c->M * 8));
+        CU_TRY(c, cudaMemsetAsync(c->v3D.p, 0xff, (size_t)c->M * 8, c->stream));
+    }
+    OT_TRY(otmb_upload3d(c, c->v3D, v3D));
     CU_TRY(c, c->mask.ensure((size_t)(c->nwords + 1) * 8));
     CU_TRY(c, c->wcount.ensure((size_t)(c->nwords + 1) * 4));
     CU_TRY(c, c->wpre.ensure((size_t)(c->nwords + 1) * 4));
@@ -225,13 +305,20 @@ int otmb_makeindices(otmb_ctx* c, const double* v3D, int64_t* N) {
                          &c->flags.as<DevFlags>()->nnz[0]));
     OT_TRY(otmb_fetch_flags(c));
     c->N = (i64)c->h_flags->nnz[0];
-    // compacted wet list (0-based linear index per wet rank) for the thread-per-wet-cell kernels
-    CU_TRY(c, c->lwet.ensure((size_t)(c->N + 1) * 4));
-    CU_TRY(c, c->rank3d.ensure((size_t)(c->M + 1) * 4));
-    k_fill_lwet32<<<grid_for(c->M, 256), 256, 0, c->stream>>>(c->mask.as<u64>(), c->wpre.as<uint32_t>(), c->M,
-                                                               c->lwet.as<int>(), c->rank3d.as<int>());
-    LAUNCHED(c);
-    CU_TRY(c, cudaGetLastError());
+    c->h_up = 0;
+    c->ncols = c->N;
+    c->w0 = 0;
+    if (c->sharded) {
+        i64 below_own = 0, below_end = 0;
+        OT_TRY(wet_below(c, c->k_own0 * c->P, &below_own));
+        OT_TRY(wet_below(c, c->k_own1 * c->P, &below_end));
+        c->h_up = below_own;
+        c->ncols = below_end - below_own;
+        c->have_rank_offset = false;   // global ranks need otmb_set_rank_offset (sum of the lower ranks' counts)
+    } else {
+        // compacted wet list (0-based linear index per wet rank) and Lwet3D for the thread-per-wet-cell kernels
+        OT_TRY(fill_ranks(c));
+    }
     c->have_indices = true;
     for (int q = 0; q < 5; ++q) c->have_mat[q] = c->preset[q] = false;
     if (N) *N = c->N;
@@ -241,6 +328,7 @@ int otmb_makeindices(otmb_ctx* c, const double* v3D, int64_t* N) {
 int otmb_get_indices(otmb_ctx* c, uint64_t* wet_chunks, int64_t* Lwet, int64_t* Lwet3D) {
     if (!c) return OTMB_ERR_BADARG;
     OT_TRY(otmb_need(c, c->have_indices, "otmb_makeindices"));
+    if (c->sharded) return otmb_fail(c, OTMB_ERR_STATE, "otmb_get_indices is not available on a slab context");
     CU_TRY(c, cudaSetDevice(c->device));
     if (wet_chunks)
         CU_TRY(c, cudaMemcpyAsync(wet_chunks, c->mask.p, (size_t)c->nwords * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -272,7 +360,7 @@ int otmb_set_facefluxes(otmb_ctx* c, const double* const phi[6]) {
     CU_TRY(c, cudaSetDevice(c->device));
     for (int q = 0; q < 6; ++q) {
         if (!phi[q]) return otmb_fail(c, OTMB_ERR_BADARG, "null face-flux array");
-        OT_TRY(upload(c, c->phi[q], phi[q], (size_t)c->M * 8));
+        OT_TRY(otmb_upload3d(c, c->phi[q], phi[q]));
     }
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     c->have_phi = true;
@@ -297,7 +385,7 @@ int otmb_set_rho3d(otmb_ctx* c, const double* rho3d) {
         c->have_rho3d = false;
         return OTMB_OK;
     }
-    OT_TRY(upload(c, c->rho3d, rho3d, (size_t)c->M * 8));
+    OT_TRY(otmb_upload3d(c, c->rho3d, rho3d));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     c->have_rho3d = true;
     return OTMB_OK;
@@ -309,12 +397,12 @@ int otmb_set_gridmetrics(otmb_ctx* c, const double* area2D, const double* thk, c
     OT_TRY(otmb_need(c, c->have_grid, "otmb_set_grid"));
     CU_TRY(c, cudaSetDevice(c->device));
     OT_TRY(upload(c, c->area2D, area2D, (size_t)c->P * 8));
-    OT_TRY(upload(c, c->thk, thk, (size_t)c->M * 8));
+    OT_TRY(otmb_upload3d(c, c->thk, thk));
     OT_TRY(upload(c, c->zt, zt, (size_t)c->nz * 8));
     OT_TRY(upload(c, c->edge, edge, (size_t)c->P * 32));
     OT_TRY(upload(c, c->dnbr, dnbr, (size_t)c->P * 32));
     if (Z3D) {
-        OT_TRY(upload(c, c->Z3D, Z3D, (size_t)c->M * 8));
+        OT_TRY(otmb_upload3d(c, c->Z3D, Z3D));
         c->have_z3d = true;
     }
     if (lon && lat) {

@@ -791,7 +791,7 @@ int launch_v2(otmb_ctx* c, V2Params& P) {
 }  // namespace
 
 int otmb_drop_zeros(otmb_ctx* c, int m, int base) {
-    const i64 n = c->N;
+    const i64 n = c->ncols;
     DevBuf &cnt = c->coo[3], &cp0 = c->coo[11];
     CU_TRY(c, cnt.ensure((size_t)(n + 1) * 4));
     CU_TRY(c, cp0.ensure((size_t)(n + 1) * 8));

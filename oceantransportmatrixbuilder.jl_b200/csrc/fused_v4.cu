@@ -67,7 +67,6 @@ struct V4Params {
     double kH, kVML, kVdeep, rho;
     int upwind, base, build;
     int ntiles;
-    int opt;             // experiment switches (OTMB_V4_OPT): 1 compact tile-state layout, 2 unrolled flush
     int w0;              // global wet rank of the launch's first column
     int ncols;
     i64* colptr[5];
@@ -77,9 +76,6 @@ struct V4Params {
     u64* tile_state;
 };
 
-__device__ __forceinline__ size_t ts_index(int opt, int ntiles, int tile, int m) {
-    return (opt & 1) ? (size_t)m * ntiles + tile : (size_t)tile * 8 + m;
-}
 __device__ __forceinline__ u64 ld_vol(const u64* p) { return *reinterpret_cast<const volatile u64*>(p); }
 __device__ __forceinline__ void st_vol(u64* p, u64 v) { *reinterpret_cast<volatile u64*>(p) = v; }
 __device__ __forceinline__ u64 warp_sum64(u64 v) {
@@ -247,17 +243,15 @@ __global__ void __launch_bounds__(TILE, MINB) k_fused_v4(const __grid_constant__
     if (wid < (NW < 5 ? NW : 5)) {   // one warp per counter; the other warps go straight to the values
         for (int m = wid; m < 5; m += NW) {
             const u64 agg = (total >> (12 * m)) & 0xfffull;
-            if (lane == 0) st_vol(P.tile_state + ts_index(P.opt, P.ntiles, tile, m), (tile == 0 ? ST_PRE : ST_AGG) | agg);
+            if (lane == 0) st_vol(P.tile_state + (size_t)tile * 8 + m, (tile == 0 ? ST_PRE : ST_AGG) | agg);
             u64 excl = 0;
-            if (P.opt & 8) excl = (u64)tile * TILE * 7;
-            if (tile > 0 && !(P.opt & 8)) {
+            if (tile > 0) {
                 int look = tile - 1;
                 while (true) {
                     const int t = look - lane;
                     u64 wv = ST_PRE;
                     if (t >= 0) {
-                        // one counter's descriptors are contiguous: a poll of 32 tiles touches 8 sectors
-                        while (((wv = ld_vol(P.tile_state + ts_index(P.opt, P.ntiles, t, m))) >> 62) == 0) {}
+                        while (((wv = ld_vol(P.tile_state + (size_t)t * 8 + m)) >> 62) == 0) {}
                     }
                     const u64 val = wv & ST_MASK;
                     const unsigned pm = __ballot_sync(0xffffffffu, (wv >> 62) == 2);
@@ -269,7 +263,7 @@ __global__ void __launch_bounds__(TILE, MINB) k_fused_v4(const __grid_constant__
                     excl += warp_sum64(val);
                     look -= 32;
                 }
-                if (lane == 0) st_vol(P.tile_state + ts_index(P.opt, P.ntiles, tile, m), ST_PRE | (excl + agg));
+                if (lane == 0) st_vol(P.tile_state + (size_t)tile * 8 + m, ST_PRE | (excl + agg));
             }
             if (lane == 0) {
                 S.excl[m] = excl;
@@ -328,20 +322,11 @@ __global__ void __launch_bounds__(TILE, MINB) k_fused_v4(const __grid_constant__
         double* __restrict__ nv = P.nzval[q] + g0 + lane;
         const int* sr = srow + lane;
         const double* sv = sval + lane;
-        if (P.opt & 4) {
-        } else if (P.opt & 2) {
 #pragma unroll
-            for (int it = 0; it < IT; ++it) {
-                if (lane + 32 * it < n) {
-                    rv[32 * it] = (i64)(unsigned)sr[32 * it];
-                    nv[32 * it] = sv[32 * it];
-                }
-            }
-        } else {
-#pragma unroll 1
-            for (int e = lane; e < n; e += 32) {
-                rv[e - lane] = (i64)(unsigned)sr[e - lane];
-                nv[e - lane] = sv[e - lane];
+        for (int it = 0; it < IT; ++it) {
+            if (lane + 32 * it < n) {
+                rv[32 * it] = (i64)(unsigned)sr[32 * it];
+                nv[32 * it] = sv[32 * it];
             }
         }
         __syncwarp();   // the staging buffer may be overwritten by the next matrix
@@ -359,24 +344,36 @@ __global__ void __launch_bounds__(TILE, MINB) k_fused_v4(const __grid_constant__
         double dsum = 0.0;
         bool first = true, bad = false;
         int pos = off1, posC = dump;
+        // software pipeline: the loads of candidate t+1 are issued before candidate t is computed
+        int c_n = ord & 7;
+        int Lc_n = S.Lc[c_n][tid];
+        double x_n = __ldg(P.phi_nb[(c_n == cN && fold) ? 7 : c_n] + Lc_n), v_n = __ldg(P.v3D + Lc_n);
+        double r_n = RHO3D ? __ldg(P.rho3d + Lc_n) : P.rho;
 #pragma unroll 1
         for (int t = 0; t < 7; ++t) {
-            const int c = (ord >> (4 * t)) & 7;
+            const int c = c_n;
+            const double x = x_n, vnb = v_n, rnb = r_n;
+            if (t < 6) {
+                c_n = (ord >> (4 * t + 4)) & 7;
+                Lc_n = S.Lc[c_n][tid];
+                x_n = __ldg(P.phi_nb[(c_n == cN && fold) ? 7 : c_n] + Lc_n);
+                v_n = __ldg(P.v3D + Lc_n);
+                if (RHO3D) r_n = __ldg(P.rho3d + Lc_n);
+            }
             const bool on = (m_adv >> c) & 1;
             if (c == cC) {
                 posC = on ? pos : dump;
                 pos += on;
                 continue;
             }
-            const int Lc = S.Lc[c][tid];
             const bool mx = (MX >> c) & 1;
-            const double f = upflux(__ldg(P.phi_nb[(c == cN && fold) ? 7 : c] + Lc), mx, up);
+            const double f = upflux(x, mx, up);
             const double p = mx ? f : -f;     // pushed magnitude: ϕ for W,S,B slots of the emitter, -ϕ for E,N,T
-            const double rb = ((RHO3D ? __ldg(P.rho3d + Lc) : P.rho) + rhoC) / 2;
+            const double rb = (rnb + rhoC) / 2;
             // absent entries divide 1/1: a zero / NaN operand would send the whole warp through the
             // slow path of the IEEE division
             const double pn = on ? p : 1.0;
-            const double a = -pn / (on ? rb * __ldg(P.v3D + Lc) : 1.0);
+            const double a = -pn / (on ? rb * vnb : 1.0);
             const double d = pn / (on ? rb * vC : 1.0);
             if (on) {
                 bad |= isnan(a) || isnan(d);
@@ -412,24 +409,43 @@ __global__ void __launch_bounds__(TILE, MINB) k_fused_v4(const __grid_constant__
             double tsW = 0.0, tsE = 0.0, tsS = 0.0, tsN = 0.0;
             bool bad = false;
             int pos = off2, posC = dump;
+            // software pipeline, as in the Tadv walk
+            struct KhIn {
+                int c;
+                double e_own, e_opp, th, d_own, d_opp, v;
+            };
+            auto load_kh = [&](const int t) {
+                KhIn in;
+                in.c = (ord >> (4 * t)) & 7;
+                const int Lc = S.Lc[in.c][tid];
+                const int own = (OWNDIR >> (4 * in.c)) & 3;
+                const int opp = (in.c == cN && fold) ? own : own ^ 2;   // the neighbour's side of the shared face (:407)
+                const int q2 = Lc - k * PP;
+                in.e_own = __ldg(P.edge + own * PP + p2);
+                in.e_opp = __ldg(P.edge + opp * PP + q2);
+                in.th = __ldg(P.thk + Lc);
+                in.d_own = __ldg(P.dnbr + own * PP + p2);
+                in.d_opp = __ldg(P.dnbr + opp * PP + q2);
+                in.v = __ldg(P.v3D + Lc);
+                return in;
+            };
+            KhIn nxt = load_kh(1);
 #pragma unroll 1
             for (int t = 1; t < 6; ++t) {      // T and B sit at both ends of every order word
-                const int c = (ord >> (4 * t)) & 7;
+                const KhIn in = nxt;
+                if (t < 5) nxt = load_kh(t + 1);
+                const int c = in.c;
                 const bool on = (m_kh >> c) & 1;
                 if (c == cC) {
                     posC = on ? pos : dump;
                     pos += on;
                     continue;
                 }
-                const int Lc = S.Lc[c][tid];
-                const int own = (OWNDIR >> (4 * c)) & 3;
-                const int opp = (c == cN && fold) ? own : own ^ 2;   // the neighbour's side of the shared face (:407)
-                const int q2 = Lc - k * PP;
-                const double a_own = thC * __ldg(P.edge + own * PP + p2);
-                const double a_nbr = __ldg(P.thk + Lc) * __ldg(P.edge + opp * PP + q2);
+                const double a_own = thC * in.e_own;
+                const double a_nbr = in.th * in.e_opp;
                 const double ka = on ? P.kH * jl_min(a_own, a_nbr) : 1.0;   // absent: 1/1, see the Tadv walk
-                const double ts = ka / (on ? __ldg(P.dnbr + own * PP + p2) * vC : 1.0);                   // row 𝑗 seen from 𝑗
-                const double tn = ka / (on ? __ldg(P.dnbr + opp * PP + q2) * __ldg(P.v3D + Lc) : 1.0);    // row 𝑖 seen from 𝑖
+                const double ts = ka / (on ? in.d_own * vC : 1.0);     // row 𝑗 seen from 𝑗
+                const double tn = ka / (on ? in.d_opp * in.v : 1.0);   // row 𝑖 seen from 𝑖
                 if (on) {
                     bad |= isnan(ts) || isnan(tn);
                     tsW = c == cW ? ts : tsW;
@@ -605,7 +621,7 @@ int otmb_fused_v4_build(otmb_ctx* c, const otmb_tm_params* prm, int build) {
     P.phi_nb[cB] = P.pt;
     P.phi_nb[7] = P.pn;
     P.rank3d = c->rank3d.as<int>();
-    P.lwet = c->lwet.as<int>();
+    P.lwet = c->lwet.as<int>() + c->h_up;   // the owned cells (all wet cells when unsharded)
     P.kH = prm->kH;
     P.kVML = prm->kVML;
     P.kVdeep = prm->kVdeep;
@@ -613,9 +629,8 @@ int otmb_fused_v4_build(otmb_ctx* c, const otmb_tm_params* prm, int build) {
     P.upwind = prm->upwind;
     P.base = prm->index_base;
     P.build = build;
-    P.w0 = 0;
-    P.opt = getenv("OTMB_V4_OPT") ? atoi(getenv("OTMB_V4_OPT")) : 0;
-    P.ncols = (int)c->N;
+    P.w0 = (int)c->w0;
+    P.ncols = (int)c->ncols;
     P.flags = c->flags.as<DevFlags>();
     const int cap_per_col[5] = {7, 7, 5, 3, 3};
     for (int m = 0; m < 5; ++m) {
@@ -623,8 +638,8 @@ int otmb_fused_v4_build(otmb_ctx* c, const otmb_tm_params* prm, int build) {
         P.rowval[m] = nullptr;
         P.nzval[m] = nullptr;
         if (!(build >> m & 1)) continue;
-        const size_t cap = (size_t)c->N * cap_per_col[m] + 8;
-        CU_TRY(c, c->colptr[m].ensure((size_t)(c->N + 1) * 8));
+        const size_t cap = (size_t)c->ncols * cap_per_col[m] + 8;
+        CU_TRY(c, c->colptr[m].ensure((size_t)(c->ncols + 1) * 8));
         CU_TRY(c, c->rowval[m].ensure(cap * 8));
         CU_TRY(c, c->nzval[m].ensure(cap * 8));
         P.colptr[m] = c->colptr[m].as<i64>();
@@ -632,12 +647,15 @@ int otmb_fused_v4_build(otmb_ctx* c, const otmb_tm_params* prm, int build) {
         P.nzval[m] = c->nzval[m].as<double>();
     }
     static const int variant = getenv("OTMB_V4_VARIANT") ? atoi(getenv("OTMB_V4_VARIANT")) : 0;
-    if (c->have_rho3d) return launch_v4<true, 256, 4>(c, P);
+    if (c->have_rho3d) return launch_v4<true, 384, 2>(c, P);
     switch (variant) {
         case 1: return launch_v4<false, 256, 3>(c, P);
         case 2: return launch_v4<false, 256, 2>(c, P);
         case 3: return launch_v4<false, 128, 8>(c, P);
         case 4: return launch_v4<false, 128, 6>(c, P);
-        default: return launch_v4<false, 256, 4>(c, P);
+        case 5: return launch_v4<false, 512, 2>(c, P);
+        case 7: return launch_v4<false, 512, 1>(c, P);
+        case 8: return launch_v4<false, 256, 4>(c, P);
+        default: return launch_v4<false, 384, 2>(c, P);   // measured best on C2 (profiles/README.md)
     }
 }

@@ -38,6 +38,11 @@ int otmb_transportmatrix_build(otmb_ctx* c, const otmb_tm_params* prm, int64_t n
     if (ops & 2) OT_TRY(otmb_need(c, c->have_phi, "otmb_facefluxes / otmb_set_facefluxes"));
     if (ops & 8) OT_TRY(otmb_need(c, c->have_mlotst, "otmb_set_mlotst"));
     if (c->topo == OTMB_TOPO_UNKNOWN) return otmb_fail(c, OTMB_ERR_UNKNOWN_GRID, otmb_status_string(OTMB_ERR_UNKNOWN_GRID));
+    if (c->sharded) {
+        OT_TRY(otmb_need(c, c->have_rank_offset, "otmb_set_rank_offset"));
+        if (prm->path != OTMB_PATH_FUSED || ops != 30)
+            return otmb_fail(c, OTMB_ERR_BADARG, "a slab context builds all four operators with OTMB_PATH_FUSED");
+    }
     if ((ops & 2) && !c->have_rho3d && prm->rho != prm->rho)
         return otmb_fail(c, OTMB_ERR_RHO_NAN, otmb_status_string(OTMB_ERR_RHO_NAN));
     CU_TRY(c, cudaSetDevice(c->device));
@@ -56,7 +61,7 @@ int otmb_transportmatrix_build(otmb_ctx* c, const otmb_tm_params* prm, int64_t n
     CU_TRY(c, cudaEventRecord(c->ev_b0, c->stream));
     const bool all4 = ops == 30;
     int st = OTMB_OK;
-    if (c->N == 0) {
+    if (c->ncols == 0) {
         // empty ocean: five empty matrices
         for (int m = 0; m < 5; ++m) {
             CU_TRY(c, c->colptr[m].ensure(8));
@@ -104,7 +109,7 @@ int otmb_transportmatrix_build(otmb_ctx* c, const otmb_tm_params* prm, int64_t n
             OT_TRY(otmb_sum_operators(c, prm->index_base));
         }
     }
-    if (!(c->N != 0 && prm->path != OTMB_PATH_COO && all4)) CU_TRY(c, cudaEventRecord(c->ev_b1, c->stream));
+    if (!(c->ncols != 0 && prm->path != OTMB_PATH_COO && all4)) CU_TRY(c, cudaEventRecord(c->ev_b1, c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     CU_TRY(c, cudaEventElapsedTime(&c->last_build_ms, c->ev_b0, c->ev_b1));
     if (nnz_out)
@@ -117,7 +122,7 @@ int otmb_transportmatrix_fetch(otmb_ctx* c, int which, int64_t* colptr, int64_t*
     OT_TRY(otmb_need(c, c->have_mat[which], "otmb_transportmatrix_build"));
     CU_TRY(c, cudaSetDevice(c->device));
     if (colptr)
-        CU_TRY(c, cudaMemcpyAsync(colptr, c->colptr[which].p, (size_t)(c->N + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(c, cudaMemcpyAsync(colptr, c->colptr[which].p, (size_t)(c->ncols + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
     if (rowval && c->nnz[which] > 0)
         CU_TRY(c, cudaMemcpyAsync(rowval, c->rowval[which].p, (size_t)c->nnz[which] * 8, cudaMemcpyDeviceToHost, c->stream));
     if (nzval && c->nnz[which] > 0)
@@ -131,10 +136,10 @@ int otmb_set_operator(otmb_ctx* c, int which, int64_t nnz, const int64_t* colptr
     if (!c || which < 1 || which > 4 || nnz < 0 || !colptr || (nnz > 0 && (!rowval || !nzval))) return OTMB_ERR_BADARG;
     OT_TRY(otmb_need(c, c->have_indices, "otmb_makeindices"));
     CU_TRY(c, cudaSetDevice(c->device));
-    CU_TRY(c, c->colptr[which].ensure((size_t)(c->N + 1) * 8));
+    CU_TRY(c, c->colptr[which].ensure((size_t)(c->ncols + 1) * 8));
     CU_TRY(c, c->rowval[which].ensure((size_t)(nnz + 1) * 8));
     CU_TRY(c, c->nzval[which].ensure((size_t)(nnz + 1) * 8));
-    CU_TRY(c, cudaMemcpyAsync(c->colptr[which].p, colptr, (size_t)(c->N + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(c->colptr[which].p, colptr, (size_t)(c->ncols + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     if (nnz > 0) {
         CU_TRY(c, cudaMemcpyAsync(c->rowval[which].p, rowval, (size_t)nnz * 8, cudaMemcpyHostToDevice, c->stream));
         CU_TRY(c, cudaMemcpyAsync(c->nzval[which].p, nzval, (size_t)nnz * 8, cudaMemcpyHostToDevice, c->stream));
