@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--path", default="fused", choices=["fused", "fused2", "coo"])
+    ap.add_argument("--mode", default="batch", choices=["batch", "sharded"],
+                    help="batch: one matrix per GPU (the contract's weak-scaling line); sharded: ONE matrix k-slab "
+                         "sharded over the GPUs (strong scaling, BASELINE configs[3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -156,7 +159,98 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+def run_sharded(args, rank, local_rank, world):
+    """ONE matrix, k-slab sharded over the ranks (oceantransportmatrixbuilder.jl_b200/sharded.py).  Timed region:
+    the device assembly of every rank's columns, inputs resident; max over ranks."""
+    import otmb_b200.api as A
+    from otmb_b200 import sharded, synthetic
+    from _util import fields
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        ex = sharded.TorchExchange(local_rank)
+    else:
+        ex = sharded.ThreadExchange(sharded.ThreadExchange._Shared(1), 0)
+    oc = synthetic.make_config(args.workload, seed=0)
+    f = fields(oc)
+    ctx0 = A.Context(local_rank)          # geometry of the whole grid (2-D fields + thkcello), computed on this GPU
+    gm = A.makegridmetrics(areacello=f["areacello"], volcello=f["volcello"], lon=f["lon"], lat=f["lat"], lev=f["lev"],
+                           lon_vertices=f["lon_vertices"], lat_vertices=f["lat_vertices"], ctx=ctx0)
+    ctx0.close()
+    t_prep = time.perf_counter()
+    slab, w0, N, info = sharded.prepare_sharded(exchange=ex, gridmetrics=gm, umo=oc.umo, vmo=oc.vmo, FillValue=oc.fill,
+                                                device=local_rank)
+    t_prep = time.perf_counter() - t_prep
+    ctx, lib = slab.ctx, slab.ctx.lib
+    kw = dict(mlotst=oc.mlotst, rho=1035.0, kH=500.0, kVML=0.1, kVdeep=1.0e-5, upwind=True)
+    nnz = slab.build(**kw)
+
+    def barrier():
+        ctx.check(lib.otmb_synchronize(ctx.h))
+        if dist is not None:
+            import torch
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    for _ in range(max(args.warmup, 3)):
+        slab.build(upload=False, **kw)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    barrier()
+    launches0 = ctx.launches()
+    kernel_ms = []
+    t0 = time.perf_counter()
+    ctx.check(lib.otmb_timer_start(ctx.h))
+    for _ in range(args.steps):
+        slab.build(upload=False, **kw)
+        kernel_ms.append(ctx.last_build_ms())
+    ms = C.c_float()
+    ctx.check(lib.otmb_timer_stop(ctx.h, C.byref(ms)))
+    barrier()
+    t1 = time.perf_counter()
+    clocks = sampler.stop(t0, t1)
+    launches = ctx.launches() - launches0
+    ms_per_step, k_ms = float(ms.value) / args.steps, sum(kernel_ms) / len(kernel_ms)
+    nx, ny, nz = gm.v3D.shape
+    P, M = nx * ny, gm.v3D.size
+    rows = ex.allgather_ints([int(ms_per_step * 1e6), int(k_ms * 1e6), launches, slab.n_owned] + list(nnz))
+    if rank == 0:
+        ms_per_step = max(r[0] for r in rows) / 1e6
+        k_ms = max(r[1] for r in rows) / 1e6
+        launches = sum(r[2] for r in rows)
+        nnz_tot = [sum(r[4 + m] for r in rows) for m in range(5)]
+        b_in, b_out = algorithmic_bytes(M, P, nz, N, nnz_tot)
+        peak, peak_src = hbm_peak()
+        # per-GPU roofline of the slowest rank: its share of the algorithmic bytes / its kernel time
+        slow = max(range(world), key=lambda r: rows[r][1])
+        k0, k1 = info["slabs"][slow]
+        b_rank = 8 * 7 * P * (k1 - k0) + 8 * 10 * P + sum(8 * (rows[slow][3] + 1) + 16 * rows[slow][4 + m] for m in range(5))
+        achieved = b_rank / (k_ms / 1e3) / 1e9
+        line = {
+            "metric": "T assembly throughput, ONE matrix k-slab sharded (adv+kH+kVML+kVdeep)", "value": nnz_tot[0] / (ms_per_step / 1e3),
+            "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload} {nx}x{ny}x{nz} {oc.topology}, one matrix set (T, Tadv, TkH, TkVML, TkVdeep) "
+                                   f"k-slab sharded over {world} GPU(s)", "N_wet": N, "nnz": dict(zip(A.MATRICES, nnz_tot)),
+                       "slabs": info["slabs"], "wet_per_rank": info["counts"],
+                       "parallelism": f"k-slab x{world}; NCCL only for the face-flux carry planes (setup, not in the timed region)",
+                       "l2": "no flush: per-step working set >> 126 MB L2", "prepare_s": t_prep},
+            "kernel_ms": k_ms,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes": b_in + b_out, "algorithmic_bytes_slowest_rank": b_rank,
+                         "kernel": "k_fused_v4 (slowest rank's slab)"},
+            "clocks": clocks, "gpu_launches": launches,
+        }
+        emit(line)
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 def pinned(lib, shape, dtype):
@@ -170,13 +264,34 @@ def pinned(lib, shape, dtype):
     return a, ptr
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract goes to the real stdout; everything else any library prints
+    (NCCL banners, warnings) was redirected to stderr at start-up."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.mode == "sharded":
+        run_sharded(args, rank, local_rank, world)
         return
 
     dist = None
@@ -307,7 +422,8 @@ def main():
         "metric": METRIC, "value": nnzT_total / (ms_per_step / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload} 360x300x50 tripolar (ACCESS-ESM1-5 1deg shape), advection + kH/kVML/kVdeep, "
+        "config": {"workload": f"{args.workload} {'x'.join(map(str, gm.v3D.shape))} {oc.topology}"
+                               f"{' (ACCESS-ESM1-5 1deg shape)' if args.workload == 'C2' else ''}, advection + kH/kVML/kVdeep, "
                                "five CSC matrices (T, Tadv, TkH, TkVML, TkVdeep)",
                    "path": args.path, "N_wet": N, "nnz": dict(zip(A.MATRICES, nnz_list)),
                    "parallelism": f"batch: one matrix per GPU x{world}, no collective",
@@ -315,7 +431,7 @@ def main():
         "kernel_ms": k_ms,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": b_in + b_out,
-                     "kernel": "k_fused<2> (whole transportmatrix in one launch)" if args.path == "fused" else args.path,
+                     "kernel": "k_fused_v4 (whole transportmatrix in one launch)" if args.path == "fused" else args.path,
                      "t_only_frac": ((b_in + 8 * (N + 1) + 16 * nnz_list[0]) / (k_ms / 1e3) / 1e9) / peak},
         "clocks": clocks,
         "gpu_launches": launches,
@@ -332,7 +448,7 @@ def main():
         line["cpu_baseline"] = {"value": otm["T"].nnz / otm["seconds"], "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": "1 full C2 matrix (360x300x50), oracle/otmb_oracle.cpp single thread "
                                           f"({otm['seconds']:.2f} s); host has {os.cpu_count()} cores; no Julia in image"}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -204,21 +204,32 @@ class CudaSlab:
         ptrs = (C.c_void_p * 6)(*[a.ctypes.data for a in arrs])
         self.ctx.check(self.lib.otmb_set_facefluxes(self.ctx.h, ptrs))
 
-    def transportmatrix(self, mlotst, rho, kH, kVML, kVdeep, upwind):
+    def build(self, mlotst, rho, kH, kVML, kVdeep, upwind, upload=True):
+        """Device assembly of this slab's columns; returns the five nnz.  upload=False re-runs the
+        kernel on the resident inputs (benchmark loop)."""
         lib, ctx = self.lib, self.ctx
-        ctx.check(lib.otmb_set_mlotst(ctx.h, A._ptr(A._f64(mlotst))))
-        ctx.check(lib.otmb_set_rho3d(ctx.h, None if np.isscalar(rho) else A._ptr(A._f64(rho))))
+        if upload:
+            ctx.check(lib.otmb_set_mlotst(ctx.h, A._ptr(A._f64(mlotst))))
+            ctx.check(lib.otmb_set_rho3d(ctx.h, None if np.isscalar(rho) else A._ptr(A._f64(rho))))
         prm = _L.TMParams(float(kH), float(kVML), float(kVdeep), float(rho) if np.isscalar(rho) else 0.0, int(bool(upwind)), 0,
                           _L.PATH["fused"], 0)
         nnz = (C.c_int64 * 5)()
         ctx.check(lib.otmb_transportmatrix_build(ctx.h, C.byref(prm), nnz))
+        self.nnz = [int(x) for x in nnz]
+        return self.nnz
+
+    def fetch(self):
         out = {}
         for m, name in enumerate(MATS):
             cp = np.empty(self.n_owned + 1, np.int64)
-            rv, nz = np.empty(nnz[m], np.int64), np.empty(nnz[m], np.float64)
-            ctx.check(lib.otmb_transportmatrix_fetch(ctx.h, m, A._ptr(cp), A._ptr(rv), A._ptr(nz)))
+            rv, nz = np.empty(self.nnz[m], np.int64), np.empty(self.nnz[m], np.float64)
+            self.ctx.check(self.lib.otmb_transportmatrix_fetch(self.ctx.h, m, A._ptr(cp), A._ptr(rv), A._ptr(nz)))
             out[name] = (cp, rv, nz)
         return out
+
+    def transportmatrix(self, mlotst, rho, kH, kVML, kVdeep, upwind):
+        self.build(mlotst, rho, kH, kVML, kVdeep, upwind)
+        return self.fetch()
 
 
 # ------------------------------------------------------------------------------------------
@@ -239,12 +250,9 @@ class ShardedCSC:
         return len(self.colptr) - 1
 
 
-def transportmatrix_sharded(*, exchange, gridmetrics, mlotst, ρ, umo=None, vmo=None, FillValue=None, ϕ=None, κH=500.0,
-                            κVML=0.1, κVdeep=1.0e-5, upwind=True, slab_factory=CudaSlab, device=0, gather=True):
-    """transportmatrix (src/matrixbuilding.jl:128-150) for ONE matrix sharded over exchange.size ranks.
-    Pass either (umo, vmo, FillValue) — facefluxes run sharded too — or a precomputed ϕ.
-    Returns (TransportMatrices of scipy CSC on rank 0 / None elsewhere when gather=True, dict of
-    ShardedCSC segments, info)."""
+def prepare_sharded(*, exchange, gridmetrics, umo=None, vmo=None, FillValue=None, ϕ=None, slab_factory=CudaSlab, device=0):
+    """Steps 1-2 of the sharded assembly: slab plan, wet-rank offsets, metrics, face fluxes (chained
+    continuity scan).  Returns (slab, w0, N, info); the slab is ready for build()."""
     ex = exchange
     v3D = gridmetrics.v3D
     nx, ny, nz = v3D.shape
@@ -274,6 +282,18 @@ def transportmatrix_sharded(*, exchange, gridmetrics, mlotst, ρ, umo=None, vmo=
         flags = ex.allgather_ints([int(vu), int(vv)])
         if not any(f[0] for f in flags) or not any(f[1] for f in flags):
             raise A.OTMBError(_L.ERR_ALL_FILL, "AssertionError: all umo/vmo values are NaN or FillValue")
+    return slab, w0, N, dict(slabs=slabs, counts=counts, N=N)
+
+
+def transportmatrix_sharded(*, exchange, gridmetrics, mlotst, ρ, umo=None, vmo=None, FillValue=None, ϕ=None, κH=500.0,
+                            κVML=0.1, κVdeep=1.0e-5, upwind=True, slab_factory=CudaSlab, device=0, gather=True):
+    """transportmatrix (src/matrixbuilding.jl:128-150) for ONE matrix sharded over exchange.size ranks.
+    Pass either (umo, vmo, FillValue) — facefluxes run sharded too — or a precomputed ϕ.
+    Returns (TransportMatrices of scipy CSC on rank 0 / None elsewhere when gather=True, dict of
+    ShardedCSC segments, info)."""
+    ex = exchange
+    slab, w0, N, info = prepare_sharded(exchange=ex, gridmetrics=gridmetrics, umo=umo, vmo=vmo, FillValue=FillValue, ϕ=ϕ,
+                                        slab_factory=slab_factory, device=device)
 
     # 3. this rank's columns
     local = slab.transportmatrix(mlotst, ρ, κH, κVML, κVdeep, upwind)
@@ -285,7 +305,7 @@ def transportmatrix_sharded(*, exchange, gridmetrics, mlotst, ρ, umo=None, vmo=
         cp, rv, nzv = local[name]
         off = sum(nnz_all[r][m] for r in range(ex.rank))
         segs[name] = ShardedCSC(N, w0, cp + off, rv, nzv)
-    info = dict(slabs=slabs, counts=counts, nnz=nnz_all, N=N)
+    info.update(nnz=nnz_all)
 
     full = None
     if gather:

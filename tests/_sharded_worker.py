@@ -18,12 +18,21 @@ from _sharded_double import NAMES, OracleSlab, oracle_gridmetrics
 
 
 def main():
-    dist.init_process_group("gloo")
-    ex = sharded.TorchExchange()
-    oc = synthetic.make_ocean(14, 10, 7, "tripolar", seed=3, land_frac=0.25)
+    backend = os.environ.get("OTMB_SHARDED_BACKEND", "gloo")     # "nccl": the CUDA slab path, one GPU per rank
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if backend == "nccl":
+        import torch
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        factory, shape = sharded.CudaSlab, (90, 45, 20)
+    else:
+        dist.init_process_group("gloo")
+        factory, shape = OracleSlab, (14, 10, 7)
+    ex = sharded.TorchExchange(local_rank if backend == "nccl" else None)
+    oc = synthetic.make_ocean(*shape, "tripolar", seed=3, land_frac=0.25)
     gm = oracle_gridmetrics(oc)
     full, segs, info = sharded.transportmatrix_sharded(exchange=ex, gridmetrics=gm, mlotst=oc.mlotst, ρ=1035.0, umo=oc.umo,
-                                                       vmo=oc.vmo, FillValue=oc.fill, slab_factory=OracleSlab)
+                                                       vmo=oc.vmo, FillValue=oc.fill, slab_factory=factory, device=local_rank)
     assert sum(info["counts"]) == info["N"] and len(info["slabs"]) == ex.size
     assert segs["T"].col0 == sum(info["counts"][:ex.rank])
     if ex.rank == 0:
@@ -35,7 +44,7 @@ def main():
             g, w = getattr(full, name), want[oname]
             assert np.array_equal(g.indptr + 1, w.colptr) and np.array_equal(g.indices + 1, w.rowval), name
             assert np.array_equal(g.data.view(np.int64), w.nzval.view(np.int64)), name
-        print(f"SHARDED-GLOO-OK ranks={ex.size} slabs={info['slabs']} counts={info['counts']}")
+        print(f"SHARDED-{backend.upper()}-OK ranks={ex.size} slabs={info['slabs']} counts={info['counts']}")
     else:
         assert full is None
     dist.barrier()
