@@ -181,6 +181,18 @@ int otmb_triad_derivative(otmb_ctx* ctx, const double* chi, int dir, double* out
 int otmb_dyad_derivative(otmb_ctx* ctx, const double* chi, double* out);
 int otmb_bolus_gm_velocity(otmb_ctx* ctx, const double* rho, double kGM, double maxslope, double* u, double* v);
 
+/* velocity <-> mass flux on the C-grid, needs the resident thkcello / edge lengths:
+ * velocity2fluxes src/velocities.jl:10-39 (ϕᵢ = u·ρ̄·min(thk)·edge_east, ϕⱼ = v·ρ̄·min(thk)·edge_north, NaN-aware
+ * two-cell mean / min :81-108), fluxes2velocity :50-74 (the inverse).  All arrays (nx,ny,nz); rho3d may be
+ * NULL (scalar rho).  Tripolar grids only: on bipolar grids the reference indexes a missing neighbour and throws.
+ * otmb_bgrid_to_cgrid: the B-grid (NE corner) branch of interpolateontodefaultCgrid,
+ * src/gridcellgeometry.jl:118-128; the Arakawa-grid detection (:50-95, one cell) stays on the host. */
+int otmb_velocity2fluxes(otmb_ctx* ctx, const double* u, const double* v, const double* rho3d, double rho,
+                         double* phi_i, double* phi_j);
+int otmb_fluxes2velocity(otmb_ctx* ctx, const double* phi_i, const double* phi_j, const double* rho3d, double rho,
+                         double* u, double* v);
+int otmb_bgrid_to_cgrid(otmb_ctx* ctx, const double* u, const double* v, double fill_value, double* u2, double* v2);
+
 /* measurement helpers: CUDA events on the ctx stream (the stream every kernel of this
  * library is launched on), an L2 flush, and per-kernel launch counting. */
 int otmb_timer_start(otmb_ctx* ctx);

@@ -8,8 +8,10 @@ from .api import (  # noqa: F401
     Context, Field, FaceFluxes, GridMetrics, GridTopology, Indices, OTMBError, TransportMatrices,
     bolus_GM_velocity, default_context, facefluxes, facefluxesfrommasstransport, getgridtopology,
     globalverticaldyadderivative, globalverticalfacetriadderivative, makegridmetrics, makeindices,
-    spadd, sparse, transportmatrix, vertexpermutation,
+    spadd, sparse, transportmatrix, vertexpermutation, velocity2fluxes, fluxes2velocity, facefluxesfromvelocities,
+    getarakawagrid, interpolateontodefaultCgrid,
 )
 from . import synthetic  # noqa: F401
 
-__all__ = ["makegridmetrics", "makeindices", "facefluxesfrommasstransport", "transportmatrix"]
+__all__ = ["makegridmetrics", "makeindices", "facefluxesfrommasstransport", "facefluxesfromvelocities", "velocity2fluxes",
+           "fluxes2velocity", "transportmatrix"]        # the reference's exports, src/OceanTransportMatrixBuilder.jl:31-36

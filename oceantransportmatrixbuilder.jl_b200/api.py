@@ -356,6 +356,107 @@ def transportmatrix(*, ϕ, mlotst, gridmetrics, indices, ρ, κH=500.0, κVML=0.
     return TransportMatrices(*out)
 
 
+# ---- velocities <-> mass fluxes (src/velocities.jl:10-108, 140-151; src/gridcellgeometry.jl:50-140) ----------
+def _haversine_host(p, q, radius=6371000.0):
+    """Distances.haversine on two (lon, lat) points in degrees — host side, used only to classify ONE cell."""
+    import math
+    dlon, dlat = math.radians(q[0] - p[0]), math.radians(q[1] - p[1])
+    a = math.sin(dlat / 2) ** 2 + math.cos(math.radians(p[1])) * math.cos(math.radians(q[1])) * math.sin(dlon / 2) ** 2
+    return 2 * (radius * math.asin(min(math.sqrt(a), 1.0)))
+
+
+def _midpointonsphere(A_, B_):
+    """src/gridcellgeometry.jl:249-255."""
+    if abs(A_[0] - B_[0]) < 180:
+        return ((A_[0] + B_[0]) / 2, (A_[1] + B_[1]) / 2)
+    return ((A_[0] + B_[0]) / 2 + 180, (A_[1] + B_[1]) / 2)
+
+
+ArakawaGrid = namedtuple("ArakawaGrid", "kind u_pos v_pos")
+
+
+def getarakawagrid(u_lon, u_lat, v_lon, v_lat, gridmetrics) -> ArakawaGrid:
+    """getarakawagrid, src/gridcellgeometry.jl:50-95: where the velocity points of cell (1,1) sit."""
+    lon, lat, lonv, latv = gridmetrics.lon, gridmetrics.lat, gridmetrics.lon_vertices, gridmetrics.lat_vertices
+    u_point, v_point = (float(u_lon[0, 0]), float(u_lat[0, 0])), (float(v_lon[0, 0]), float(v_lat[0, 0]))
+    cell = {"C": (float(lon[0, 0]), float(lat[0, 0]))}
+    for q, name in enumerate(("SW", "SE", "NE", "NW")):
+        cell[name] = (float(lonv[q, 0, 0]), float(latv[q, 0, 0]))
+    cell["S"] = _midpointonsphere(cell["SW"], cell["SE"])
+    cell["N"] = _midpointonsphere(cell["NE"], cell["NW"])
+    cell["W"] = _midpointonsphere(cell["SW"], cell["NW"])
+    cell["E"] = _midpointonsphere(cell["SE"], cell["NE"])
+    u_pos = min(cell, key=lambda k: _haversine_host(cell[k], u_point))      # findmin keeps the first minimum
+    v_pos = min(cell, key=lambda k: _haversine_host(cell[k], v_point))
+    if u_pos == v_pos == "C":
+        return ArakawaGrid("A", u_pos, v_pos)
+    if u_pos == v_pos and u_pos in ("NE", "NW", "SE", "SW"):
+        return ArakawaGrid("B", u_pos, v_pos)
+    if u_pos in ("E", "W") and v_pos in ("N", "S"):
+        return ArakawaGrid("C", u_pos, v_pos)
+    raise OTMBError(_L.ERR_BADARG, "Unknown Arakawa grid type")
+
+
+def interpolateontodefaultCgrid(u, u_lon, u_lat, v, v_lon, v_lat, gridmetrics, ctx=None):
+    """interpolateontodefaultCgrid, src/gridcellgeometry.jl:103-140.  Returns (u, u_lon, u_lat, v, v_lon, v_lat)."""
+    grid = getarakawagrid(np.asarray(u_lon), np.asarray(u_lat), np.asarray(v_lon), np.asarray(v_lat), gridmetrics)
+    if grid.kind == "C":
+        return u, u_lon, u_lat, v, v_lon, v_lat
+    if grid.kind == "A":
+        raise OTMBError(_L.ERR_BADARG, "Interpolation not implemented for A-grid type")
+    if not (grid.u_pos == grid.v_pos == "NE"):
+        raise OTMBError(_L.ERR_BADARG, f"Interpolation not implemented for this B-grid({grid.u_pos},{grid.v_pos}) type")
+    fill = u.properties["_FillValue"]
+    ctx = _ctx_of(gridmetrics.v3D, ctx=ctx)
+    _ensure_grid(ctx, gridmetrics)
+    ua, va = _f64(_data(u)), _f64(_data(v))
+    u2, v2 = np.empty_like(ua), np.empty_like(va)
+    ctx.check(ctx.lib.otmb_bgrid_to_cgrid(ctx.h, _ptr(ua), _ptr(va), float(fill), _ptr(u2), _ptr(v2)))
+    lonv, latv = gridmetrics.lon_vertices, gridmetrics.lat_vertices
+    mid = np.vectorize(lambda a0, a1, b0, b1: _midpointonsphere((a0, a1), (b0, b1)))
+    u2_lon, u2_lat = mid(lonv[2], latv[2], lonv[1], latv[1])        # midpoints of the east side (NE, SE)
+    v2_lon, v2_lat = mid(lonv[3], latv[3], lonv[2], latv[2])        # midpoints of the north side (NW, NE)
+    return u2, u2_lon, u2_lat, v2, v2_lon, v2_lat
+
+
+def _vel_common(gridmetrics, ctx):
+    ctx = _ctx_of(gridmetrics.v3D, ctx=ctx)
+    _ensure_z(ctx, gridmetrics)          # thkcello and edge lengths resident
+    return ctx
+
+
+def velocity2fluxes(u, u_lon, u_lat, v, v_lon, v_lat, gridmetrics, ρ, ctx=None):
+    """velocity2fluxes, src/velocities.jl:10-39."""
+    ctx = _vel_common(gridmetrics, ctx)
+    u, _, _, v, _, _ = interpolateontodefaultCgrid(u, u_lon, u_lat, v, v_lon, v_lat, gridmetrics, ctx=ctx)
+    ua, va = _f64(_data(u)), _f64(_data(v))
+    pi, pj = np.empty_like(ua), np.empty_like(va)
+    rho3 = None if np.isscalar(ρ) else _f64(_data(ρ))
+    ctx.check(ctx.lib.otmb_velocity2fluxes(ctx.h, _ptr(ua), _ptr(va), _ptr(rho3), float(ρ) if np.isscalar(ρ) else 0.0,
+                                           _ptr(pi), _ptr(pj)))
+    return pi, pj
+
+
+def fluxes2velocity(ϕᵢ, ϕⱼ, gridmetrics, ρ, ctx=None):
+    """fluxes2velocity, src/velocities.jl:50-74."""
+    ctx = _vel_common(gridmetrics, ctx)
+    pi, pj = _f64(_data(ϕᵢ)), _f64(_data(ϕⱼ))
+    u, v = np.empty_like(pi), np.empty_like(pj)
+    rho3 = None if np.isscalar(ρ) else _f64(_data(ρ))
+    ctx.check(ctx.lib.otmb_fluxes2velocity(ctx.h, _ptr(pi), _ptr(pj), _ptr(rho3), float(ρ) if np.isscalar(ρ) else 0.0,
+                                           _ptr(u), _ptr(v)))
+    return u, v
+
+
+def facefluxesfromvelocities(*, uo, uo_lon, uo_lat, vo, vo_lon, vo_lat, gridmetrics, indices, ρ, ctx=None) -> FaceFluxes:
+    """facefluxesfromvelocities, src/velocities.jl:140-151."""
+    fill = uo.properties["_FillValue"]
+    fv = vo.properties["_FillValue"]
+    assert (fill == fv) or (fill != fill and fv != fv), "AssertionError: isequal(FillValue, vo.properties[\"_FillValue\"])"
+    umo, vmo = velocity2fluxes(uo, uo_lon, uo_lat, vo, vo_lon, vo_lat, gridmetrics, ρ, ctx=ctx)
+    return facefluxes(umo, vmo, gridmetrics, indices, FillValue=fill, ctx=ctx)
+
+
 # ---- Redi/GM helpers (experimental and non-exported in the reference) -------------------------
 def _ensure_z(ctx, gridmetrics):
     _ensure_grid(ctx, gridmetrics)
