@@ -10,7 +10,8 @@ module OceanTransportMatrixBuilderB200
 
 using SparseArrays
 
-export makegridmetrics, makeindices, facefluxesfrommasstransport, transportmatrix
+export makegridmetrics, makeindices, facefluxesfrommasstransport, facefluxesfromvelocities, velocity2fluxes,
+       fluxes2velocity, transportmatrix
 
 const LIBOTMB = get(ENV, "LIBOTMB", joinpath(@__DIR__, "..", "libotmb.so"))
 
@@ -112,7 +113,11 @@ end
 function facefluxesfrommasstransport(; umo, vmo, gridmetrics, indices)
     FillValue = umo.properties["_FillValue"]
     @assert isequal(FillValue, vmo.properties["_FillValue"])
-    u = umo |> Array{Float64}; v = vmo |> Array{Float64}
+    return facefluxes(umo |> Array{Float64}, vmo |> Array{Float64}, gridmetrics, indices; FillValue)
+end
+
+"facefluxes (+ nofluxboundaries!), src/velocities.jl:154-255; umo / vmo are not modified"
+function facefluxes(u::Array{Float64, 3}, v::Array{Float64, 3}, gridmetrics, indices; FillValue)
     c = ctx()
     east = similar(u); west = similar(u); north = similar(u); south = similar(u); top = similar(u); bottom = similar(u)
     check(c, ccall((:otmb_facefluxes, LIBOTMB), Cint,
@@ -169,6 +174,34 @@ function transportmatrix(; ϕ, mlotst, gridmetrics, indices, ρ, κH = 500.0, κ
     TκVML = isnothing(TκVML) ? fetch(3) : TκVML
     TκVdeep = isnothing(TκVdeep) ? fetch(4) : TκVdeep
     return (; T, Tadv, TκH, TκVML, TκVdeep)
+end
+
+# ---- velocities <-> mass fluxes (src/velocities.jl:10-108, 140-151).  The Arakawa-grid detection and the
+# C/A/B dispatch of interpolateontodefaultCgrid (src/gridcellgeometry.jl:50-140) are host work on one cell and
+# keep their Julia code; only the B-grid stencil and the per-cell conversion run on the GPU.
+function bgrid_to_cgrid(u::Array{Float64, 3}, v::Array{Float64, 3}, fill)
+    c = ctx(); u2 = similar(u); v2 = similar(v)
+    check(c, ccall((:otmb_bgrid_to_cgrid, LIBOTMB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}, Ptr{Float64}),
+                   c.h, u, v, fill, u2, v2))
+    return u2, v2
+end
+function _velflux(sym, a::Array{Float64, 3}, b::Array{Float64, 3}, ρ)
+    c = ctx(); oa = similar(a); ob = similar(b)
+    ρ3 = ρ isa Number ? Ptr{Float64}(C_NULL) : pointer(ρ)
+    GC.@preserve ρ check(c, ccall((sym, LIBOTMB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}, Ptr{Float64}),
+                                  c.h, a, b, ρ3, ρ isa Number ? Float64(ρ) : 0.0, oa, ob))
+    return oa, ob
+end
+function velocity2fluxes(u, u_lon, u_lat, v, v_lon, v_lat, gridmetrics, ρ)          # src/velocities.jl:10-39
+    u, _, _, v, _, _ = interpolateontodefaultCgrid(u, u_lon, u_lat, v, v_lon, v_lat, gridmetrics)   # host dispatch, B-grid -> bgrid_to_cgrid
+    return _velflux(:otmb_velocity2fluxes, Array{Float64}(u), Array{Float64}(v), ρ)
+end
+fluxes2velocity(ϕᵢ, ϕⱼ, gridmetrics, ρ) = _velflux(:otmb_fluxes2velocity, Array{Float64}(ϕᵢ), Array{Float64}(ϕⱼ), ρ)   # :50-74
+function facefluxesfromvelocities(; uo, uo_lon, uo_lat, vo, vo_lon, vo_lat, gridmetrics, indices, ρ)   # :140-151
+    FillValue = uo.properties["_FillValue"]
+    @assert isequal(FillValue, vo.properties["_FillValue"])
+    umo, vmo = velocity2fluxes(uo, uo_lon, uo_lat, vo, vo_lon, vo_lat, gridmetrics, ρ)
+    return facefluxes(umo, vmo, gridmetrics, indices; FillValue)
 end
 
 end # module
