@@ -65,7 +65,7 @@ struct V4Params {
     const int* rank3d;   // (M) global wet rank, -1 = dry
     const int* lwet;     // (ncols) linear index of the launch's wet cells
     double kH, kVML, kVdeep, rho;
-    int upwind, base, build;
+    int upwind, base, build, prefetch;
     int ntiles;
     int w0;              // global wet rank of the launch's first column
     int ncols;
@@ -76,8 +76,13 @@ struct V4Params {
     u64* tile_state;
 };
 
-__device__ __forceinline__ u64 ld_vol(const u64* p) { return *reinterpret_cast<const volatile u64*>(p); }
-__device__ __forceinline__ void st_vol(u64* p, u64 v) { *reinterpret_cast<volatile u64*>(p) = v; }
+// look-back descriptors: device-scope relaxed accesses (a plain `volatile` access is system scope)
+__device__ __forceinline__ u64 ld_vol(const u64* p) {
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_vol(u64* p, u64 v) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
 __device__ __forceinline__ u64 warp_sum64(u64 v) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
@@ -87,6 +92,7 @@ __device__ __forceinline__ double upflux(double x, bool take_max, bool up) {
     return up ? (take_max ? jl_max(x, 0.0) : jl_min(x, 0.0)) : x / 2;
 }
 __device__ __forceinline__ bool nz(double f) { return f > 0 || f < 0; }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int TILE>
 struct Smem {
@@ -95,20 +101,80 @@ struct Smem {
     int row[TILE / 32][WCAP];      // warp-private staging: row indices (+ index base)
     int Lc[7][TILE];               // linear index of candidate c (clamped to a valid cell)
     int rk[7][TILE];               // row index (+ index base) of candidate c
-    u64 warp[TILE / 32];
+    u64 lexcl[TILE];               // in-warp exclusive offsets of the column, five 12-bit fields
+    u64 warp[TILE / 32];           // entries of each warp, five 12-bit fields
+    u64 wbase[TILE / 32];          // in-tile offset of each warp
     u64 excl[5];
 };
 
 // ---------------------------------------------------------------------------------------
 template <bool RHO3D, int TILE, int MINB>
 // __grid_constant__: P is indexed dynamically and its address is taken by the generic branch
-__global__ void __launch_bounds__(TILE, MINB) k_fused_v4(const __grid_constant__ V4Params P) {
-    constexpr int NW = TILE / 32;
+__global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_constant__ V4Params P) {
+    constexpr int NW = TILE / 32;   // column warps; warp NW is the scan warp
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem<TILE>& S = *reinterpret_cast<Smem<TILE>*>(smem_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int tile = blockIdx.x;
+
+    // ================= the scan warp: decoupled look-back for all five counters =================
+    // It owns no columns, so the column warps never wait for a warp that still has values to compute:
+    // by the time they reach the second barrier the offsets have long been resolved.
+    if (wid == NW) {
+        // producer / consumer named barriers: the column warps only ARRIVE at barrier 1 (no wait) once their
+        // counts are in S.warp; the scan warp only arrives at barrier 2 once the offsets are in S.excl
+        asm volatile("bar.sync 1, %0;" ::"r"(TILE + 32) : "memory");
+        u64 total = 0;
+#pragma unroll
+        for (int q = 0; q < NW; ++q) total += *reinterpret_cast<volatile u64*>(&S.warp[q]);
+        if (lane < 5) st_vol(P.tile_state + (size_t)tile * 8 + lane, (tile == 0 ? ST_PRE : ST_AGG) | ((total >> (12 * lane)) & 0xfffull));
+        u64 excl[5] = {0, 0, 0, 0, 0};
+        unsigned pending = tile > 0 ? 31u : 0u;   // counters still looking back
+        int look = tile - 1;
+        while (pending) {
+            const int t = look - lane;
+            u64 wv[5];
+#pragma unroll
+            for (int m = 0; m < 5; ++m) wv[m] = t >= 0 ? 0ull : ST_PRE;   // before the first tile: prefix 0
+            bool again;
+            do {   // the five descriptors of a tile share a 64-byte line; all loads are issued before any is tested
+#pragma unroll
+                for (int m = 0; m < 5; ++m)
+                    if ((pending >> m & 1) && (wv[m] >> 62) == 0) wv[m] = ld_vol(P.tile_state + (size_t)t * 8 + m);
+                again = false;
+#pragma unroll
+                for (int m = 0; m < 5; ++m) again |= (pending >> m & 1) && (wv[m] >> 62) == 0;
+            } while (__any_sync(0xffffffffu, again));
+#pragma unroll
+            for (int m = 0; m < 5; ++m) {
+                if (!(pending >> m & 1)) continue;
+                const u64 val = wv[m] & ST_MASK;
+                const unsigned pm = __ballot_sync(0xffffffffu, (wv[m] >> 62) == 2);
+                if (pm) {
+                    const int first = __ffs(pm) - 1;
+                    excl[m] += warp_sum64(lane <= first ? val : 0ull);
+                    pending &= ~(1u << m);
+                } else {
+                    excl[m] += warp_sum64(val);
+                }
+            }
+            look -= 32;
+        }
+        const u64 mine = lane == 0 ? excl[0] : lane == 1 ? excl[1] : lane == 2 ? excl[2] : lane == 3 ? excl[3] : excl[4];
+        if (lane < 5) {
+            const u64 agg = (total >> (12 * lane)) & 0xfffull;
+            if (tile > 0) st_vol(P.tile_state + (size_t)tile * 8 + lane, ST_PRE | (mine + agg));
+            S.excl[lane] = mine;
+            if (tile == P.ntiles - 1) {
+                P.flags->nnz[lane] = mine + agg;
+                if (P.build >> lane & 1) P.colptr[lane][P.ncols] = (i64)(mine + agg) + P.base;
+            }
+        }
+        __threadfence_block();
+        asm volatile("bar.arrive 2, %0;" ::"r"(TILE + 32) : "memory");   // S.excl published
+        return;
+    }
     const GridDims g = P.g;
     const int PP = g.P;
     const int w = tile * TILE + tid;       // column of this launch
@@ -142,6 +208,24 @@ __global__ void __launch_bounds__(TILE, MINB) k_fused_v4(const __grid_constant__
         Lc[cW] = seamW ? L + (g.nx - 1) : L - 1;
         Lc[cE] = seamE ? L - (g.nx - 1) : L + 1;
         Lc[cN] = (j < g.ny - 1) ? L + g.nx : (fold ? L + (g.nx - 1 - 2 * i) : L);
+        // ---- L2 prefetch one level ahead.  Tiles sweep the wet cells level by level, so the lines of level
+        // k+1 (k+2 for what is read at the bottom neighbour) are what the tiles one sweep-window later will
+        // demand; asking for them now turns those DRAM-latency loads into L2 hits.  Ocean columns are wet
+        // from the surface down, so a wet cell at k+1 always has this wet cell above it to do the asking.
+        if (P.prefetch && hasB) {
+            const int L1 = L + PP;
+            prefetch_l2(P.pe + L1);
+            prefetch_l2(P.pw + L1);
+            prefetch_l2(P.pn + L1);
+            prefetch_l2(P.ps + L1);
+            prefetch_l2(P.pb + L1);
+            prefetch_l2(P.thk + L1);
+            if (RHO3D) prefetch_l2(P.rho3d + L1);
+            const int L2 = k < g.nz - 2 ? L1 + PP : L1;
+            prefetch_l2(P.pt + L2);
+            prefetch_l2(P.v3D + L2);
+            prefetch_l2(P.rank3d + L2);
+        }
         // ---- loads: neighbour ranks, the six face fluxes the neighbours carry, mixed-layer inputs
         const int qT = __ldg(P.rank3d + Lc[cT]), qS = __ldg(P.rank3d + Lc[cS]), qW = __ldg(P.rank3d + Lc[cW]),
                   qE = __ldg(P.rank3d + Lc[cE]), qN = __ldg(P.rank3d + Lc[cN]), qB = __ldg(P.rank3d + Lc[cB]);
@@ -230,52 +314,11 @@ __global__ void __launch_bounds__(TILE, MINB) k_fused_v4(const __grid_constant__
         if (lane >= d) incl += o;
     }
     if (lane == 31) S.warp[wid] = incl;
-    const u64 lane_excl = incl - packed;                       // in-warp exclusive offsets of this column
-    const u64 warp_tot = __shfl_sync(0xffffffffu, incl, 31);   // entries of this warp, per matrix
-    __syncthreads();
-    u64 wbase = 0, total = 0;                                  // in-tile offset of this warp, tile totals
-#pragma unroll
-    for (int q = 0; q < NW; ++q) {
-        const u64 sw = S.warp[q];
-        if (q < wid) wbase += sw;
-        total += sw;
-    }
-    if (wid < (NW < 5 ? NW : 5)) {   // one warp per counter; the other warps go straight to the values
-        for (int m = wid; m < 5; m += NW) {
-            const u64 agg = (total >> (12 * m)) & 0xfffull;
-            if (lane == 0) st_vol(P.tile_state + (size_t)tile * 8 + m, (tile == 0 ? ST_PRE : ST_AGG) | agg);
-            u64 excl = 0;
-            if (tile > 0) {
-                int look = tile - 1;
-                while (true) {
-                    const int t = look - lane;
-                    u64 wv = ST_PRE;
-                    if (t >= 0) {
-                        while (((wv = ld_vol(P.tile_state + (size_t)t * 8 + m)) >> 62) == 0) {}
-                    }
-                    const u64 val = wv & ST_MASK;
-                    const unsigned pm = __ballot_sync(0xffffffffu, (wv >> 62) == 2);
-                    if (pm) {
-                        const int first = __ffs(pm) - 1;
-                        excl += warp_sum64(lane <= first ? val : 0ull);
-                        break;
-                    }
-                    excl += warp_sum64(val);
-                    look -= 32;
-                }
-                if (lane == 0) st_vol(P.tile_state + (size_t)tile * 8 + m, ST_PRE | (excl + agg));
-            }
-            if (lane == 0) {
-                S.excl[m] = excl;
-                if (tile == P.ntiles - 1) {
-                    const u64 nnz = excl + agg;
-                    P.flags->nnz[m] = nnz;
-                    if (P.build >> m & 1) P.colptr[m][P.ncols] = (i64)nnz + P.base;
-                }
-            }
-        }
-    }
-
+    __threadfence_block();
+    asm volatile("bar.arrive 1, %0;" ::"r"(TILE + 32) : "memory");   // counts published; nobody waits here
+    // kept in shared memory, not in registers: they are needed again only at the five flushes, and as
+    // registers they were spilled to local memory (ncu: 25 % of the long-scoreboard stalls were their reloads)
+    S.lexcl[tid] = incl - packed;                              // in-warp exclusive offsets of this column
     // ================= phase 1: operator by operator: walk -> warp staging -> flush =================
     int* const srow = S.row[wid];
     double* const sval = S.val[wid];
@@ -302,6 +345,9 @@ __global__ void __launch_bounds__(TILE, MINB) k_fused_v4(const __grid_constant__
         wetm = act = mlm = 0;
     }
 
+    // no seam / fold-right cell in this warp: the unrolled fast paths apply (generic columns stage nothing there)
+    const bool warp_regular = __all_sync(0xffffffffu, ord == ORD0);
+
     // copies a generic column's entries of matrix q behind the regular ones
     auto stage_generic = [&](const int q, const int off) {
         if (generic)
@@ -314,8 +360,8 @@ __global__ void __launch_bounds__(TILE, MINB) k_fused_v4(const __grid_constant__
     // (iters = compile-time bound on ceil(entries of a warp / 32): the matrix's maximum entries per column)
     auto flush = [&](auto iters, const int q, const int off) {
         constexpr int IT = decltype(iters)::value;
-        const u64 g0 = S.excl[q] + ((wbase >> (12 * q)) & 0xfffull);
-        const int n = (int)((warp_tot >> (12 * q)) & 0xfffull);
+        const u64 g0 = *reinterpret_cast<volatile u64*>(&S.excl[q]) + ((S.wbase[wid] >> (12 * q)) & 0xfffull);
+        const int n = (int)((S.warp[wid] >> (12 * q)) & 0xfffull);
         if (valid) P.colptr[q][w] = (i64)(g0 + (u64)off) + P.base;
         __syncwarp();
         i64* __restrict__ rv = P.rowval[q] + g0 + lane;
@@ -331,7 +377,7 @@ __global__ void __launch_bounds__(TILE, MINB) k_fused_v4(const __grid_constant__
         }
         __syncwarp();   // the staging buffer may be overwritten by the next matrix
     };
-    auto offset_of = [&](const int q) { return (int)((lane_excl >> (12 * q)) & 0xfffull); };
+    auto offset_of = [&](const int q) { return (int)((S.lexcl[tid] >> (12 * q)) & 0xfffull); };
 
     // ---- Tadv walk (:193-204, :237-297): candidates in ascending row order = ascending emitter rank.
     // Off-diagonal (𝑖, 𝑗) = -p/m𝑖 as the emitter 𝑖 computes it; the diagonal adds p/m𝑗 per emitter,
@@ -344,47 +390,86 @@ __global__ void __launch_bounds__(TILE, MINB) k_fused_v4(const __grid_constant__
         double dsum = 0.0;
         bool first = true, bad = false;
         int pos = off1, posC = dump;
-        // software pipeline: the loads of candidate t+1 are issued before candidate t is computed
-        int c_n = ord & 7;
-        int Lc_n = S.Lc[c_n][tid];
-        double x_n = __ldg(P.phi_nb[(c_n == cN && fold) ? 7 : c_n] + Lc_n), v_n = __ldg(P.v3D + Lc_n);
-        double r_n = RHO3D ? __ldg(P.rho3d + Lc_n) : P.rho;
-#pragma unroll 1
-        for (int t = 0; t < 7; ++t) {
-            const int c = c_n;
-            const double x = x_n, vnb = v_n, rnb = r_n;
-            if (t < 6) {
-                c_n = (ord >> (4 * t + 4)) & 7;
-                Lc_n = S.Lc[c_n][tid];
-                x_n = __ldg(P.phi_nb[(c_n == cN && fold) ? 7 : c_n] + Lc_n);
-                v_n = __ldg(P.v3D + Lc_n);
-                if (RHO3D) r_n = __ldg(P.rho3d + Lc_n);
+        if (warp_regular) {
+            // ---- regular rows (no seam / fold-right cell in the warp): row order = candidate order, so the
+            // code is unrolled with compile-time candidates, the loads are batched, absent faces are skipped
+            // and the staging position is a popcount under a constant mask
+            double xs[7], vn[7], rn[7];
+#pragma unroll
+            for (int c = 0; c < 7; ++c) {
+                if (c == cC) continue;
+                const int Lc = S.Lc[c][tid];
+                const double* ph = c == cT ? P.pb : c == cS ? P.pn : c == cW ? P.pe : c == cE ? P.pw : c == cB ? P.pt
+                                                                                               : (fold ? P.pn : P.ps);
+                xs[c] = __ldg(ph + Lc);
+                vn[c] = __ldg(P.v3D + Lc);
+                rn[c] = RHO3D ? __ldg(P.rho3d + Lc) : P.rho;
             }
-            const bool on = (m_adv >> c) & 1;
-            if (c == cC) {
-                posC = on ? pos : dump;
+#pragma unroll
+            for (int c = 0; c < 7; ++c) {
+                if (c == cC) continue;
+                if ((m_adv >> c) & 1) {
+                    const bool mx = c == cT || c == cE || (c == cN && !fold);
+                    const double f = upflux(xs[c], mx, up);
+                    const double p = mx ? f : -f;
+                    const double rb = (rn[c] + rhoC) / 2;
+                    const double a = -p / (rb * vn[c]);
+                    const double d = p / (rb * vC);
+                    bad |= isnan(a) || isnan(d);
+                    dsum = first ? d : dsum + d;
+                    first = false;
+                    const int pp = off1 + __popc(m_adv & ((1u << c) - 1u));
+                    srow[pp] = S.rk[c][tid];
+                    sval[pp] = a;
+                    S.Tv[c][tid] = a;
+                } else {
+                    S.Tv[c][tid] = 0.0;
+                }
+            }
+            posC = (m_adv & bC) ? off1 + __popc(m_adv & (bT | bS | bW)) : dump;
+        } else {
+            // software pipeline: the loads of candidate t+1 are issued before candidate t is computed
+            int c_n = ord & 7;
+            int Lc_n = S.Lc[c_n][tid];
+            double x_n = __ldg(P.phi_nb[(c_n == cN && fold) ? 7 : c_n] + Lc_n), v_n = __ldg(P.v3D + Lc_n);
+            double r_n = RHO3D ? __ldg(P.rho3d + Lc_n) : P.rho;
+    #pragma unroll 1
+            for (int t = 0; t < 7; ++t) {
+                const int c = c_n;
+                const double x = x_n, vnb = v_n, rnb = r_n;
+                if (t < 6) {
+                    c_n = (ord >> (4 * t + 4)) & 7;
+                    Lc_n = S.Lc[c_n][tid];
+                    x_n = __ldg(P.phi_nb[(c_n == cN && fold) ? 7 : c_n] + Lc_n);
+                    v_n = __ldg(P.v3D + Lc_n);
+                    if (RHO3D) r_n = __ldg(P.rho3d + Lc_n);
+                }
+                const bool on = (m_adv >> c) & 1;
+                if (c == cC) {
+                    posC = on ? pos : dump;
+                    pos += on;
+                    continue;
+                }
+                const bool mx = (MX >> c) & 1;
+                const double f = upflux(x, mx, up);
+                const double p = mx ? f : -f;     // pushed magnitude: ϕ for W,S,B slots of the emitter, -ϕ for E,N,T
+                const double rb = (rnb + rhoC) / 2;
+                // absent entries divide 1/1: a zero / NaN operand would send the whole warp through the
+                // slow path of the IEEE division
+                const double pn = on ? p : 1.0;
+                const double a = -pn / (on ? rb * vnb : 1.0);
+                const double d = pn / (on ? rb * vC : 1.0);
+                if (on) {
+                    bad |= isnan(a) || isnan(d);
+                    dsum = first ? d : dsum + d;
+                    first = false;
+                }
+                const int pp = on ? pos : dump;
+                srow[pp] = S.rk[c][tid];
+                sval[pp] = a;
                 pos += on;
-                continue;
+                S.Tv[c][tid] = on ? a : 0.0;
             }
-            const bool mx = (MX >> c) & 1;
-            const double f = upflux(x, mx, up);
-            const double p = mx ? f : -f;     // pushed magnitude: ϕ for W,S,B slots of the emitter, -ϕ for E,N,T
-            const double rb = (rnb + rhoC) / 2;
-            // absent entries divide 1/1: a zero / NaN operand would send the whole warp through the
-            // slow path of the IEEE division
-            const double pn = on ? p : 1.0;
-            const double a = -pn / (on ? rb * vnb : 1.0);
-            const double d = pn / (on ? rb * vC : 1.0);
-            if (on) {
-                bad |= isnan(a) || isnan(d);
-                dsum = first ? d : dsum + d;
-                first = false;
-            }
-            const int pp = on ? pos : dump;
-            srow[pp] = S.rk[c][tid];
-            sval[pp] = a;
-            pos += on;
-            S.Tv[c][tid] = on ? a : 0.0;
         }
         if (bad) errbits |= 2u;
         srow[posC] = rkC;
@@ -396,7 +481,50 @@ __global__ void __launch_bounds__(TILE, MINB) k_fused_v4(const __grid_constant__
         for (int c = 0; c < 7; ++c) S.Tv[c][tid] = 0.0;
     }
 
-    __syncthreads();   // look-back results (S.excl) published
+    // ---- TκH values of regular rows, computed ahead of the barrier so that the look-back has time to finish
+    // (:348-415, :426-435): own slots in emit order W,E,S,N with compile-time directions
+    double khv[4] = {0.0, 0.0, 0.0, 0.0}, kh_dsum = 0.0;
+    if ((P.build & 4) && warp_regular) {
+        const double thC = __ldg(P.thk + L);
+        bool first = true, bad = false;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = q == 0 ? cW : q == 1 ? cE : q == 2 ? cS : cN;
+            const int own = c == cW ? OTMB_DIR_WEST : c == cE ? OTMB_DIR_EAST : c == cS ? OTMB_DIR_SOUTH : OTMB_DIR_NORTH;
+            const int Lc = S.Lc[c][tid];
+            const int q2 = Lc - k * PP;
+            // unconditional loads (clamped indices): free to be hoisted and batched
+            const double e_own = __ldg(P.edge + own * PP + p2), d_own = __ldg(P.dnbr + own * PP + p2);
+            const double* e_oppp = c == cW ? P.edge + OTMB_DIR_EAST * PP : c == cE ? P.edge + OTMB_DIR_WEST * PP
+                                   : c == cS ? P.edge + OTMB_DIR_NORTH * PP
+                                             : P.edge + (fold ? OTMB_DIR_NORTH : OTMB_DIR_SOUTH) * PP;
+            const double e_opp = __ldg(e_oppp + q2);
+            const double d_opp = __ldg(e_oppp + (P.dnbr - P.edge) + q2);
+            const double th = __ldg(P.thk + Lc), vnb = __ldg(P.v3D + Lc);
+            if ((m_kh >> c) & 1) {
+                const double ka = P.kH * jl_min(thC * e_own, th * e_opp);
+                const double ts = ka / (d_own * vC);       // row 𝑗 seen from 𝑗
+                const double tn = ka / (d_opp * vnb);      // row 𝑖 seen from 𝑖
+                bad |= isnan(ts) || isnan(tn);
+                kh_dsum = first ? ts : kh_dsum + ts;
+                first = false;
+                khv[q] = -tn;
+            }
+        }
+        if (bad) errbits |= 4u;
+    }
+
+    // meet the other column warps' counts and the scan warp's offsets (barrier 2; the scan warp has normally
+    // arrived long ago)
+    asm volatile("bar.sync 2, %0;" ::"r"(TILE + 32) : "memory");
+    {
+        u64 wbase = 0;                                         // in-tile offset of this warp
+#pragma unroll
+        for (int q = 0; q < NW; ++q)
+            if (q < wid) wbase += *reinterpret_cast<volatile u64*>(&S.warp[q]);
+        if (lane == 0) S.wbase[wid] = wbase;
+        __syncwarp();
+    }
 
     if (tile * TILE + wid * 32 < P.ncols) {
         if (P.build & 2) flush(std::integral_constant<int, 7>{}, 1, off1);
@@ -406,66 +534,83 @@ __global__ void __launch_bounds__(TILE, MINB) k_fused_v4(const __grid_constant__
         if (P.build & 4) {
             const int off2 = offset_of(2);
             const double thC = __ldg(P.thk + L);
-            double tsW = 0.0, tsE = 0.0, tsS = 0.0, tsN = 0.0;
             bool bad = false;
-            int pos = off2, posC = dump;
-            // software pipeline, as in the Tadv walk
-            struct KhIn {
-                int c;
-                double e_own, e_opp, th, d_own, d_opp, v;
-            };
-            auto load_kh = [&](const int t) {
-                KhIn in;
-                in.c = (ord >> (4 * t)) & 7;
-                const int Lc = S.Lc[in.c][tid];
-                const int own = (OWNDIR >> (4 * in.c)) & 3;
-                const int opp = (in.c == cN && fold) ? own : own ^ 2;   // the neighbour's side of the shared face (:407)
-                const int q2 = Lc - k * PP;
-                in.e_own = __ldg(P.edge + own * PP + p2);
-                in.e_opp = __ldg(P.edge + opp * PP + q2);
-                in.th = __ldg(P.thk + Lc);
-                in.d_own = __ldg(P.dnbr + own * PP + p2);
-                in.d_opp = __ldg(P.dnbr + opp * PP + q2);
-                in.v = __ldg(P.v3D + Lc);
-                return in;
-            };
-            KhIn nxt = load_kh(1);
-#pragma unroll 1
-            for (int t = 1; t < 6; ++t) {      // T and B sit at both ends of every order word
-                const KhIn in = nxt;
-                if (t < 5) nxt = load_kh(t + 1);
-                const int c = in.c;
-                const bool on = (m_kh >> c) & 1;
-                if (c == cC) {
-                    posC = on ? pos : dump;
-                    pos += on;
-                    continue;
-                }
-                const double a_own = thC * in.e_own;
-                const double a_nbr = in.th * in.e_opp;
-                const double ka = on ? P.kH * jl_min(a_own, a_nbr) : 1.0;   // absent: 1/1, see the Tadv walk
-                const double ts = ka / (on ? in.d_own * vC : 1.0);     // row 𝑗 seen from 𝑗
-                const double tn = ka / (on ? in.d_opp * in.v : 1.0);   // row 𝑖 seen from 𝑖
-                if (on) {
-                    bad |= isnan(ts) || isnan(tn);
-                    tsW = c == cW ? ts : tsW;
-                    tsE = c == cE ? ts : tsE;
-                    tsS = c == cS ? ts : tsS;
-                    tsN = c == cN ? ts : tsN;
-                    S.Tv[c][tid] = S.Tv[c][tid] + (-tn);
-                }
-                const int pp = on ? pos : dump;
-                srow[pp] = S.rk[c][tid];
-                sval[pp] = -tn;
-                pos += on;
-            }
-            if (bad) errbits |= 4u;
+            int posC = dump;
             double dsum = 0.0;
-            bool first = true;
-            if (m_kh & bW) { dsum = tsW; first = false; }
-            if (m_kh & bE) { dsum = first ? tsE : dsum + tsE; first = false; }
-            if (m_kh & bS) { dsum = first ? tsS : dsum + tsS; first = false; }
-            if (m_kh & bN) { dsum = first ? tsN : dsum + tsN; first = false; }
+            if (warp_regular) {
+                // ---- regular rows: the values were computed ahead of the look-back barrier (khv, kh_dsum)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int c = q == 0 ? cW : q == 1 ? cE : q == 2 ? cS : cN;
+                    if ((m_kh >> c) & 1) {
+                        const int pp = off2 + __popc(m_kh & ((1u << c) - 1u));
+                        srow[pp] = S.rk[c][tid];
+                        sval[pp] = khv[q];
+                        S.Tv[c][tid] = S.Tv[c][tid] + khv[q];
+                    }
+                }
+                dsum = kh_dsum;
+                posC = (m_kh & bC) ? off2 + __popc(m_kh & (bT | bS | bW)) : dump;
+            } else {
+                double tsW = 0.0, tsE = 0.0, tsS = 0.0, tsN = 0.0;
+                int pos = off2;
+                // software pipeline, as in the Tadv walk
+                struct KhIn {
+                    int c;
+                    double e_own, e_opp, th, d_own, d_opp, v;
+                };
+                auto load_kh = [&](const int t) {
+                    KhIn in;
+                    in.c = (ord >> (4 * t)) & 7;
+                    const int Lc = S.Lc[in.c][tid];
+                    const int own = (OWNDIR >> (4 * in.c)) & 3;
+                    const int opp = (in.c == cN && fold) ? own : own ^ 2;   // the neighbour's side of the shared face (:407)
+                    const int q2 = Lc - k * PP;
+                    in.e_own = __ldg(P.edge + own * PP + p2);
+                    in.e_opp = __ldg(P.edge + opp * PP + q2);
+                    in.th = __ldg(P.thk + Lc);
+                    in.d_own = __ldg(P.dnbr + own * PP + p2);
+                    in.d_opp = __ldg(P.dnbr + opp * PP + q2);
+                    in.v = __ldg(P.v3D + Lc);
+                    return in;
+                };
+                KhIn nxt = load_kh(1);
+    #pragma unroll 1
+                for (int t = 1; t < 6; ++t) {      // T and B sit at both ends of every order word
+                    const KhIn in = nxt;
+                    if (t < 5) nxt = load_kh(t + 1);
+                    const int c = in.c;
+                    const bool on = (m_kh >> c) & 1;
+                    if (c == cC) {
+                        posC = on ? pos : dump;
+                        pos += on;
+                        continue;
+                    }
+                    const double a_own = thC * in.e_own;
+                    const double a_nbr = in.th * in.e_opp;
+                    const double ka = on ? P.kH * jl_min(a_own, a_nbr) : 1.0;   // absent: 1/1, see the Tadv walk
+                    const double ts = ka / (on ? in.d_own * vC : 1.0);     // row 𝑗 seen from 𝑗
+                    const double tn = ka / (on ? in.d_opp * in.v : 1.0);   // row 𝑖 seen from 𝑖
+                    if (on) {
+                        bad |= isnan(ts) || isnan(tn);
+                        tsW = c == cW ? ts : tsW;
+                        tsE = c == cE ? ts : tsE;
+                        tsS = c == cS ? ts : tsS;
+                        tsN = c == cN ? ts : tsN;
+                        S.Tv[c][tid] = S.Tv[c][tid] + (-tn);
+                    }
+                    const int pp = on ? pos : dump;
+                    srow[pp] = S.rk[c][tid];
+                    sval[pp] = -tn;
+                    pos += on;
+                }
+                if (bad) errbits |= 4u;
+                bool first = true;
+                if (m_kh & bW) { dsum = tsW; first = false; }
+                if (m_kh & bE) { dsum = first ? tsE : dsum + tsE; first = false; }
+                if (m_kh & bS) { dsum = first ? tsS : dsum + tsS; first = false; }
+                if (m_kh & bN) { dsum = first ? tsN : dsum + tsN; first = false; }
+            }
             srow[posC] = rkC;
             sval[posC] = dsum;
             if (m_kh & bC) S.Tv[cC][tid] = S.Tv[cC][tid] + dsum;
@@ -585,7 +730,7 @@ int launch_v4(otmb_ctx* c, V4Params& P) {
     CU_TRY(c, cudaMemsetAsync(P.tile_state, 0, (size_t)ntiles * 8 * sizeof(u64), c->stream));
     const size_t smem = sizeof(Smem<TILE>);
     CU_TRY(c, cudaFuncSetAttribute(k_fused_v4<RHO3D, TILE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_fused_v4<RHO3D, TILE, MINB><<<ntiles, TILE, smem, c->stream>>>(P);
+    k_fused_v4<RHO3D, TILE, MINB><<<ntiles, TILE + 32, smem, c->stream>>>(P);
     LAUNCHED(c);
     CU_TRY(c, cudaGetLastError());
     return OTMB_OK;
@@ -629,6 +774,7 @@ int otmb_fused_v4_build(otmb_ctx* c, const otmb_tm_params* prm, int build) {
     P.upwind = prm->upwind;
     P.base = prm->index_base;
     P.build = build;
+    P.prefetch = getenv("OTMB_V4_NOPREFETCH") ? 0 : 1;
     P.w0 = (int)c->w0;
     P.ncols = (int)c->ncols;
     P.flags = c->flags.as<DevFlags>();
@@ -647,15 +793,14 @@ int otmb_fused_v4_build(otmb_ctx* c, const otmb_tm_params* prm, int build) {
         P.nzval[m] = c->nzval[m].as<double>();
     }
     static const int variant = getenv("OTMB_V4_VARIANT") ? atoi(getenv("OTMB_V4_VARIANT")) : 0;
-    if (c->have_rho3d) return launch_v4<true, 384, 2>(c, P);
+    // TILE column threads + one scan warp per block
+    if (c->have_rho3d) return launch_v4<true, 352, 2>(c, P);
     switch (variant) {
-        case 1: return launch_v4<false, 256, 3>(c, P);
-        case 2: return launch_v4<false, 256, 2>(c, P);
-        case 3: return launch_v4<false, 128, 8>(c, P);
-        case 4: return launch_v4<false, 128, 6>(c, P);
-        case 5: return launch_v4<false, 512, 2>(c, P);
-        case 7: return launch_v4<false, 512, 1>(c, P);
-        case 8: return launch_v4<false, 256, 4>(c, P);
-        default: return launch_v4<false, 384, 2>(c, P);   // measured best on C2 (profiles/README.md)
+        case 1: return launch_v4<false, 224, 3>(c, P);
+        case 2: return launch_v4<false, 480, 1>(c, P);
+        case 3: return launch_v4<false, 160, 4>(c, P);
+        case 4: return launch_v4<false, 224, 4>(c, P);
+        case 5: return launch_v4<false, 288, 2>(c, P);
+        default: return launch_v4<false, 352, 2>(c, P);   // measured best on C2 (profiles/README.md)
     }
 }
