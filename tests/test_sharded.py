@@ -107,3 +107,55 @@ def test_sharded_cuda_with_precomputed_phi():
     full, _, _ = sharded.run_threaded(4, fn)[0]
     for gname, oname in NAMES.items():
         assert_csc_equal(getattr(full, gname), o["tm"][oname], oname, exact=True)
+
+
+@pytest.mark.gpu
+def test_large_grid_sharded_equals_unsharded_and_invariants():
+    """A grid too large for the oracle to be the checker in reasonable time (720x540x25, ~5 M wet cells): the
+    size-independent properties — CSC structure (monotone colptr, strictly ascending rows per column), the
+    reference's sign pattern and conservation invariants (test/online.jl:110-123), and bit-identity of the
+    k-slab sharded assembly (4 slabs, one context each) with the single-context assembly."""
+    import otmb_b200.api as A
+    from _util import fields
+    oc = synthetic.make_ocean(720, 540, 25, "tripolar", seed=11)
+    f = fields(oc)
+    ctx = A.Context(0)
+    gm = A.makegridmetrics(areacello=f["areacello"], volcello=f["volcello"], lon=f["lon"], lat=f["lat"], lev=f["lev"],
+                           lon_vertices=f["lon_vertices"], lat_vertices=f["lat_vertices"], ctx=ctx)
+    ix = A.makeindices(gm.v3D, ctx=ctx)
+    phi = A.facefluxesfrommasstransport(umo=f["umo"], vmo=f["vmo"], gridmetrics=gm, indices=ix, ctx=ctx)
+    tm = A.transportmatrix(ϕ=phi, mlotst=oc.mlotst, gridmetrics=gm, indices=ix, ρ=1035.0, ctx=ctx)
+    N = ix.N
+    assert N > 3_000_000
+    for name in A.MATRICES:
+        m = getattr(tm, name)
+        assert m.shape == (N, N) and m.indptr[0] == 0 and m.indptr[-1] == m.nnz
+        assert (np.diff(m.indptr) >= 0).all()
+        d = np.diff(m.indices)
+        starts = m.indptr[1:-1][np.diff(m.indptr)[:-1] > 0]           # positions where a new column begins
+        inner = np.ones(m.nnz - 1, bool)
+        inner[starts[(starts > 0) & (starts < m.nnz)] - 1] = False
+        assert (d[inner] > 0).all(), f"{name}: rows not strictly ascending inside a column"
+        assert m.indices.min() >= 0 and m.indices.max() < N and np.isfinite(m.data).all()
+    T = tm.T
+    one, v = np.ones(N), gm.v3D.ravel(order="F")[~np.isnan(gm.v3D.ravel(order="F"))]
+    Myr = 365.25 * 86400 * 1e6
+    for name in ("TκH", "TκVML", "TκVdeep"):
+        assert np.linalg.norm(one) / np.linalg.norm(getattr(tm, name) @ one) / Myr > 1e6, name
+    for name in A.MATRICES:
+        assert np.linalg.norm(v) / np.linalg.norm(getattr(tm, name).T @ v) / Myr > 1e6, name
+    assert (T.diagonal() > 0).all()
+    off = T.copy()
+    off.setdiag(0)
+    off.eliminate_zeros()
+    assert (off.data < 0).all()
+    ctx.close()
+    # the same matrix from four slabs (threads, one context each, all on this GPU)
+    fn = lambda ex: sharded.transportmatrix_sharded(exchange=ex, gridmetrics=gm, mlotst=oc.mlotst, ρ=1035.0, umo=oc.umo,
+                                                    vmo=oc.vmo, FillValue=oc.fill)
+    full, segs, info = sharded.run_threaded(4, fn)[0]
+    assert info["N"] == N and len(info["slabs"]) == 4
+    for name in A.MATRICES:
+        a, b = getattr(tm, name), getattr(full, name)
+        assert np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices), name
+        assert np.array_equal(a.data.view(np.int64), b.data.view(np.int64)), name
