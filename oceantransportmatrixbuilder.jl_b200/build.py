@@ -39,20 +39,36 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> Path:
+    """Compile every translation unit for sm_100a (in parallel) and link libotmb.so in-tree."""
     if not force and not needs_build():
         return LIB
-    cmd = [nvcc(), *NVCC_FLAGS, f"-I{INCLUDE}", f"-I{CSRC}"]
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = HERE / "build"
+    objdir.mkdir(exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + [f"-I{INCLUDE}", f"-I{CSRC}"]
     if ptxas_info:
-        cmd += ["-Xptxas", "-v"]
-    cmd += [str(CSRC / s) for s in SOURCES] + ["-o", str(LIB)]
-    if verbose:
-        print(" ".join(cmd), file=sys.stderr)
-    env = dict(os.environ)
-    r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        flags += ["-Xptxas", "-v"]
+
+    def compile_one(src):
+        obj = objdir / (Path(src).stem + ".o")
+        cmd = [nvcc(), *flags, "-c", str(CSRC / src), "-o", str(obj)]
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        return obj, r.returncode, r.stdout
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    log = "".join(out for _, _, out in results)
+    if any(rc != 0 for _, rc, _ in results):
+        raise RuntimeError("nvcc failed:\n" + log)
+    cmd = [nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC",
+           *[str(o) for o, _, _ in results], "-o", str(LIB)]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout)
+        raise RuntimeError("nvcc link failed:\n" + r.stdout)
     if verbose or ptxas_info:
-        print(r.stdout, file=sys.stderr)
+        print(log + r.stdout, file=sys.stderr)
     return LIB
 
 

@@ -861,9 +861,6 @@ int otmb_fused_v2_build(otmb_ctx* c, const otmb_tm_params* prm, int build) {
         P.rowval[m] = c->rowval[m].as<i64>();
         P.nzval[m] = c->nzval[m].as<double>();
     }
-    static const int variant = getenv("OTMB_V2_VARIANT") ? atoi(getenv("OTMB_V2_VARIANT")) : 0;
     if (c->have_rho3d) return launch_v2<true, 256, 2>(c, P);
-    if (variant == 1) return launch_v2<false, 128, 4>(c, P);
-    if (variant == 2) return launch_v2<false, 128, 3>(c, P);
     return launch_v2<false, 256, 2>(c, P);
 }

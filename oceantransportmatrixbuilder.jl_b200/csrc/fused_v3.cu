@@ -790,13 +790,6 @@ int otmb_fused_v3_build(otmb_ctx* c, const otmb_tm_params* prm, int build) {
         P.rowval[m] = c->rowval[m].as<i64>();
         P.nzval[m] = c->nzval[m].as<double>();
     }
-    static const int variant = getenv("OTMB_V3_VARIANT") ? atoi(getenv("OTMB_V3_VARIANT")) : 0;
     if (c->have_rho3d) return launch_v3<true, 256, 3>(c, P);
-    switch (variant) {
-        case 1: return launch_v3<false, 256, 3>(c, P);
-        case 2: return launch_v3<false, 256, 2>(c, P);
-        case 3: return launch_v3<false, 128, 8>(c, P);
-        case 4: return launch_v3<false, 128, 6>(c, P);
-        default: return launch_v3<false, 256, 4>(c, P);
-    }
+    return launch_v3<false, 256, 2>(c, P);
 }

@@ -795,11 +795,8 @@ int otmb_fused_v4_build(otmb_ctx* c, const otmb_tm_params* prm, int build) {
     static const int variant = getenv("OTMB_V4_VARIANT") ? atoi(getenv("OTMB_V4_VARIANT")) : 0;
     // TILE column threads + one scan warp per block
     if (c->have_rho3d) return launch_v4<true, 352, 2>(c, P);
-    switch (variant) {
+    switch (variant) {   // launch geometries kept for A/B runs (profiles/bench_variants.sh)
         case 1: return launch_v4<false, 224, 3>(c, P);
-        case 2: return launch_v4<false, 480, 1>(c, P);
-        case 3: return launch_v4<false, 160, 4>(c, P);
-        case 4: return launch_v4<false, 224, 4>(c, P);
         case 5: return launch_v4<false, 288, 2>(c, P);
         default: return launch_v4<false, 352, 2>(c, P);   // measured best on C2 (profiles/README.md)
     }
