@@ -193,6 +193,18 @@ int otmb_fluxes2velocity(otmb_ctx* ctx, const double* phi_i, const double* phi_j
                          double* u, double* v);
 int otmb_bgrid_to_cgrid(otmb_ctx* ctx, const double* u, const double* v, double fill_value, double* u2, double* v2);
 
+/* lump_and_spray(wet3D, vol, T; di, dj, dk), src/extratools.jl:38-112, default mask only:
+ * LUMP (N_c x N, volume-weighted average onto di x dj x dk boxes split into connected components of T's stored
+ * pattern), SPRAY (N x N_c, = LUMP' with ones) and the coarse volumes.  vol: N doubles (volumes of the wet
+ * cells).  T's pattern: t_colptr / t_rowval (host, base t_index_base), or NULL to use the T of the last
+ * otmb_transportmatrix_build on this context.  Results in index_base; two-phase like transportmatrix. */
+int otmb_lump_and_spray_build(otmb_ctx* ctx, int64_t di, int64_t dj, int64_t dk, const double* vol,
+                              const int64_t* t_colptr, const int64_t* t_rowval, int32_t t_index_base,
+                              int32_t index_base, int64_t* n_coarse);
+int otmb_lump_and_spray_fetch(otmb_ctx* ctx, int64_t* lump_colptr /* N+1 */, int64_t* lump_rowval /* N */,
+                              double* lump_nzval /* N */, int64_t* spray_colptr /* N_c+1 */, int64_t* spray_rowval /* N */,
+                              double* spray_nzval /* N */, double* vol_c /* N_c */);
+
 /* measurement helpers: CUDA events on the ctx stream (the stream every kernel of this
  * library is launched on), an L2 flush, and per-kernel launch counting. */
 int otmb_timer_start(otmb_ctx* ctx);

@@ -457,6 +457,38 @@ def facefluxesfromvelocities(*, uo, uo_lon, uo_lat, vo, vo_lon, vo_lat, gridmetr
     return facefluxes(umo, vmo, gridmetrics, indices, FillValue=fill, ctx=ctx)
 
 
+# ---- lump_and_spray (src/extratools.jl:38-112) ------------------------------------------------------------
+def lump_and_spray(wet3D, vol, T, mask=None, *, di=2, dj=2, dk=1, ctx=None):
+    """lump_and_spray(wet3D, vol, T, mask; di, dj, dk) -> (LUMP, SPRAY, vol_c).  Coarsen with LUMP @ x and
+    LUMP @ T @ SPRAY.  Only the default mask (lump everywhere) runs on the device: a custom mask makes the
+    reference's sweep data dependent and is rejected."""
+    wet3D = np.asarray(wet3D, dtype=bool)
+    if mask is not None and not np.asarray(mask, dtype=bool).all():
+        raise OTMBError(_L.ERR_BADARG, "lump_and_spray: a custom mask is not supported on the device path")
+    ctx = ctx or default_context()
+    v = ctx.resident.get("v3D")
+    if v is None or v.shape != wet3D.shape or not np.array_equal(~np.isnan(v), wet3D):
+        v = np.asfortranarray(np.where(wet3D, 1.0, np.nan))          # any array with this wet pattern will do
+        _ensure_indices(ctx, v, "bipolar")                             # the topology plays no role here
+    N = ctx.resident["N"]
+    vol = np.ascontiguousarray(vol, dtype=np.float64)
+    Tc = sp.csc_matrix(T)
+    assert Tc.shape == (N, N) and vol.shape == (N,)
+    cp, rv = Tc.indptr.astype(np.int64), Tc.indices.astype(np.int64)
+    Nc = C.c_int64()
+    ctx.check(ctx.lib.otmb_lump_and_spray_build(ctx.h, int(di), int(dj), int(dk), _ptr(vol), _ptr(cp), _ptr(rv), 0, 0, C.byref(Nc)))
+    Nc = Nc.value
+    lcp, lrv, lnz = np.empty(N + 1, np.int64), np.empty(N, np.int64), np.empty(N, np.float64)
+    scp, srv, snz = np.empty(Nc + 1, np.int64), np.empty(N, np.int64), np.empty(N, np.float64)
+    vol_c = np.empty(Nc, np.float64)
+    ctx.check(ctx.lib.otmb_lump_and_spray_fetch(ctx.h, _ptr(lcp), _ptr(lrv), _ptr(lnz), _ptr(scp), _ptr(srv), _ptr(snz), _ptr(vol_c)))
+    LUMP = sp.csc_matrix((Nc, N), dtype=np.float64)
+    LUMP.data, LUMP.indices, LUMP.indptr = lnz, lrv, lcp
+    SPRAY = sp.csc_matrix((N, Nc), dtype=np.float64)
+    SPRAY.data, SPRAY.indices, SPRAY.indptr = snz, srv, scp
+    return LUMP, SPRAY, vol_c
+
+
 # ---- Redi/GM helpers (experimental and non-exported in the reference) -------------------------
 def _ensure_z(ctx, gridmetrics):
     _ensure_grid(ctx, gridmetrics)

@@ -91,6 +91,10 @@ struct otmb_ctx {
     DevBuf sp_colptr, sp_rowval, sp_nzval;  // results of otmb_sparse_build / otmb_spadd_build
     i64 sp_n = 0, sp_nnz = 0;
     DevBuf add_tmp[6];
+    DevBuf lump[7];      // lump_and_spray results: LUMP colptr/rowval/nzval, SPRAY colptr/rowval/nzval, vol_c
+    i64 lump_nc = 0;
+    int lump_base = 0;
+    bool have_lump = false;
     DevBuf l2;
 
     i64 launches = 0;

@@ -187,6 +187,7 @@ int otmb_destroy(otmb_ctx* c) {
     for (DevBuf* b : bufs) b->release();
     for (int q = 0; q < 6; ++q) c->phi[q].release();
     for (int q = 0; q < 2; ++q) c->carry[q].release();
+    for (int q = 0; q < 7; ++q) c->lump[q].release();
     for (int q = 0; q < 6; ++q) c->add_tmp[q].release();
     for (int q = 0; q < 12; ++q) c->coo[q].release();
     for (int q = 0; q < 5; ++q) {
