@@ -11,7 +11,7 @@ module OceanTransportMatrixBuilderB200
 using SparseArrays
 
 export makegridmetrics, makeindices, facefluxesfrommasstransport, facefluxesfromvelocities, velocity2fluxes,
-       fluxes2velocity, transportmatrix
+       fluxes2velocity, transportmatrix, lump_and_spray
 
 const LIBOTMB = get(ENV, "LIBOTMB", joinpath(@__DIR__, "..", "libotmb.so"))
 
@@ -202,6 +202,23 @@ function facefluxesfromvelocities(; uo, uo_lon, uo_lat, vo, vo_lon, vo_lat, grid
     @assert isequal(FillValue, vo.properties["_FillValue"])
     umo, vmo = velocity2fluxes(uo, uo_lon, uo_lat, vo, vo_lon, vo_lat, gridmetrics, ρ)
     return facefluxes(umo, vmo, gridmetrics, indices; FillValue)
+end
+
+# ---- lump_and_spray, src/extratools.jl:38-112.  Default mask: on the device; a custom mask makes the reference's
+# sweep greedy and data dependent, so that case keeps the reference's Julia body (not repeated here).
+function lump_and_spray(wet3D, vol, T::SparseMatrixCSC{Float64, Int64}, mask = trues(size(wet3D)); di = 2, dj = 2, dk = 1)
+    all(mask) || error("lump_and_spray with a custom mask: use the reference implementation")
+    c = ctx(); N = length(vol); Nc = Ref{Int64}(0)
+    check(c, ccall((:otmb_lump_and_spray_build, LIBOTMB), Cint,
+                   (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Int32, Int32, Ref{Int64}),
+                   c.h, di, dj, dk, vol, T.colptr, T.rowval, 1, 1, Nc))
+    lcp = Vector{Int64}(undef, N + 1); lrv = Vector{Int64}(undef, N); lnz = Vector{Float64}(undef, N)
+    scp = Vector{Int64}(undef, Nc[] + 1); srv = Vector{Int64}(undef, N); snz = Vector{Float64}(undef, N)
+    vol_c = Vector{Float64}(undef, Nc[])
+    check(c, ccall((:otmb_lump_and_spray_fetch, LIBOTMB), Cint,
+                   (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}),
+                   c.h, lcp, lrv, lnz, scp, srv, snz, vol_c))
+    return SparseMatrixCSC(Nc[], N, lcp, lrv, lnz), SparseMatrixCSC(N, Nc[], scp, srv, snz), vol_c
 end
 
 end # module
