@@ -167,7 +167,6 @@ int otmb_need(otmb_ctx* ctx, bool cond, const char* what);
 int otmb_upload3d(otmb_ctx* ctx, DevBuf& buf, const double* host);   // whole (nx,ny,nz) array, or only the slab window
 int otmb_fused_build(otmb_ctx* ctx, const otmb_tm_params* prm, int mask, bool two_pass);
 int otmb_fused_v2_build(otmb_ctx* ctx, const otmb_tm_params* prm, int mask);
-int otmb_fused_v3_build(otmb_ctx* ctx, const otmb_tm_params* prm, int mask);
 int otmb_fused_v4_build(otmb_ctx* ctx, const otmb_tm_params* prm, int mask);
 int otmb_drop_zeros(otmb_ctx* ctx, int m, int base);
 int otmb_coo_build(otmb_ctx* ctx, const otmb_tm_params* prm, int mask);

@@ -4,7 +4,7 @@
 //
 // Same mathematics and ordering rules as fused.cu (read its header first: gather form, emit
 // order, generic branch for coincident neighbours).  Why this shape (ncu profiles under
-// profiles/): the fully unrolled v2/v3 kernels were 8 000-10 000 SASS instructions of straight-line
+// profiles/): the fully unrolled predecessors (fused_v2.cu and a v3 since removed) were 8 000-10 000 SASS instructions of straight-line
 // code, each executed once per warp — instruction-cache hit rate 83-95 %, the GPC-level instruction
 // cache at 60-80 % of its request peak, 128 registers (16 warps per SM) or heavy spilling below
 // that; DRAM sat at 20-30 % with traffic equal to the algorithmic bytes.  The kernel was bound by

@@ -83,12 +83,11 @@ int otmb_transportmatrix_build(otmb_ctx* c, const otmb_tm_params* prm, int64_t n
         OT_TRY(otmb_sum_operators(c, prm->index_base));
     } else {
         const int build = ops | (all4 ? 1 : 0);
-        // OTMB_FUSED_IMPL=v2|v3 selects an earlier schedule of the same column kernel (A/B measurements)
+        // OTMB_FUSED_IMPL=v2 selects the earlier unrolled schedule of the same column kernel (A/B measurements)
         static const char* impl = getenv("OTMB_FUSED_IMPL");
         const int ver = impl && impl[0] == 'v' ? atoi(impl + 1) : 4;
         st = prm->path == OTMB_PATH_FUSED2 ? otmb_fused_build(c, prm, build, true)
              : ver == 2                    ? otmb_fused_v2_build(c, prm, build)
-             : ver == 3                    ? otmb_fused_v3_build(c, prm, build)
                                            : otmb_fused_v4_build(c, prm, build);
         if (st != OTMB_OK) return st;
         CU_TRY(c, cudaEventRecord(c->ev_b1, c->stream));
