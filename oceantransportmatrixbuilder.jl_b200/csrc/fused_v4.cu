@@ -112,6 +112,7 @@ template <bool RHO3D, int TILE, int MINB>
 // __grid_constant__: P is indexed dynamically and its address is taken by the generic branch
 __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_constant__ V4Params P) {
     constexpr int NW = TILE / 32;   // column warps; warp NW is the scan warp
+    static_assert(NW + 2 <= 16, "one named barrier per column warp");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem<TILE>& S = *reinterpret_cast<Smem<TILE>*>(smem_raw);
 
@@ -127,7 +128,10 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
         asm volatile("bar.sync 1, %0;" ::"r"(TILE + 32) : "memory");
         u64 total = 0;
 #pragma unroll
-        for (int q = 0; q < NW; ++q) total += *reinterpret_cast<volatile u64*>(&S.warp[q]);
+        for (int q = 0; q < NW; ++q) {
+            if (lane == q) S.wbase[q] = total;     // in-tile offset of column warp q
+            total += *reinterpret_cast<volatile u64*>(&S.warp[q]);
+        }
         if (lane < 5) st_vol(P.tile_state + (size_t)tile * 8 + lane, (tile == 0 ? ST_PRE : ST_AGG) | ((total >> (12 * lane)) & 0xfffull));
         u64 excl[5] = {0, 0, 0, 0, 0};
         unsigned pending = tile > 0 ? 31u : 0u;   // counters still looking back
@@ -172,7 +176,10 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
             }
         }
         __threadfence_block();
-        asm volatile("bar.arrive 2, %0;" ::"r"(TILE + 32) : "memory");   // S.excl published
+        // S.excl and S.wbase published: release every column warp through its own barrier (ids 2 .. NW+1, 64
+        // participants: the warp + this one), so that no column warp waits for a sibling's values
+#pragma unroll
+        for (int q = 0; q < NW; ++q) asm volatile("bar.arrive %0, 64;" ::"r"(2 + q) : "memory");
         return;
     }
     const GridDims g = P.g;
@@ -514,17 +521,8 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
         if (bad) errbits |= 4u;
     }
 
-    // meet the other column warps' counts and the scan warp's offsets (barrier 2; the scan warp has normally
-    // arrived long ago)
-    asm volatile("bar.sync 2, %0;" ::"r"(TILE + 32) : "memory");
-    {
-        u64 wbase = 0;                                         // in-tile offset of this warp
-#pragma unroll
-        for (int q = 0; q < NW; ++q)
-            if (q < wid) wbase += *reinterpret_cast<volatile u64*>(&S.warp[q]);
-        if (lane == 0) S.wbase[wid] = wbase;
-        __syncwarp();
-    }
+    // meet the scan warp's offsets (S.excl, S.wbase) at this warp's own barrier; it has normally arrived long ago
+    asm volatile("bar.sync %0, 64;" ::"r"(2 + wid) : "memory");
 
     if (tile * TILE + wid * 32 < P.ncols) {
         if (P.build & 2) flush(std::integral_constant<int, 7>{}, 1, off1);
