@@ -103,7 +103,7 @@ struct Smem {
     int rk[7][TILE];               // row index (+ index base) of candidate c
     u64 lexcl[TILE];               // in-warp exclusive offsets of the column, five 12-bit fields
     u64 warp[TILE / 32];           // entries of each warp, five 12-bit fields
-    u64 wbase[TILE / 32];          // in-tile offset of each warp
+    unsigned wbase5[TILE / 32][8]; // in-tile offset of each warp, per matrix
     u64 excl[5];
 };
 
@@ -112,7 +112,8 @@ template <bool RHO3D, int TILE, int MINB>
 // __grid_constant__: P is indexed dynamically and its address is taken by the generic branch
 __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_constant__ V4Params P) {
     constexpr int NW = TILE / 32;   // column warps; warp NW is the scan warp
-    static_assert(NW + 2 <= 16, "one named barrier per column warp");
+    constexpr int BG = (NW + 13) / 14;          // column warps per release barrier (ids 2 .. 15)
+    constexpr int NBG = (NW + BG - 1) / BG;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem<TILE>& S = *reinterpret_cast<Smem<TILE>*>(smem_raw);
 
@@ -126,13 +127,16 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
         // producer / consumer named barriers: the column warps only ARRIVE at barrier 1 (no wait) once their
         // counts are in S.warp; the scan warp only arrives at barrier 2 once the offsets are in S.excl
         asm volatile("bar.sync 1, %0;" ::"r"(TILE + 32) : "memory");
-        u64 total = 0;
+        // lane m < 5 owns counter m: in-tile offsets of the column warps (a tile's total may exceed a 12-bit field)
+        unsigned agg_m = 0;
+        if (lane < 5) {
 #pragma unroll
-        for (int q = 0; q < NW; ++q) {
-            if (lane == q) S.wbase[q] = total;     // in-tile offset of column warp q
-            total += *reinterpret_cast<volatile u64*>(&S.warp[q]);
+            for (int q = 0; q < NW; ++q) {
+                S.wbase5[q][lane] = agg_m;
+                agg_m += (unsigned)((*reinterpret_cast<volatile u64*>(&S.warp[q]) >> (12 * lane)) & 0xfffull);
+            }
+            st_vol(P.tile_state + (size_t)tile * 8 + lane, (tile == 0 ? ST_PRE : ST_AGG) | (u64)agg_m);
         }
-        if (lane < 5) st_vol(P.tile_state + (size_t)tile * 8 + lane, (tile == 0 ? ST_PRE : ST_AGG) | ((total >> (12 * lane)) & 0xfffull));
         u64 excl[5] = {0, 0, 0, 0, 0};
         unsigned pending = tile > 0 ? 31u : 0u;   // counters still looking back
         int look = tile - 1;
@@ -167,7 +171,7 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
         }
         const u64 mine = lane == 0 ? excl[0] : lane == 1 ? excl[1] : lane == 2 ? excl[2] : lane == 3 ? excl[3] : excl[4];
         if (lane < 5) {
-            const u64 agg = (total >> (12 * lane)) & 0xfffull;
+            const u64 agg = agg_m;
             if (tile > 0) st_vol(P.tile_state + (size_t)tile * 8 + lane, ST_PRE | (mine + agg));
             S.excl[lane] = mine;
             if (tile == P.ntiles - 1) {
@@ -176,10 +180,14 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
             }
         }
         __threadfence_block();
-        // S.excl and S.wbase published: release every column warp through its own barrier (ids 2 .. NW+1, 64
-        // participants: the warp + this one), so that no column warp waits for a sibling's values
+        // S.excl and S.wbase5 published: release the column warps through their own barriers (ids 2 .. 15, one per
+        // warp when the tile has at most 14 of them; participants: the warps of the group + this one), so that no
+        // column warp waits for a sibling's values
 #pragma unroll
-        for (int q = 0; q < NW; ++q) asm volatile("bar.arrive %0, 64;" ::"r"(2 + q) : "memory");
+        for (int gq = 0; gq < NBG; ++gq) {
+            const int members = (gq + 1) * BG <= NW ? BG : NW - gq * BG;
+            asm volatile("bar.arrive %0, %1;" ::"r"(2 + gq), "r"(32 * members + 32) : "memory");
+        }
         return;
     }
     const GridDims g = P.g;
@@ -367,7 +375,7 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
     // (iters = compile-time bound on ceil(entries of a warp / 32): the matrix's maximum entries per column)
     auto flush = [&](auto iters, const int q, const int off) {
         constexpr int IT = decltype(iters)::value;
-        const u64 g0 = *reinterpret_cast<volatile u64*>(&S.excl[q]) + ((S.wbase[wid] >> (12 * q)) & 0xfffull);
+        const u64 g0 = *reinterpret_cast<volatile u64*>(&S.excl[q]) + *reinterpret_cast<volatile unsigned*>(&S.wbase5[wid][q]);
         const int n = (int)((S.warp[wid] >> (12 * q)) & 0xfffull);
         if (valid) P.colptr[q][w] = (i64)(g0 + (u64)off) + P.base;
         __syncwarp();
@@ -521,8 +529,12 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
         if (bad) errbits |= 4u;
     }
 
-    // meet the scan warp's offsets (S.excl, S.wbase) at this warp's own barrier; it has normally arrived long ago
-    asm volatile("bar.sync %0, 64;" ::"r"(2 + wid) : "memory");
+    // meet the scan warp's offsets (S.excl, S.wbase5) at this warp's own barrier; it has normally arrived long ago
+    {
+        const int gq = wid / BG;
+        const int members = (gq + 1) * BG <= NW ? BG : NW - gq * BG;
+        asm volatile("bar.sync %0, %1;" ::"r"(2 + gq), "r"(32 * members + 32) : "memory");
+    }
 
     if (tile * TILE + wid * 32 < P.ncols) {
         if (P.build & 2) flush(std::integral_constant<int, 7>{}, 1, off1);
@@ -796,6 +808,7 @@ int otmb_fused_v4_build(otmb_ctx* c, const otmb_tm_params* prm, int build) {
     switch (variant) {   // launch geometries kept for A/B runs (profiles/bench_variants.sh)
         case 1: return launch_v4<false, 224, 3>(c, P);
         case 5: return launch_v4<false, 288, 2>(c, P);
+        case 7: return launch_v4<false, 608, 1>(c, P);   // one block per SM: 2 % faster on C2, 8 % slower on C4
         default: return launch_v4<false, 352, 2>(c, P);   // measured best on C2 (profiles/README.md)
     }
 }
