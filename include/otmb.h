@@ -205,6 +205,12 @@ int otmb_lump_and_spray_fetch(otmb_ctx* ctx, int64_t* lump_colptr /* N+1 */, int
                               double* lump_nzval /* N */, int64_t* spray_colptr /* N_c+1 */, int64_t* spray_rowval /* N */,
                               double* spray_nzval /* N */, double* vol_c /* N_c */);
 
+/* y = X x (transpose = 0) or y = Xᵀ x (transpose != 0) on the RESIDENT result matrix `which` (OTMB_MAT_*) of the
+ * last build: the products behind the reference's conservation checks τdiv = ‖1‖/‖T 1‖, τvol = ‖v‖/‖Tᵀ v‖
+ * (test/online.jl:110-115) without copying the matrix to the host first.  x, y: N doubles (host).  Deterministic
+ * and bit-identical to a sequential CSC product. */
+int otmb_spmv(otmb_ctx* ctx, int which, int transpose, const double* x, double* y);
+
 /* measurement helpers: CUDA events on the ctx stream (the stream every kernel of this
  * library is launched on), an L2 flush, and per-kernel launch counting. */
 int otmb_timer_start(otmb_ctx* ctx);

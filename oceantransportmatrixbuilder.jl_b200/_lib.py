@@ -23,7 +23,7 @@ EXPORTS = [
     "otmb_sparse_build", "otmb_sparse_fetch", "otmb_spadd_build", "otmb_spadd_fetch", "otmb_triad_derivative",
     "otmb_dyad_derivative", "otmb_bolus_gm_velocity", "otmb_timer_start", "otmb_timer_stop", "otmb_l2_flush",
     "otmb_launch_count", "otmb_last_build_ms", "otmb_synchronize", "otmb_set_slab", "otmb_slab_counts",
-    "otmb_set_rank_offset", "otmb_facefluxes_slab", "otmb_velocity2fluxes", "otmb_fluxes2velocity", "otmb_bgrid_to_cgrid", "otmb_lump_and_spray_build", "otmb_lump_and_spray_fetch",
+    "otmb_set_rank_offset", "otmb_facefluxes_slab", "otmb_velocity2fluxes", "otmb_fluxes2velocity", "otmb_bgrid_to_cgrid", "otmb_lump_and_spray_build", "otmb_lump_and_spray_fetch", "otmb_spmv",
 ]
 
 
@@ -85,6 +85,7 @@ def load():
         "otmb_bgrid_to_cgrid": ([vp, vp, vp, dbl, vp, vp], C.c_int),
         "otmb_lump_and_spray_build": ([vp, i64, i64, i64, vp, vp, vp, i32, i32, pi64], C.c_int),
         "otmb_lump_and_spray_fetch": ([vp] * 8, C.c_int),
+        "otmb_spmv": ([vp, C.c_int, C.c_int, vp, vp], C.c_int),
         "otmb_set_slab": ([vp, i64, i64], C.c_int),
         "otmb_slab_counts": ([vp, pi64, pi64], C.c_int),
         "otmb_set_rank_offset": ([vp, i64], C.c_int),

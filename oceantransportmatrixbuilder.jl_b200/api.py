@@ -489,6 +489,17 @@ def lump_and_spray(wet3D, vol, T, mask=None, *, di=2, dj=2, dk=1, ctx=None):
     return LUMP, SPRAY, vol_c
 
 
+# ---- products with the resident matrices (no host copy of the matrix needed) ------------------------------
+def resident_matvec(name, x, *, transpose=False, ctx=None):
+    """y = X @ x (or X.T @ x) with X the resident matrix `name` ("T", "Tadv", "TκH", "TκVML", "TκVdeep") of the last
+    transportmatrix call on this context — e.g. the reference's conservation checks (test/online.jl:110-115)."""
+    ctx = ctx or default_context()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.empty_like(x)
+    ctx.check(ctx.lib.otmb_spmv(ctx.h, _L.MAT[name], int(bool(transpose)), _ptr(x), _ptr(y)))
+    return y
+
+
 # ---- Redi/GM helpers (experimental and non-exported in the reference) -------------------------
 def _ensure_z(ctx, gridmetrics):
     _ensure_grid(ctx, gridmetrics)

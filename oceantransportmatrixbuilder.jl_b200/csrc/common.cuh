@@ -91,6 +91,10 @@ struct otmb_ctx {
     DevBuf sp_colptr, sp_rowval, sp_nzval;  // results of otmb_sparse_build / otmb_spadd_build
     i64 sp_n = 0, sp_nnz = 0;
     DevBuf add_tmp[6];
+    DevBuf tp[5][3];     // transposes of the result matrices (CSC of Xᵀ, 0-based), built on demand by otmb_spmv
+    i64 tp_serial[5] = {-1, -1, -1, -1, -1};
+    i64 build_serial = 0; // bumped by every transportmatrix build / set_operator
+    DevBuf spmv_x, spmv_y;
     DevBuf lump[7];      // lump_and_spray results: LUMP colptr/rowval/nzval, SPRAY colptr/rowval/nzval, vol_c
     i64 lump_nc = 0;
     int lump_base = 0;

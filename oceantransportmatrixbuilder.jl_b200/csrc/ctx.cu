@@ -188,6 +188,10 @@ int otmb_destroy(otmb_ctx* c) {
     for (int q = 0; q < 6; ++q) c->phi[q].release();
     for (int q = 0; q < 2; ++q) c->carry[q].release();
     for (int q = 0; q < 7; ++q) c->lump[q].release();
+    for (int q = 0; q < 5; ++q)
+        for (int r = 0; r < 3; ++r) c->tp[q][r].release();
+    c->spmv_x.release();
+    c->spmv_y.release();
     for (int q = 0; q < 6; ++q) c->add_tmp[q].release();
     for (int q = 0; q < 12; ++q) c->coo[q].release();
     for (int q = 0; q < 5; ++q) {

@@ -57,6 +57,7 @@ int otmb_transportmatrix_build(otmb_ctx* c, const otmb_tm_params* prm, int64_t n
             return otmb_fail(c, OTMB_ERR_BADARG, "pre-built operators were supplied with a different index_base");
     }
     c->out_base = prm->index_base;
+    c->build_serial++;
     OT_TRY(otmb_reset_flags(c));
     CU_TRY(c, cudaEventRecord(c->ev_b0, c->stream));
     const bool all4 = ops == 30;
@@ -145,6 +146,7 @@ int otmb_set_operator(otmb_ctx* c, int which, int64_t nnz, const int64_t* colptr
     }
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     c->nnz[which] = nnz;
+    c->build_serial++;
     c->preset[which] = true;
     c->have_mat[which] = true;
     c->out_base = index_base;

@@ -340,3 +340,26 @@ def test_triad_on_bipolar_top_row_throws_like_reference():
         O.triad(oc.rho3d, oc.lon, oc.lat, o["gm"]["Z3D"], o["v3D"], "bipolar", "J")
     with pytest.raises(A.OTMBError):
         A.globalverticalfacetriadderivative(oc.rho3d, gm, None, "J")
+
+
+# ------------------------------------------------------------------------------------------ resident products
+def test_resident_matvec_matches_scipy_bitwise():
+    """y = X x and y = Xᵀ x on the device-resident results (the τdiv / τvol products of test/online.jl:110-115)
+    against scipy's sequential CSC products on the fetched matrices."""
+    oc = synthetic.make_config("C1t", seed=2)
+    g = gpu_pipeline(oc)
+    N = g["ix"].N
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=N)
+    one = np.ones(N)
+    for name in A.MATRICES:
+        M = getattr(g["tm"], name)
+        for vec in (x, one):
+            yt = otmb_b200.resident_matvec(name, vec, transpose=True)
+            assert np.array_equal(bits(yt), bits(M.T.tocsr() @ vec)), name
+            y = otmb_b200.resident_matvec(name, vec)
+            want = np.zeros(N)
+            ip, ix_, dv = M.indptr, M.indices, M.data
+            for j in range(N):                       # column-by-column CSC product: the order scipy / SparseArrays add in
+                want[ix_[ip[j]:ip[j + 1]]] += dv[ip[j]:ip[j + 1]] * vec[j]
+            assert np.array_equal(bits(y), bits(want)), name
