@@ -360,8 +360,24 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
         wetm = act = mlm = 0;
     }
 
-    // no seam / fold-right cell in this warp: the unrolled fast paths apply (generic columns stage nothing there)
-    const bool warp_regular = __all_sync(0xffffffffu, ord == ORD0);
+    // Rows that precede candidate c inside a column, per class (see ORD0..ORD3): the staging position of an entry
+    // is the popcount of the matrix's mask under this mask.  T, S and B are the same in every class.
+    unsigned lowW, lowC, lowE, lowN;
+    {
+        const unsigned TS = bT | bS;
+        if (ord == ORD0) {            // T S W C E N B
+            lowW = TS; lowC = TS | bW; lowE = TS | bW | bC; lowN = TS | bW | bC | bE;
+        } else if (ord == ORD1) {     // T S C E W N B
+            lowC = TS; lowE = TS | bC; lowW = TS | bC | bE; lowN = TS | bW | bC | bE;
+        } else if (ord == ORD2) {     // T S E W C N B
+            lowE = TS; lowW = TS | bE; lowC = TS | bE | bW; lowN = TS | bW | bC | bE;
+        } else {                      // T S N W C E B
+            lowN = TS; lowW = TS | bN; lowC = TS | bN | bW; lowE = TS | bN | bW | bC;
+        }
+    }
+    auto low_of = [&](const int c) -> unsigned {
+        return c == cT ? 0u : c == cS ? bT : c == cW ? lowW : c == cC ? lowC : c == cE ? lowE : c == cN ? lowN : 0x3fu;
+    };
 
     // copies a generic column's entries of matrix q behind the regular ones
     auto stage_generic = [&](const int q, const int off) {
@@ -404,11 +420,10 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
         const unsigned MX = bT | bE | (fold ? 0u : bN);
         double dsum = 0.0;
         bool first = true, bad = false;
-        int pos = off1, posC = dump;
-        if (warp_regular) {
-            // ---- regular rows (no seam / fold-right cell in the warp): row order = candidate order, so the
-            // code is unrolled with compile-time candidates, the loads are batched, absent faces are skipped
-            // and the staging position is a popcount under a constant mask
+        int posC = dump;
+        {
+            // unrolled with compile-time candidates: the loads are batched, absent faces are skipped, the staging
+            // position is a popcount under the class's row-order mask
             double xs[7], vn[7], rn[7];
 #pragma unroll
             for (int c = 0; c < 7; ++c) {
@@ -420,8 +435,16 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
                 vn[c] = __ldg(P.v3D + Lc);
                 rn[c] = RHO3D ? __ldg(P.rho3d + Lc) : P.rho;
             }
+            auto add = [&](const bool on, const double d) {
+                if (on) {
+                    dsum = first ? d : dsum + d;
+                    first = false;
+                }
+            };
+            double dd[7];
 #pragma unroll
             for (int c = 0; c < 7; ++c) {
+                dd[c] = 0.0;
                 if (c == cC) continue;
                 if ((m_adv >> c) & 1) {
                     const bool mx = c == cT || c == cE || (c == cN && !fold);
@@ -429,11 +452,9 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
                     const double p = mx ? f : -f;
                     const double rb = (rn[c] + rhoC) / 2;
                     const double a = -p / (rb * vn[c]);
-                    const double d = p / (rb * vC);
-                    bad |= isnan(a) || isnan(d);
-                    dsum = first ? d : dsum + d;
-                    first = false;
-                    const int pp = off1 + __popc(m_adv & ((1u << c) - 1u));
+                    dd[c] = p / (rb * vC);
+                    bad |= isnan(a) || isnan(dd[c]);
+                    const int pp = off1 + __popc(m_adv & low_of(c));
                     srow[pp] = S.rk[c][tid];
                     sval[pp] = a;
                     S.Tv[c][tid] = a;
@@ -441,50 +462,24 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
                     S.Tv[c][tid] = 0.0;
                 }
             }
-            posC = (m_adv & bC) ? off1 + __popc(m_adv & (bT | bS | bW)) : dump;
-        } else {
-            // software pipeline: the loads of candidate t+1 are issued before candidate t is computed
-            int c_n = ord & 7;
-            int Lc_n = S.Lc[c_n][tid];
-            double x_n = __ldg(P.phi_nb[(c_n == cN && fold) ? 7 : c_n] + Lc_n), v_n = __ldg(P.v3D + Lc_n);
-            double r_n = RHO3D ? __ldg(P.rho3d + Lc_n) : P.rho;
-    #pragma unroll 1
-            for (int t = 0; t < 7; ++t) {
-                const int c = c_n;
-                const double x = x_n, vnb = v_n, rnb = r_n;
-                if (t < 6) {
-                    c_n = (ord >> (4 * t + 4)) & 7;
-                    Lc_n = S.Lc[c_n][tid];
-                    x_n = __ldg(P.phi_nb[(c_n == cN && fold) ? 7 : c_n] + Lc_n);
-                    v_n = __ldg(P.v3D + Lc_n);
-                    if (RHO3D) r_n = __ldg(P.rho3d + Lc_n);
-                }
-                const bool on = (m_adv >> c) & 1;
-                if (c == cC) {
-                    posC = on ? pos : dump;
-                    pos += on;
-                    continue;
-                }
-                const bool mx = (MX >> c) & 1;
-                const double f = upflux(x, mx, up);
-                const double p = mx ? f : -f;     // pushed magnitude: ϕ for W,S,B slots of the emitter, -ϕ for E,N,T
-                const double rb = (rnb + rhoC) / 2;
-                // absent entries divide 1/1: a zero / NaN operand would send the whole warp through the
-                // slow path of the IEEE division
-                const double pn = on ? p : 1.0;
-                const double a = -pn / (on ? rb * vnb : 1.0);
-                const double d = pn / (on ? rb * vC : 1.0);
-                if (on) {
-                    bad |= isnan(a) || isnan(d);
-                    dsum = first ? d : dsum + d;
-                    first = false;
-                }
-                const int pp = on ? pos : dump;
-                srow[pp] = S.rk[c][tid];
-                sval[pp] = a;
-                pos += on;
-                S.Tv[c][tid] = on ? a : 0.0;
+            // the diagonal adds the emitters' contributions in ascending wet rank = row order of the class
+            add(m_adv & bT, dd[cT]);
+            add(m_adv & bS, dd[cS]);
+            if (ord == ORD0) {
+                add(m_adv & bW, dd[cW]);
+                add(m_adv & bE, dd[cE]);
+                add(m_adv & bN, dd[cN]);
+            } else if (ord == ORD3) {
+                add(m_adv & bN, dd[cN]);
+                add(m_adv & bW, dd[cW]);
+                add(m_adv & bE, dd[cE]);
+            } else {
+                add(m_adv & bE, dd[cE]);
+                add(m_adv & bW, dd[cW]);
+                add(m_adv & bN, dd[cN]);
             }
+            add(m_adv & bB, dd[cB]);
+            posC = (m_adv & bC) ? off1 + __popc(m_adv & lowC) : dump;
         }
         if (bad) errbits |= 2u;
         srow[posC] = rkC;
@@ -499,7 +494,7 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
     // ---- TκH values of regular rows, computed ahead of the barrier so that the look-back has time to finish
     // (:348-415, :426-435): own slots in emit order W,E,S,N with compile-time directions
     double khv[4] = {0.0, 0.0, 0.0, 0.0}, kh_dsum = 0.0;
-    if ((P.build & 4) && warp_regular) {
+    if (P.build & 4) {
         const double thC = __ldg(P.thk + L);
         bool first = true, bad = false;
 #pragma unroll
@@ -547,80 +542,19 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
             bool bad = false;
             int posC = dump;
             double dsum = 0.0;
-            if (warp_regular) {
-                // ---- regular rows: the values were computed ahead of the look-back barrier (khv, kh_dsum)
+            // the values were computed ahead of the look-back barrier (khv, kh_dsum)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int c = q == 0 ? cW : q == 1 ? cE : q == 2 ? cS : cN;
-                    if ((m_kh >> c) & 1) {
-                        const int pp = off2 + __popc(m_kh & ((1u << c) - 1u));
-                        srow[pp] = S.rk[c][tid];
-                        sval[pp] = khv[q];
-                        S.Tv[c][tid] = S.Tv[c][tid] + khv[q];
-                    }
-                }
-                dsum = kh_dsum;
-                posC = (m_kh & bC) ? off2 + __popc(m_kh & (bT | bS | bW)) : dump;
-            } else {
-                double tsW = 0.0, tsE = 0.0, tsS = 0.0, tsN = 0.0;
-                int pos = off2;
-                // software pipeline, as in the Tadv walk
-                struct KhIn {
-                    int c;
-                    double e_own, e_opp, th, d_own, d_opp, v;
-                };
-                auto load_kh = [&](const int t) {
-                    KhIn in;
-                    in.c = (ord >> (4 * t)) & 7;
-                    const int Lc = S.Lc[in.c][tid];
-                    const int own = (OWNDIR >> (4 * in.c)) & 3;
-                    const int opp = (in.c == cN && fold) ? own : own ^ 2;   // the neighbour's side of the shared face (:407)
-                    const int q2 = Lc - k * PP;
-                    in.e_own = __ldg(P.edge + own * PP + p2);
-                    in.e_opp = __ldg(P.edge + opp * PP + q2);
-                    in.th = __ldg(P.thk + Lc);
-                    in.d_own = __ldg(P.dnbr + own * PP + p2);
-                    in.d_opp = __ldg(P.dnbr + opp * PP + q2);
-                    in.v = __ldg(P.v3D + Lc);
-                    return in;
-                };
-                KhIn nxt = load_kh(1);
-    #pragma unroll 1
-                for (int t = 1; t < 6; ++t) {      // T and B sit at both ends of every order word
-                    const KhIn in = nxt;
-                    if (t < 5) nxt = load_kh(t + 1);
-                    const int c = in.c;
-                    const bool on = (m_kh >> c) & 1;
-                    if (c == cC) {
-                        posC = on ? pos : dump;
-                        pos += on;
-                        continue;
-                    }
-                    const double a_own = thC * in.e_own;
-                    const double a_nbr = in.th * in.e_opp;
-                    const double ka = on ? P.kH * jl_min(a_own, a_nbr) : 1.0;   // absent: 1/1, see the Tadv walk
-                    const double ts = ka / (on ? in.d_own * vC : 1.0);     // row 𝑗 seen from 𝑗
-                    const double tn = ka / (on ? in.d_opp * in.v : 1.0);   // row 𝑖 seen from 𝑖
-                    if (on) {
-                        bad |= isnan(ts) || isnan(tn);
-                        tsW = c == cW ? ts : tsW;
-                        tsE = c == cE ? ts : tsE;
-                        tsS = c == cS ? ts : tsS;
-                        tsN = c == cN ? ts : tsN;
-                        S.Tv[c][tid] = S.Tv[c][tid] + (-tn);
-                    }
-                    const int pp = on ? pos : dump;
+            for (int q = 0; q < 4; ++q) {
+                const int c = q == 0 ? cW : q == 1 ? cE : q == 2 ? cS : cN;
+                if ((m_kh >> c) & 1) {
+                    const int pp = off2 + __popc(m_kh & low_of(c));
                     srow[pp] = S.rk[c][tid];
-                    sval[pp] = -tn;
-                    pos += on;
+                    sval[pp] = khv[q];
+                    S.Tv[c][tid] = S.Tv[c][tid] + khv[q];
                 }
-                if (bad) errbits |= 4u;
-                bool first = true;
-                if (m_kh & bW) { dsum = tsW; first = false; }
-                if (m_kh & bE) { dsum = first ? tsE : dsum + tsE; first = false; }
-                if (m_kh & bS) { dsum = first ? tsS : dsum + tsS; first = false; }
-                if (m_kh & bN) { dsum = first ? tsN : dsum + tsN; first = false; }
             }
+            dsum = kh_dsum;
+            posC = (m_kh & bC) ? off2 + __popc(m_kh & lowC) : dump;
             srow[posC] = rkC;
             sval[posC] = dsum;
             if (m_kh & bC) S.Tv[cC][tid] = S.Tv[cC][tid] + dsum;
