@@ -1,29 +1,28 @@
-// fused_v4.cu — OTMB_PATH_FUSED: single-pass direct CSC assembly, one thread per WET cell,
-// written as ROLLED loops over a column's candidates so that the hot code stays inside the
-// instruction caches and the per-thread state stays inside 64 registers.
+// fused_v4.cu — OTMB_PATH_FUSED: single-pass direct CSC assembly, one thread per WET cell.
 //
-// Same mathematics and ordering rules as fused.cu (read its header first: gather form, emit
-// order, generic branch for coincident neighbours).  Why this shape (ncu profiles under
-// profiles/): the fully unrolled predecessors (fused_v2.cu and a v3 since removed) were 8 000-10 000 SASS instructions of straight-line
-// code, each executed once per warp — instruction-cache hit rate 83-95 %, the GPC-level instruction
-// cache at 60-80 % of its request peak, 128 registers (16 warps per SM) or heavy spilling below
-// that; DRAM sat at 20-30 % with traffic equal to the algorithmic bytes.  The kernel was bound by
-// instruction supply and exposed latency, not by bandwidth.  Here:
-//   * per-thread candidate arrays (neighbour linear index, row index, running T value) live in
-//     shared memory, [candidate][thread] so that every access is conflict-free, and are indexed by
-//     a loop variable: the advection, horizontal-diffusion and T "walks" are 7-iteration loops;
-//   * a walk visits the candidates in ascending ROW order, which is a function of the cell's class
-//     only (regular T S W C E N B; west seam T S C E W N B; east seam T S E W C N B; right half
-//     of the tripolar fold row T S N W C E B) — one packed order word per class.  Ascending row
-//     order is also the reference's emit order of Tadv's diagonal contributions, so the walk
-//     accumulates the diagonal in passing; entries are appended to the staging buffer with a
-//     running position (absent entries go to a per-lane dump slot: no branches);
-//   * neighbours are resolved through `rank3d` (Int32 wet rank per grid cell, -1 = dry — the
-//     reference's own Lwet3D, /root/reference/src/matrixbuilding.jl:18-20);
-//   * staging is warp-private and reused matrix by matrix; each warp flushes its own contiguous
-//     slice of rowval/nzval with coalesced stores as soon as it is staged.
+// Same mathematics and ordering rules as fused.cu (read its header first: gather form, emit order, generic
+// branch for coincident neighbours).  The schedule is the result of the ncu profiles under profiles/
+// (history in profiles/README.md).  The fully unrolled predecessor (fused_v2.cu) was 8 000 SASS instructions
+// of straight-line code at 128 registers; a version with rolled loops over the candidates fixed the
+// instruction-cache misses but paid for the warps that held a seam / fold cell.  What is here:
+//   * per-thread candidate arrays (neighbour linear index, row index, running T value) live in shared memory,
+//     [candidate][thread], conflict-free, so that only scalars stay in registers (80, two blocks per SM);
+//   * the row order inside a column is a function of the cell's CLASS only (regular T S W C E N B; west seam
+//     T S C E W N B; east seam T S E W C N B; right half of the tripolar fold row T S N W C E B).  Each class
+//     is four bit masks "rows that precede candidate c"; the staging position of an entry is a popcount of
+//     the matrix's pattern under that mask, and the diagonal of Tadv adds the emitters' contributions in the
+//     class's order (ascending wet rank = the reference's emit order).  One unrolled code path with
+//     compile-time candidates serves every class; absent entries are skipped by a branch;
+//   * neighbours are resolved through `rank3d` (Int32 wet rank per grid cell, -1 = dry — the reference's own
+//     Lwet3D, /root/reference/src/matrixbuilding.jl:18-20);
+//   * a dedicated scan warp per block runs the decoupled look-back for all five counters and releases each
+//     column warp through its own named barrier, so no warp waits for a sibling or for the look-back while it
+//     still has values to compute; the TκH values are computed ahead of that barrier;
+//   * staging is warp-private and reused matrix by matrix; each warp flushes its own contiguous slice of
+//     rowval / nzval with coalesced stores as soon as a matrix is staged;
+//   * the lines of the next level are prefetched into L2 while a level is being assembled.
 //
-// Launch geometry: one tile of TILE consecutive wet cells per block, tiles in block-index order
+// Launch geometry: one tile of TILE consecutive wet cells per block (+ the scan warp), tiles in block-index order
 // (the decoupled look-back only waits on lower-numbered tiles, which are resident or finished).
 // A launch covers the wet ranks [w0, w0 + ncols): the whole matrix on one GPU, or the columns of
 // one k-slab when a matrix is sharded across GPUs (rows are global wet ranks either way).
@@ -44,8 +43,6 @@ constexpr unsigned ORD0 = 0x6543210u;   // T S W C E N B
 constexpr unsigned ORD1 = 0x6524310u;   // T S C E W N B   (west seam: W wraps to the end of the row)
 constexpr unsigned ORD2 = 0x6532410u;   // T S E W C N B   (east seam: E wraps to the start of the row)
 constexpr unsigned ORD3 = 0x6432510u;   // T S N W C E B   (fold row, right half: N mirrors to the left of W)
-// own-side direction (OTMB_DIR_*) of the horizontal candidates: S -> south 0, W -> west 3, E -> east 1, N -> north 2
-constexpr unsigned OWNDIR = 0x00210300u;
 
 struct FastDiv {
     u64 mul;
@@ -410,14 +407,13 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
     };
     auto offset_of = [&](const int q) { return (int)((S.lexcl[tid] >> (12 * q)) & 0xfffull); };
 
-    // ---- Tadv walk (:193-204, :237-297): candidates in ascending row order = ascending emitter rank.
+    // ---- Tadv (:193-204, :237-297).
     // Off-diagonal (𝑖, 𝑗) = -p/m𝑖 as the emitter 𝑖 computes it; the diagonal adds p/m𝑗 per emitter,
     // sparse! keeping the first value and adding the later ones in that order.
     const int off1 = offset_of(1);
     if (P.build & 2) {
         const double rhoC = RHO3D ? __ldg(P.rho3d + L) : P.rho;
         if (RHO3D && valid && isnan(rhoC)) errbits |= 64u;
-        const unsigned MX = bT | bE | (fold ? 0u : bN);
         double dsum = 0.0;
         bool first = true, bad = false;
         int posC = dump;
@@ -534,12 +530,10 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
     if (tile * TILE + wid * 32 < P.ncols) {
         if (P.build & 2) flush(std::integral_constant<int, 7>{}, 1, off1);
 
-        // ---- TκH walk (:348-415, :426-435).  Off-diagonal (𝑖, 𝑗) = -t as 𝑖 computes it; the diagonal sums
-        // 𝑗's own slots in emit order W,E,S,N.
+        // ---- TκH (:348-415, :426-435): stage what was computed ahead of the barrier.  Off-diagonal (𝑖, 𝑗) = -t as 𝑖
+        // computes it; the diagonal sums 𝑗's own slots in emit order W,E,S,N.
         if (P.build & 4) {
             const int off2 = offset_of(2);
-            const double thC = __ldg(P.thk + L);
-            bool bad = false;
             int posC = dump;
             double dsum = 0.0;
             // the values were computed ahead of the look-back barrier (khv, kh_dsum)
@@ -619,21 +613,18 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
             if (P.build & 16) emit_vertical(4, m_dp, dpT, dps, dpB);
         }
 
-        // ---- T walk: union pattern; exact zeros are flagged and removed by the compaction pass
+        // ---- T: union pattern; exact zeros are flagged and removed by the compaction pass
         if (P.build & 1) {
             const int off0 = offset_of(0);
-            int pos = off0;
             bool zero = false;
-#pragma unroll 1
-            for (int t = 0; t < 7; ++t) {
-                const int c = (ord >> (4 * t)) & 7;
+#pragma unroll
+            for (int c = 0; c < 7; ++c) {
                 const bool on = (m_T >> c) & 1;
                 const double v = S.Tv[c][tid];
                 zero |= on && (v == 0.0);
-                const int pp = on ? pos : dump;
+                const int pp = on ? off0 + __popc(m_T & low_of(c)) : dump;
                 srow[pp] = S.rk[c][tid];
                 sval[pp] = v;
-                pos += on;
             }
             if (zero) errbits |= 32u;
             stage_generic(0, off0);
