@@ -247,6 +247,8 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
         const double xE = __ldg(P.pw + Lc[cE]);                       // its West slot, max
         const double xN = __ldg((fold ? P.pn : P.ps) + Lc[cN]);       // its South slot (max), or North on the fold (min)
         const double xB = __ldg(P.pt + Lc[cB]);                       // emitter below: its Top slot, min
+        const double oW = __ldg(P.pw + L), oE = __ldg(P.pe + L), oS = __ldg(P.ps + L), oN = __ldg(P.pn + L),
+                     oB = __ldg(P.pb + L), oT = __ldg(P.pt + L);   // own faces, for the dry-neighbour check below
         const double ml = __ldg(P.mlotst + p2);
         const double z0 = __ldg(P.zt + k), zT = __ldg(P.zt + (hasT ? k - 1 : k)), zB = __ldg(P.zt + (hasB ? k + 1 : k));
         r[cC] = rC;
@@ -272,14 +274,15 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
             if ((wetm & bN) && nz(upflux(xN, !fold, up))) act |= bN;
             if ((wetm & bB) && nz(upflux(xB, false, up))) act |= bB;
             // own faces that point at a dry or absent cell: the reference would push `missing` (:247-250)
+            // (the six own faces were loaded with the first batch: a coastal warp does not pay a second round trip)
             const unsigned dry = ~wetm;
             bool bad = false;
-            if (dry & bW) bad |= nz(upflux(__ldg(P.pw + L), true, up));
-            if (dry & bE) bad |= nz(upflux(__ldg(P.pe + L), false, up));
-            if (dry & bS) bad |= nz(upflux(__ldg(P.ps + L), true, up));
-            if (dry & bN) bad |= nz(upflux(__ldg(P.pn + L), false, up));
-            if (dry & bB) bad |= nz(upflux(__ldg(P.pb + L), true, up));
-            if ((dry & bT) && hasT) bad |= nz(upflux(__ldg(P.pt + L), false, up));
+            if (dry & bW) bad |= nz(upflux(oW, true, up));
+            if (dry & bE) bad |= nz(upflux(oE, false, up));
+            if (dry & bS) bad |= nz(upflux(oS, true, up));
+            if (dry & bN) bad |= nz(upflux(oN, false, up));
+            if (dry & bB) bad |= nz(upflux(oB, true, up));
+            if ((dry & bT) && hasT) bad |= nz(upflux(oT, false, up));
             if (bad) errbits |= 1u;
         }
         // mixed-layer mask Ω = zt[k] < mlotst[i,j] (false for NaN / missing), :85
