@@ -85,8 +85,10 @@ __device__ __forceinline__ u64 warp_sum64(u64 v) {
     for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
     return v;
 }
+// upwind flux max(ϕ, 0) / min(ϕ, 0), or ϕ/2 when centred (:244-295).  Julia's max/min against the literal 0.0 reduce
+// to one comparison: NaN propagates (both comparisons are false for NaN), max(-0.0, 0.0) = 0.0, min(-0.0, 0.0) = -0.0.
 __device__ __forceinline__ double upflux(double x, bool take_max, bool up) {
-    return up ? (take_max ? jl_max(x, 0.0) : jl_min(x, 0.0)) : x / 2;
+    return up ? (take_max ? (!(x <= 0.0) ? x : 0.0) : (!(x > 0.0) ? x : 0.0)) : x / 2;
 }
 __device__ __forceinline__ bool nz(double f) { return f > 0 || f < 0; }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
