@@ -90,6 +90,13 @@ __device__ __forceinline__ u64 warp_sum64(u64 v) {
 __device__ __forceinline__ double upflux(double x, bool take_max, bool up) {
     return up ? (take_max ? (!(x <= 0.0) ? x : 0.0) : (!(x > 0.0) ? x : 0.0)) : x / 2;
 }
+// "is that flux non-zero?" (the reference's `f > 0 || f < 0`, :245), without forming it: upwind -> the sign test
+// itself; centred -> ϕ/2 rounds to zero only for |ϕ| <= the smallest subnormal.  NaN: no.
+template <bool UP>
+__device__ __forceinline__ bool inflow(double x, bool take_max) {
+    if (UP) return take_max ? x > 0.0 : x < 0.0;
+    return fabs(x) > __longlong_as_double(1ll);
+}
 __device__ __forceinline__ bool nz(double f) { return f > 0 || f < 0; }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -107,7 +114,7 @@ struct Smem {
 };
 
 // ---------------------------------------------------------------------------------------
-template <bool RHO3D, int TILE, int MINB>
+template <bool RHO3D, bool UP, int TILE, int MINB, int KHB = 2, bool VAH = true, bool VC0 = true>
 // __grid_constant__: P is indexed dynamically and its address is taken by the generic branch
 __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_constant__ V4Params P) {
     constexpr int NW = TILE / 32;   // column warps; warp NW is the scan warp
@@ -139,34 +146,47 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
         u64 excl[5] = {0, 0, 0, 0, 0};
         unsigned pending = tile > 0 ? 31u : 0u;   // counters still looking back
         int look = tile - 1;
+        // Each step covers LB_SUB windows of 32 tiles with one round trip (all loads are issued before any is tested).
+        // Measured: 1 window 0.466 ms, 2 windows 0.494 ms, 4 windows 0.506 ms — the wider the window, the more scan
+        // warps poll the same hot descriptor lines and the later a publisher's store becomes visible.
+        constexpr int LB_SUB = 1;
         while (pending) {
-            const int t = look - lane;
-            u64 wv[5];
+            u64 wv[LB_SUB][5];
 #pragma unroll
-            for (int m = 0; m < 5; ++m) wv[m] = t >= 0 ? 0ull : ST_PRE;   // before the first tile: prefix 0
+            for (int s = 0; s < LB_SUB; ++s)
+#pragma unroll
+                for (int m = 0; m < 5; ++m) wv[s][m] = (look - 32 * s - lane) >= 0 ? 0ull : ST_PRE;   // before the first tile: prefix 0
             bool again;
-            do {   // the five descriptors of a tile share a 64-byte line; all loads are issued before any is tested
+            do {   // the five descriptors of a tile share a 64-byte line
 #pragma unroll
-                for (int m = 0; m < 5; ++m)
-                    if ((pending >> m & 1) && (wv[m] >> 62) == 0) wv[m] = ld_vol(P.tile_state + (size_t)t * 8 + m);
+                for (int s = 0; s < LB_SUB; ++s)
+#pragma unroll
+                    for (int m = 0; m < 5; ++m)
+                        if ((pending >> m & 1) && (wv[s][m] >> 62) == 0)
+                            wv[s][m] = ld_vol(P.tile_state + (size_t)(look - 32 * s - lane) * 8 + m);
                 again = false;
 #pragma unroll
-                for (int m = 0; m < 5; ++m) again |= (pending >> m & 1) && (wv[m] >> 62) == 0;
+                for (int s = 0; s < LB_SUB; ++s)
+#pragma unroll
+                    for (int m = 0; m < 5; ++m) again |= (pending >> m & 1) && (wv[s][m] >> 62) == 0;
             } while (__any_sync(0xffffffffu, again));
 #pragma unroll
-            for (int m = 0; m < 5; ++m) {
-                if (!(pending >> m & 1)) continue;
-                const u64 val = wv[m] & ST_MASK;
-                const unsigned pm = __ballot_sync(0xffffffffu, (wv[m] >> 62) == 2);
-                if (pm) {
-                    const int first = __ffs(pm) - 1;
-                    excl[m] += warp_sum64(lane <= first ? val : 0ull);
-                    pending &= ~(1u << m);
-                } else {
-                    excl[m] += warp_sum64(val);
+            for (int s = 0; s < LB_SUB; ++s) {   // nearest window first; a counter stops at its first inclusive prefix
+#pragma unroll
+                for (int m = 0; m < 5; ++m) {
+                    if (!(pending >> m & 1)) continue;
+                    const u64 val = wv[s][m] & ST_MASK;
+                    const unsigned pm = __ballot_sync(0xffffffffu, (wv[s][m] >> 62) == 2);
+                    if (pm) {
+                        const int first = __ffs(pm) - 1;
+                        excl[m] += warp_sum64(lane <= first ? val : 0ull);
+                        pending &= ~(1u << m);
+                    } else {
+                        excl[m] += warp_sum64(val);
+                    }
                 }
             }
-            look -= 32;
+            look -= 32 * LB_SUB;
         }
         const u64 mine = lane == 0 ? excl[0] : lane == 1 ? excl[1] : lane == 2 ? excl[2] : lane == 3 ? excl[3] : excl[4];
         if (lane < 5) {
@@ -194,7 +214,7 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
     const int w = tile * TILE + tid;       // column of this launch
     const bool valid = w < P.ncols;
     const int rC = P.w0 + w;               // global wet rank = row/column index
-    const bool up = P.upwind != 0;
+    constexpr bool up = UP;
 
     // ================= phase 0: pattern =================
     int L = 0, k = 0, p2 = 0;
@@ -204,6 +224,7 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
     unsigned m_T = 0, m_adv = 0, m_kh = 0, m_ml = 0, m_dp = 0;
     unsigned errbits = 0;  // 1 dry nbr, 2 nan adv, 4 nan kh, 8 nan ml, 16 nan deep, 32 zero dropped, 64 nan rho
     u64 packed = 0;        // 5 counts, 12 bits each
+    double vC0 = 0.0;      // own volume, requested with the phase-0 batch
     if (valid) {
         int Lc[7], r[7];
         L = __ldg(P.lwet + w);
@@ -252,6 +273,7 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
         const double oW = __ldg(P.pw + L), oE = __ldg(P.pe + L), oS = __ldg(P.ps + L), oN = __ldg(P.pn + L),
                      oB = __ldg(P.pb + L), oT = __ldg(P.pt + L);   // own faces, for the dry-neighbour check below
         const double ml = __ldg(P.mlotst + p2);
+        if (VC0) vC0 = __ldg(P.v3D + L);
         const double z0 = __ldg(P.zt + k), zT = __ldg(P.zt + (hasT ? k - 1 : k)), zB = __ldg(P.zt + (hasB ? k + 1 : k));
         r[cC] = rC;
         r[cT] = hasT ? qT : -1;
@@ -269,22 +291,22 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
         // face flux each neighbour carries through the face it shares with this cell (the value the
         // reference reads at the neighbour, :244-295): only the sign pattern is needed here
         if (P.build & 2) {
-            if ((wetm & bT) && nz(upflux(xT, true, up))) act |= bT;
-            if ((wetm & bS) && nz(upflux(xS, false, up))) act |= bS;
-            if ((wetm & bW) && nz(upflux(xW, false, up))) act |= bW;
-            if ((wetm & bE) && nz(upflux(xE, true, up))) act |= bE;
-            if ((wetm & bN) && nz(upflux(xN, !fold, up))) act |= bN;
-            if ((wetm & bB) && nz(upflux(xB, false, up))) act |= bB;
+            if ((wetm & bT) && inflow<UP>(xT, true)) act |= bT;
+            if ((wetm & bS) && inflow<UP>(xS, false)) act |= bS;
+            if ((wetm & bW) && inflow<UP>(xW, false)) act |= bW;
+            if ((wetm & bE) && inflow<UP>(xE, true)) act |= bE;
+            if ((wetm & bN) && inflow<UP>(xN, !fold)) act |= bN;
+            if ((wetm & bB) && inflow<UP>(xB, false)) act |= bB;
             // own faces that point at a dry or absent cell: the reference would push `missing` (:247-250)
             // (the six own faces were loaded with the first batch: a coastal warp does not pay a second round trip)
             const unsigned dry = ~wetm;
             bool bad = false;
-            if (dry & bW) bad |= nz(upflux(oW, true, up));
-            if (dry & bE) bad |= nz(upflux(oE, false, up));
-            if (dry & bS) bad |= nz(upflux(oS, true, up));
-            if (dry & bN) bad |= nz(upflux(oN, false, up));
-            if (dry & bB) bad |= nz(upflux(oB, true, up));
-            if ((dry & bT) && hasT) bad |= nz(upflux(oT, false, up));
+            if (dry & bW) bad |= inflow<UP>(oW, true);
+            if (dry & bE) bad |= inflow<UP>(oE, false);
+            if (dry & bS) bad |= inflow<UP>(oS, true);
+            if (dry & bN) bad |= inflow<UP>(oN, false);
+            if (dry & bB) bad |= inflow<UP>(oB, true);
+            if ((dry & bT) && hasT) bad |= inflow<UP>(oT, false);
             if (bad) errbits |= 1u;
         }
         // mixed-layer mask Ω = zt[k] < mlotst[i,j] (false for NaN / missing), :85
@@ -340,7 +362,7 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
     int* const srow = S.row[wid];
     double* const sval = S.val[wid];
     const int dump = WDATA + lane;
-    const double vC = __ldg(P.v3D + L);
+    const double vC = VC0 ? vC0 : __ldg(P.v3D + L);
     const int rkC = rC + P.base;
     GenOut gen;      // local memory, only touched by generic columns
 
@@ -404,8 +426,9 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
 #pragma unroll
         for (int it = 0; it < IT; ++it) {
             if (lane + 32 * it < n) {
-                rv[32 * it] = (i64)(unsigned)sr[32 * it];
-                nv[32 * it] = sv[32 * it];
+                // streaming stores: the results are never read again by this kernel; keep L2 for the inputs
+                __stcs(rv + 32 * it, (i64)(unsigned)sr[32 * it]);
+                __stcs(nv + 32 * it, sv[32 * it]);
             }
         }
         __syncwarp();   // the staging buffer may be overwritten by the next matrix
@@ -449,7 +472,7 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
                 if (c == cC) continue;
                 if ((m_adv >> c) & 1) {
                     const bool mx = c == cT || c == cE || (c == cN && !fold);
-                    const double f = upflux(xs[c], mx, up);
+                    const double f = UP ? xs[c] : xs[c] / 2;   // active: max / min picked the flux itself
                     const double p = mx ? f : -f;
                     const double rb = (rn[c] + rhoC) / 2;
                     const double a = -p / (rb * vn[c]);
@@ -498,31 +521,57 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
     if (P.build & 4) {
         const double thC = __ldg(P.thk + L);
         bool first = true, bad = false;
+        // loads of KHB directions are issued as one batch (one round trip), then their values are computed;
+        // the S / N neighbours live on other cache lines than the cell itself, W / E mostly on its own
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int c = q == 0 ? cW : q == 1 ? cE : q == 2 ? cS : cN;
-            const int own = c == cW ? OTMB_DIR_WEST : c == cE ? OTMB_DIR_EAST : c == cS ? OTMB_DIR_SOUTH : OTMB_DIR_NORTH;
-            const int Lc = S.Lc[c][tid];
-            const int q2 = Lc - k * PP;
-            // unconditional loads (clamped indices): free to be hoisted and batched
-            const double e_own = __ldg(P.edge + own * PP + p2), d_own = __ldg(P.dnbr + own * PP + p2);
-            const double* e_oppp = c == cW ? P.edge + OTMB_DIR_EAST * PP : c == cE ? P.edge + OTMB_DIR_WEST * PP
-                                   : c == cS ? P.edge + OTMB_DIR_NORTH * PP
-                                             : P.edge + (fold ? OTMB_DIR_NORTH : OTMB_DIR_SOUTH) * PP;
-            const double e_opp = __ldg(e_oppp + q2);
-            const double d_opp = __ldg(e_oppp + (P.dnbr - P.edge) + q2);
-            const double th = __ldg(P.thk + Lc), vnb = __ldg(P.v3D + Lc);
-            if ((m_kh >> c) & 1) {
-                const double ka = P.kH * jl_min(thC * e_own, th * e_opp);
-                const double ts = ka / (d_own * vC);       // row 𝑗 seen from 𝑗
-                const double tn = ka / (d_opp * vnb);      // row 𝑖 seen from 𝑖
-                bad |= isnan(ts) || isnan(tn);
-                kh_dsum = first ? ts : kh_dsum + ts;
-                first = false;
-                khv[q] = -tn;
+        for (int q0 = 0; q0 < 4; q0 += KHB) {
+            double e_own[KHB], d_own[KHB], e_opp[KHB], d_opp[KHB], th[KHB], vnb[KHB];
+#pragma unroll
+            for (int u = 0; u < KHB; ++u) {
+                const int q = q0 + u;
+                const int c = q == 0 ? cW : q == 1 ? cE : q == 2 ? cS : cN;
+                const int own = c == cW ? OTMB_DIR_WEST : c == cE ? OTMB_DIR_EAST : c == cS ? OTMB_DIR_SOUTH : OTMB_DIR_NORTH;
+                const int Lc = S.Lc[c][tid];
+                const int q2 = Lc - k * PP;
+                // unconditional loads (clamped indices)
+                e_own[u] = __ldg(P.edge + own * PP + p2);
+                d_own[u] = __ldg(P.dnbr + own * PP + p2);
+                const double* e_oppp = c == cW ? P.edge + OTMB_DIR_EAST * PP : c == cE ? P.edge + OTMB_DIR_WEST * PP
+                                       : c == cS ? P.edge + OTMB_DIR_NORTH * PP
+                                                 : P.edge + (fold ? OTMB_DIR_NORTH : OTMB_DIR_SOUTH) * PP;
+                e_opp[u] = __ldg(e_oppp + q2);
+                d_opp[u] = __ldg(e_oppp + (P.dnbr - P.edge) + q2);
+                th[u] = __ldg(P.thk + Lc);
+                vnb[u] = __ldg(P.v3D + Lc);
+            }
+#pragma unroll
+            for (int u = 0; u < KHB; ++u) {
+                const int q = q0 + u;
+                const int c = q == 0 ? cW : q == 1 ? cE : q == 2 ? cS : cN;
+                if ((m_kh >> c) & 1) {
+                    const double ka = P.kH * jl_min(thC * e_own[u], th[u] * e_opp[u]);
+                    const double ts = ka / (d_own[u] * vC);       // row 𝑗 seen from 𝑗
+                    const double tn = ka / (d_opp[u] * vnb[u]);   // row 𝑖 seen from 𝑖
+                    bad |= isnan(ts) || isnan(tn);
+                    kh_dsum = first ? ts : kh_dsum + ts;
+                    first = false;
+                    khv[q] = -tn;
+                }
             }
         }
         if (bad) errbits |= 4u;
+    }
+
+    // ---- inputs of the vertical operators, requested ahead of the barrier: they arrive while the warp waits for
+    // its offsets and flushes Tadv / TκH (clamped indices, unconditional)
+    double vt_area = 0.0, vt_dB = 0.0, vt_dT = 0.0, vt_vB = 0.0, vt_vT = 0.0;
+    if (VAH && (P.build & 24)) {
+        vt_area = __ldg(P.area2D + p2);
+        const double ztC = __ldg(P.zt + k);
+        vt_dB = fabs(ztC - __ldg(P.zt + (k < g.nz - 1 ? k + 1 : k)));
+        vt_dT = fabs(ztC - __ldg(P.zt + (k > 0 ? k - 1 : k)));
+        vt_vB = __ldg(P.v3D + S.Lc[cB][tid]);
+        vt_vT = __ldg(P.v3D + S.Lc[cT][tid]);
     }
 
     // meet the scan warp's offsets (S.excl, S.wbase5) at this warp's own barrier; it has normally arrived long ago
@@ -565,14 +614,14 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
         if (P.build & 24) {
             double dpT = 0.0, dpB = 0.0, dps = 0.0, mlT = 0.0, mlB = 0.0, mls = 0.0;
             if (m_dp | m_ml) {
-                const double area = __ldg(P.area2D + p2), ztC = __ldg(P.zt + k);
+                const double area = VAH ? vt_area : __ldg(P.area2D + p2), ztC = VAH ? 0.0 : __ldg(P.zt + k);
                 bool firstm = true, firstd = true, badm = false, badd = false;
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     const int c = q == 0 ? cB : cT;
                     if (!(wetm >> c & 1)) continue;
-                    const double d = fabs(ztC - __ldg(P.zt + (c == cT ? k - 1 : k + 1)));
-                    const double qs = d * vC, qn = d * __ldg(P.v3D + S.Lc[c][tid]);
+                    const double d = VAH ? (c == cT ? vt_dT : vt_dB) : fabs(ztC - __ldg(P.zt + (c == cT ? k - 1 : k + 1)));
+                    const double qs = d * vC, qn = d * (VAH ? (c == cT ? vt_vT : vt_vB) : __ldg(P.v3D + S.Lc[c][tid]));
                     if (m_dp) {
                         const double ka = P.kVdeep * area;
                         const double ts = ka / qs, tn = ka / qn;
@@ -661,7 +710,7 @@ FastDiv make_fastdiv(unsigned d) {
     return f;
 }
 
-template <bool RHO3D, int TILE, int MINB>
+template <bool RHO3D, bool UP, int TILE, int MINB, int KHB = 2, bool VAH = true, bool VC0 = true>
 int launch_v4(otmb_ctx* c, V4Params& P) {
     const int ntiles = (int)(((i64)P.ncols + TILE - 1) / TILE);
     P.ntiles = ntiles;
@@ -669,8 +718,8 @@ int launch_v4(otmb_ctx* c, V4Params& P) {
     P.tile_state = c->tile_state.as<u64>();
     CU_TRY(c, cudaMemsetAsync(P.tile_state, 0, (size_t)ntiles * 8 * sizeof(u64), c->stream));
     const size_t smem = sizeof(Smem<TILE>);
-    CU_TRY(c, cudaFuncSetAttribute(k_fused_v4<RHO3D, TILE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_fused_v4<RHO3D, TILE, MINB><<<ntiles, TILE + 32, smem, c->stream>>>(P);
+    CU_TRY(c, cudaFuncSetAttribute(k_fused_v4<RHO3D, UP, TILE, MINB, KHB, VAH, VC0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_fused_v4<RHO3D, UP, TILE, MINB, KHB, VAH, VC0><<<ntiles, TILE + 32, smem, c->stream>>>(P);
     LAUNCHED(c);
     CU_TRY(c, cudaGetLastError());
     return OTMB_OK;
@@ -734,11 +783,15 @@ int otmb_fused_v4_build(otmb_ctx* c, const otmb_tm_params* prm, int build) {
     }
     static const int variant = getenv("OTMB_V4_VARIANT") ? atoi(getenv("OTMB_V4_VARIANT")) : 0;
     // TILE column threads + one scan warp per block
-    if (c->have_rho3d) return launch_v4<true, 352, 2>(c, P);
-    switch (variant) {   // launch geometries kept for A/B runs (profiles/bench_variants.sh)
-        case 1: return launch_v4<false, 224, 3>(c, P);
-        case 5: return launch_v4<false, 288, 2>(c, P);
-        case 7: return launch_v4<false, 608, 1>(c, P);   // one block per SM: 2 % faster on C2, 8 % slower on C4
-        default: return launch_v4<false, 352, 2>(c, P);   // measured best on C2 (profiles/README.md)
+    const bool up = prm->upwind != 0;
+    if (c->have_rho3d) return up ? launch_v4<true, true, 352, 2>(c, P) : launch_v4<true, false, 352, 2>(c, P);
+    if (!up) return launch_v4<false, false, 352, 2>(c, P);
+    switch (variant) {   // launch geometries / schedules kept for A/B runs (profiles/bench_variants.sh)
+        case 1: return launch_v4<false, true, 224, 3>(c, P);
+        case 2: return launch_v4<false, true, 416, 2>(c, P);   // 72 registers
+        case 3: return launch_v4<false, true, 352, 2, 1>(c, P);   // TκH loads direction by direction
+        case 4: return launch_v4<false, true, 352, 2, 2, false, false>(c, P);   // vertical inputs and own volume loaded where they are used
+        case 7: return launch_v4<false, true, 608, 1>(c, P);   // one block per SM
+        default: return launch_v4<false, true, 352, 2>(c, P);   // measured best on C2 (profiles/README.md)
     }
 }
