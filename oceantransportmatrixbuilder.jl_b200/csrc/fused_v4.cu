@@ -175,14 +175,15 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
 #pragma unroll
                 for (int m = 0; m < 5; ++m) {
                     if (!(pending >> m & 1)) continue;
+                    // a tile's aggregate fits 13 bits, 32 of them one redux.sync; only an inclusive prefix needs 62 bits
                     const u64 val = wv[s][m] & ST_MASK;
                     const unsigned pm = __ballot_sync(0xffffffffu, (wv[s][m] >> 62) == 2);
                     if (pm) {
                         const int first = __ffs(pm) - 1;
-                        excl[m] += warp_sum64(lane <= first ? val : 0ull);
+                        excl[m] += (u64)__reduce_add_sync(0xffffffffu, lane < first ? (unsigned)val : 0u) + __shfl_sync(0xffffffffu, val, first);
                         pending &= ~(1u << m);
                     } else {
-                        excl[m] += warp_sum64(val);
+                        excl[m] += (u64)__reduce_add_sync(0xffffffffu, (unsigned)val);
                     }
                 }
             }
