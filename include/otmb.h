@@ -157,6 +157,13 @@ typedef struct otmb_tm_params {
 int otmb_transportmatrix_build(otmb_ctx* ctx, const otmb_tm_params* params, int64_t nnz_out[5]);
 /* copy one result out as SparseMatrixCSC fields: colptr (N+1), rowval (nnz), nzval (nnz) */
 int otmb_transportmatrix_fetch(otmb_ctx* ctx, int which, int64_t* colptr, int64_t* rowval, double* nzval);
+/* the same for several results at once (bit m of mask = matrix OTMB_MAT_m, 0 = all five; NULL entries are
+ * skipped): what the shim calls to fill the NamedTuple (; T, Tadv, TκH, TκVML, TκVdeep) of
+ * src/matrixbuilding.jl:149.  One pipeline for all arrays: the Int64 indices cross PCIe as Int32 and are widened
+ * into the caller's arrays by host threads (OTMB_HOST_THREADS, default min(8, cores/2)) while the values are in
+ * flight; matrices with 2^31 or more rows / entries are copied as they are.  Both calls return identical arrays. */
+int otmb_transportmatrix_fetch_all(otmb_ctx* ctx, int mask, int64_t* const colptr[5], int64_t* const rowval[5],
+                                   double* const nzval[5]);
 /* a pre-built operator passed by the caller (the Tadv/TκH/TκVML/TκVdeep kwargs, :133-143);
  * indices in params.index_base of the next build */
 int otmb_set_operator(otmb_ctx* ctx, int which, int64_t nnz, const int64_t* colptr, const int64_t* rowval,

@@ -369,14 +369,16 @@ def transportmatrix(*, ϕ, mlotst, gridmetrics, indices, ρ, κH=500.0, κVML=0.
                       _L.PATH[path], mask)
     nnz = (C.c_int64 * 5)()
     ctx.check(lib.otmb_transportmatrix_build(ctx.h, C.byref(prm), nnz))
-    out = []
+    # every result that was built comes back through ONE pipelined fetch (Int32 indices on the link, widened on the host)
+    arrays, fmask = {}, 0
     for m in range(5):
         if m >= 1 and preset[m] is not None:
-            out.append(preset[m])
             continue
-        cp, rv, nz = ctx.pinned_empty(N + 1, np.int64), ctx.pinned_empty(nnz[m], np.int64), ctx.pinned_empty(nnz[m], np.float64)
-        ctx.check(lib.otmb_transportmatrix_fetch(ctx.h, m, _ptr(cp), _ptr(rv), _ptr(nz)))
-        out.append(_csc(N, cp, rv, nz))
+        arrays[m] = (ctx.pinned_empty(N + 1, np.int64), ctx.pinned_empty(nnz[m], np.int64), ctx.pinned_empty(nnz[m], np.float64))
+        fmask |= 1 << m
+    ptrs = [(C.c_void_p * 5)(*[_ptr(arrays[m][q]).value if m in arrays else None for m in range(5)]) for q in range(3)]
+    ctx.check(lib.otmb_transportmatrix_fetch_all(ctx.h, fmask, *ptrs))
+    out = [_csc(N, *arrays[m]) if m in arrays else preset[m] for m in range(5)]
     return TransportMatrices(*out)
 
 

@@ -101,6 +101,10 @@ struct otmb_ctx {
     bool have_lump = false;
     DevBuf l2;
 
+    // host-side fetch pipeline (fetch.cu): aux stream, pinned ring, widening threads; created on first use
+    void* fetch_state = nullptr;
+    void (*fetch_state_free)(void*) = nullptr;
+
     i64 launches = 0;
     float last_build_ms = 0.f;
 };

@@ -199,6 +199,7 @@ int otmb_destroy(otmb_ctx* c) {
         c->rowval[q].release();
         c->nzval[q].release();
     }
+    if (c->fetch_state && c->fetch_state_free) c->fetch_state_free(c->fetch_state);
     if (c->h_flags) cudaFreeHost(c->h_flags);
     cudaEventDestroy(c->ev_t0);
     cudaEventDestroy(c->ev_t1);

@@ -117,19 +117,7 @@ int otmb_transportmatrix_build(otmb_ctx* c, const otmb_tm_params* prm, int64_t n
     return OTMB_OK;
 }
 
-int otmb_transportmatrix_fetch(otmb_ctx* c, int which, int64_t* colptr, int64_t* rowval, double* nzval) {
-    if (!c || which < 0 || which > 4) return OTMB_ERR_BADARG;
-    OT_TRY(otmb_need(c, c->have_mat[which], "otmb_transportmatrix_build"));
-    CU_TRY(c, cudaSetDevice(c->device));
-    if (colptr)
-        CU_TRY(c, cudaMemcpyAsync(colptr, c->colptr[which].p, (size_t)(c->ncols + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
-    if (rowval && c->nnz[which] > 0)
-        CU_TRY(c, cudaMemcpyAsync(rowval, c->rowval[which].p, (size_t)c->nnz[which] * 8, cudaMemcpyDeviceToHost, c->stream));
-    if (nzval && c->nnz[which] > 0)
-        CU_TRY(c, cudaMemcpyAsync(nzval, c->nzval[which].p, (size_t)c->nnz[which] * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU_TRY(c, cudaStreamSynchronize(c->stream));
-    return OTMB_OK;
-}
+// otmb_transportmatrix_fetch / otmb_transportmatrix_fetch_all: fetch.cu
 
 int otmb_set_operator(otmb_ctx* c, int which, int64_t nnz, const int64_t* colptr, const int64_t* rowval,
                       const double* nzval, int32_t index_base) {

@@ -163,16 +163,26 @@ function transportmatrix(; ϕ, mlotst, gridmetrics, indices, ρ, κH = 500.0, κ
     prm = Ref(TMParams(κH, κVML, κVdeep, ρ isa Number ? Float64(ρ) : 0.0, upwind, 1, 0, mask))
     nnzs = zeros(Int64, 5)
     check(c, ccall((:otmb_transportmatrix_build, LIBOTMB), Cint, (Ptr{Cvoid}, Ref{TMParams}, Ptr{Int64}), c.h, prm, nnzs))
-    function fetch(m)
-        colptr = Vector{Int64}(undef, N + 1); rowval = Vector{Int64}(undef, nnzs[m + 1]); nzval = Vector{Float64}(undef, nnzs[m + 1])
-        check(c, ccall((:otmb_transportmatrix_fetch, LIBOTMB), Cint, (Ptr{Cvoid}, Cint, Ptr{Int64}, Ptr{Int64}, P), c.h, m, colptr, rowval, nzval))
-        return SparseMatrixCSC{Float64, Int64}(N, N, colptr, rowval, nzval)   # already sorted, 1-based: no copy
+    # one pipelined fetch for every matrix that was built (otmb_transportmatrix_fetch_all: Int32 indices on the PCIe
+    # link, widened into these Int64 vectors by host threads while the values are in flight)
+    want = [true, isnothing(Tadv), isnothing(TκH), isnothing(TκVML), isnothing(TκVdeep)]
+    colptrs = [want[m] ? Vector{Int64}(undef, N + 1) : Int64[] for m in 1:5]
+    rowvals = [want[m] ? Vector{Int64}(undef, nnzs[m]) : Int64[] for m in 1:5]
+    nzvals = [want[m] ? Vector{Float64}(undef, nnzs[m]) : Float64[] for m in 1:5]
+    fmask = Cint(sum(want[m] ? 1 << (m - 1) : 0 for m in 1:5))
+    GC.@preserve colptrs rowvals nzvals begin
+        pc = [want[m] ? pointer(colptrs[m]) : Ptr{Int64}(C_NULL) for m in 1:5]
+        pr = [want[m] ? pointer(rowvals[m]) : Ptr{Int64}(C_NULL) for m in 1:5]
+        pv = [want[m] ? pointer(nzvals[m]) : Ptr{Float64}(C_NULL) for m in 1:5]
+        check(c, ccall((:otmb_transportmatrix_fetch_all, LIBOTMB), Cint, (Ptr{Cvoid}, Cint, Ptr{Ptr{Int64}}, Ptr{Ptr{Int64}}, Ptr{Ptr{Float64}}),
+                       c.h, fmask, pc, pr, pv))
     end
-    T = fetch(0)
-    Tadv = isnothing(Tadv) ? fetch(1) : Tadv
-    TκH = isnothing(TκH) ? fetch(2) : TκH
-    TκVML = isnothing(TκVML) ? fetch(3) : TκVML
-    TκVdeep = isnothing(TκVdeep) ? fetch(4) : TκVdeep
+    csc(m) = SparseMatrixCSC{Float64, Int64}(N, N, colptrs[m], rowvals[m], nzvals[m])   # already sorted, 1-based: no copy
+    T = csc(1)
+    Tadv = isnothing(Tadv) ? csc(2) : Tadv
+    TκH = isnothing(TκH) ? csc(3) : TκH
+    TκVML = isnothing(TκVML) ? csc(4) : TκVML
+    TκVdeep = isnothing(TκVdeep) ? csc(5) : TκVdeep
     return (; T, Tadv, TκH, TκVML, TκVdeep)
 end
 

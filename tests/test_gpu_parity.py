@@ -363,3 +363,36 @@ def test_resident_matvec_matches_scipy_bitwise():
             for j in range(N):                       # column-by-column CSC product: the order scipy / SparseArrays add in
                 want[ix_[ip[j]:ip[j + 1]]] += dv[ip[j]:ip[j + 1]] * vec[j]
             assert np.array_equal(bits(y), bits(want)), name
+
+
+# ------------------------------------------------------------------------------------------ fetch pipeline
+def test_fetch_paths_return_identical_arrays(monkeypatch):
+    """otmb_transportmatrix_fetch_all (Int32 indices on the link, widened on the host, chunked ring) against the
+    direct 8-byte copies and the one-matrix call: same bits in every array."""
+    import ctypes as C
+    oc = synthetic.make_config("C1t", seed=3)
+    g = gpu_pipeline(oc)
+    ctx = otmb_b200.default_context(0)
+    N = g["ix"].N
+    nnz = [getattr(g["tm"], n).nnz for n in A.MATRICES]
+
+    def fetch_all():
+        arrs = [[np.full(N + 1, -7, np.int64) for _ in range(5)], [np.full(nnz[m], -7, np.int64) for m in range(5)],
+                [np.full(nnz[m], np.nan) for m in range(5)]]
+        ptrs = [(C.c_void_p * 5)(*[a.ctypes.data for a in arrs[q]]) for q in range(3)]
+        ctx.check(ctx.lib.otmb_transportmatrix_fetch_all(ctx.h, 0, *ptrs))
+        return arrs
+
+    narrow = fetch_all()
+    monkeypatch.setenv("OTMB_FETCH_DIRECT", "1")
+    direct = fetch_all()
+    monkeypatch.delenv("OTMB_FETCH_DIRECT")
+    for q in range(3):
+        for m in range(5):
+            assert np.array_equal(bits(narrow[q][m]) if q == 2 else narrow[q][m], bits(direct[q][m]) if q == 2 else direct[q][m]), (q, m)
+    for m, name in enumerate(A.MATRICES):
+        cp, rv, nz = np.empty(N + 1, np.int64), np.empty(nnz[m], np.int64), np.empty(nnz[m])
+        ctx.check(ctx.lib.otmb_transportmatrix_fetch(ctx.h, m, A._ptr(cp), A._ptr(rv), A._ptr(nz)))
+        assert np.array_equal(cp, direct[0][m]) and np.array_equal(rv, direct[1][m]) and np.array_equal(bits(nz), bits(direct[2][m]))
+        M = getattr(g["tm"], name)        # 0-based scipy view of the same build
+        assert np.array_equal(cp - cp[0], M.indptr) and np.array_equal(rv - cp[0], M.indices)
