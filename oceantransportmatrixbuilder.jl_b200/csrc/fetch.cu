@@ -144,7 +144,10 @@ int fetch_state(otmb_ctx* c, FetchState** out, size_t entries) {
             f->narrow.release();
             delete f;
         };
-        int nt = (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+        // half the cores, shared with the other ranks of this box (torchrun exports LOCAL_WORLD_SIZE)
+        int lws = 1;
+        if (const char* e = getenv("LOCAL_WORLD_SIZE")) lws = std::max(1, atoi(e));
+        int nt = (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / (2u * (unsigned)lws)));
         if (const char* e = getenv("OTMB_HOST_THREADS")) nt = std::max(0, atoi(e));
         f->pool = new WidenPool(nt);
     }
