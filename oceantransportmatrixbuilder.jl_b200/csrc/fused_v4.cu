@@ -20,13 +20,21 @@
 //     still has values to compute; the TκH values are computed ahead of that barrier;
 //   * staging is warp-private and reused matrix by matrix; each warp flushes its own contiguous slice of
 //     rowval / nzval with coalesced stores as soon as a matrix is staged;
-//   * the lines of the next level are prefetched into L2 while a level is being assembled.
+//   * the lines of the next level are prefetched into L2 while a level is being assembled;
+//   * the upwind switch is a template parameter (flux-sign tests are single comparisons); the TκH inputs are
+//     requested in two batches of two directions, the vertical operators' inputs and the cell's own volume ahead of
+//     the barrier / with the phase-0 batch; results leave with streaming stores; the scan warp sums a tile's counts
+//     and a look-back window's aggregates with redux.sync, the per-warp offsets inside a tile are derived by the
+//     column warps themselves (they are not on the path to the publication of the tile's aggregate);
+//   * OTMB_V4_TIMELINE=<file> runs a debug instantiation that stamps every tile's phases (profiles/timeline.py).
 //
 // Launch geometry: one tile of TILE consecutive wet cells per block (+ the scan warp), tiles in block-index order
 // (the decoupled look-back only waits on lower-numbered tiles, which are resident or finished).
 // A launch covers the wet ranks [w0, w0 + ncols): the whole matrix on one GPU, or the columns of
 // one k-slab when a matrix is sharded across GPUs (rows are global wet ranks either way).
+#include <cstdio>
 #include <cstdlib>
+#include <vector>
 #include <type_traits>
 
 #include "fused_generic.cuh"
@@ -71,6 +79,7 @@ struct V4Params {
     double* nzval[5];
     DevFlags* flags;
     u64* tile_state;
+    long long* timeline;   // TLINE instantiation only (OTMB_V4_TIMELINE): 64 stamps per tile, see profiles/timeline.py
 };
 
 // look-back descriptors: device-scope relaxed accesses (a plain `volatile` access is system scope)
@@ -109,12 +118,11 @@ struct Smem {
     int rk[7][TILE];               // row index (+ index base) of candidate c
     u64 lexcl[TILE];               // in-warp exclusive offsets of the column, five 12-bit fields
     u64 warp[TILE / 32];           // entries of each warp, five 12-bit fields
-    unsigned wbase5[TILE / 32][8]; // in-tile offset of each warp, per matrix
     u64 excl[5];
 };
 
 // ---------------------------------------------------------------------------------------
-template <bool RHO3D, bool UP, int TILE, int MINB, int KHB = 2, bool VAH = true, bool VC0 = true>
+template <bool RHO3D, bool UP, int TILE, int MINB, int KHB = 2, bool VAH = true, bool VC0 = true, bool TLINE = false>
 // __grid_constant__: P is indexed dynamically and its address is taken by the generic branch
 __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_constant__ V4Params P) {
     constexpr int NW = TILE / 32;   // column warps; warp NW is the scan warp
@@ -125,6 +133,26 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int tile = blockIdx.x;
+    // timeline instrumentation (debug instantiation): SM clock stamps of one tile's phases
+    long long* const tl = TLINE ? P.timeline + (size_t)tile * 64 : nullptr;
+    // (a clock read right behind BAR.SYNC.DEFER_BLOCKING issues before the barrier resolves: stamps behind a barrier
+    // take a value loaded from shared memory AFTER it as an input, which orders them)
+    auto stamp = [&](const int slot, const u64 dep = 0) {
+        if (TLINE) {
+            long long t;
+            asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "l"(dep) : "memory");
+            if (lane == 0) tl[slot] = t;
+        }
+    };
+    if (TLINE && tid == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+        tl[0] = (long long)gt;
+        tl[1] = clock64();
+        unsigned smid;
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        tl[6] = smid;
+    }
 
     // ================= the scan warp: decoupled look-back for all five counters =================
     // It owns no columns, so the column warps never wait for a warp that still has values to compute:
@@ -133,16 +161,20 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
         // producer / consumer named barriers: the column warps only ARRIVE at barrier 1 (no wait) once their
         // counts are in S.warp; the scan warp only arrives at barrier 2 once the offsets are in S.excl
         asm volatile("bar.sync 1, %0;" ::"r"(TILE + 32) : "memory");
-        // lane m < 5 owns counter m: in-tile offsets of the column warps (a tile's total may exceed a 12-bit field)
+        stamp(2, TLINE ? *reinterpret_cast<volatile u64*>(&S.warp[0]) : 0);
+        // the tile's five totals: lane q < NW holds the packed counts of column warp q, one redux.sync per counter; lane
+        // m < 5 publishes counter m.  (The in-tile offsets of the column warps are NOT computed here: every column warp
+        // derives its own from S.warp after its release barrier, which keeps them off the path to the publication.)
+        const u64 pk = lane < NW ? *reinterpret_cast<volatile u64*>(&S.warp[lane]) : 0ull;
         unsigned agg_m = 0;
-        if (lane < 5) {
 #pragma unroll
-            for (int q = 0; q < NW; ++q) {
-                S.wbase5[q][lane] = agg_m;
-                agg_m += (unsigned)((*reinterpret_cast<volatile u64*>(&S.warp[q]) >> (12 * lane)) & 0xfffull);
-            }
-            st_vol(P.tile_state + (size_t)tile * 8 + lane, (tile == 0 ? ST_PRE : ST_AGG) | (u64)agg_m);
+        for (int m = 0; m < 5; ++m) {
+            const unsigned tot = __reduce_add_sync(0xffffffffu, (unsigned)((pk >> (12 * m)) & 0xfffull));
+            if (lane == m) agg_m = tot;
         }
+        if (lane < 5) st_vol(P.tile_state + (size_t)tile * 8 + lane, (tile == 0 ? ST_PRE : ST_AGG) | (u64)agg_m);
+        stamp(3);
+        int rounds = 0;
         u64 excl[5] = {0, 0, 0, 0, 0};
         unsigned pending = tile > 0 ? 31u : 0u;   // counters still looking back
         int look = tile - 1;
@@ -188,7 +220,10 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
                 }
             }
             look -= 32 * LB_SUB;
+            ++rounds;
         }
+        stamp(4);
+        if (TLINE && lane == 0) tl[5] = rounds;
         const u64 mine = lane == 0 ? excl[0] : lane == 1 ? excl[1] : lane == 2 ? excl[2] : lane == 3 ? excl[3] : excl[4];
         if (lane < 5) {
             const u64 agg = agg_m;
@@ -200,7 +235,7 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
             }
         }
         __threadfence_block();
-        // S.excl and S.wbase5 published: release the column warps through their own barriers (ids 2 .. 15, one per
+        // S.excl published: release the column warps through their own barriers (ids 2 .. 15, one per
         // warp when the tile has at most 14 of them; participants: the warps of the group + this one), so that no
         // column warp waits for a sibling's values
 #pragma unroll
@@ -356,6 +391,7 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
     if (lane == 31) S.warp[wid] = incl;
     __threadfence_block();
     asm volatile("bar.arrive 1, %0;" ::"r"(TILE + 32) : "memory");   // counts published; nobody waits here
+    stamp(8 + 4 * wid);
     // kept in shared memory, not in registers: they are needed again only at the five flushes, and as
     // registers they were spilled to local memory (ncu: 25 % of the long-scoreboard stalls were their reloads)
     S.lexcl[tid] = incl - packed;                              // in-warp exclusive offsets of this column
@@ -416,7 +452,9 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
     // (iters = compile-time bound on ceil(entries of a warp / 32): the matrix's maximum entries per column)
     auto flush = [&](auto iters, const int q, const int off) {
         constexpr int IT = decltype(iters)::value;
-        const u64 g0 = *reinterpret_cast<volatile u64*>(&S.excl[q]) + *reinterpret_cast<volatile unsigned*>(&S.wbase5[wid][q]);
+        // offset of this warp inside the tile: the counts of the column warps before it
+        const u64 pkq = lane < wid ? *reinterpret_cast<volatile u64*>(&S.warp[lane]) : 0ull;
+        const u64 g0 = *reinterpret_cast<volatile u64*>(&S.excl[q]) + __reduce_add_sync(0xffffffffu, (unsigned)((pkq >> (12 * q)) & 0xfffull));
         const int n = (int)((S.warp[wid] >> (12 * q)) & 0xfffull);
         if (valid) P.colptr[q][w] = (i64)(g0 + (u64)off) + P.base;
         __syncwarp();
@@ -575,12 +613,14 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
         vt_vT = __ldg(P.v3D + S.Lc[cT][tid]);
     }
 
-    // meet the scan warp's offsets (S.excl, S.wbase5) at this warp's own barrier; it has normally arrived long ago
+    // meet the scan warp's offsets (S.excl) at this warp's own barrier; it has normally arrived long ago
+    stamp(9 + 4 * wid);
     {
         const int gq = wid / BG;
         const int members = (gq + 1) * BG <= NW ? BG : NW - gq * BG;
         asm volatile("bar.sync %0, %1;" ::"r"(2 + gq), "r"(32 * members + 32) : "memory");
     }
+    stamp(10 + 4 * wid, TLINE ? *reinterpret_cast<volatile u64*>(&S.excl[0]) : 0);
 
     if (tile * TILE + wid * 32 < P.ncols) {
         if (P.build & 2) flush(std::integral_constant<int, 7>{}, 1, off1);
@@ -687,6 +727,7 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
         }
     }
 
+    stamp(11 + 4 * wid);
     // ---- flags: one atomic per warp and kind
     if (__any_sync(0xffffffffu, errbits != 0)) {
 #pragma unroll
@@ -711,18 +752,34 @@ FastDiv make_fastdiv(unsigned d) {
     return f;
 }
 
-template <bool RHO3D, bool UP, int TILE, int MINB, int KHB = 2, bool VAH = true, bool VC0 = true>
+template <bool RHO3D, bool UP, int TILE, int MINB, int KHB = 2, bool VAH = true, bool VC0 = true, bool TLINE = false>
 int launch_v4(otmb_ctx* c, V4Params& P) {
     const int ntiles = (int)(((i64)P.ncols + TILE - 1) / TILE);
     P.ntiles = ntiles;
     CU_TRY(c, c->tile_state.ensure((size_t)ntiles * 8 * sizeof(u64)));
     P.tile_state = c->tile_state.as<u64>();
     CU_TRY(c, cudaMemsetAsync(P.tile_state, 0, (size_t)ntiles * 8 * sizeof(u64), c->stream));
+    DevBuf tline;
+    if (TLINE) {
+        CU_TRY(c, tline.ensure((size_t)ntiles * 64 * 8));
+        CU_TRY(c, cudaMemsetAsync(tline.p, 0, (size_t)ntiles * 64 * 8, c->stream));
+    }
+    P.timeline = tline.as<long long>();
     const size_t smem = sizeof(Smem<TILE>);
-    CU_TRY(c, cudaFuncSetAttribute(k_fused_v4<RHO3D, UP, TILE, MINB, KHB, VAH, VC0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_fused_v4<RHO3D, UP, TILE, MINB, KHB, VAH, VC0><<<ntiles, TILE + 32, smem, c->stream>>>(P);
+    CU_TRY(c, cudaFuncSetAttribute(k_fused_v4<RHO3D, UP, TILE, MINB, KHB, VAH, VC0, TLINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_fused_v4<RHO3D, UP, TILE, MINB, KHB, VAH, VC0, TLINE><<<ntiles, TILE + 32, smem, c->stream>>>(P);
     LAUNCHED(c);
     CU_TRY(c, cudaGetLastError());
+    if (TLINE) {   // raw dump: ntiles x 64 int64 (profiles/timeline.py)
+        std::vector<long long> h((size_t)ntiles * 64);
+        CU_TRY(c, cudaMemcpyAsync(h.data(), tline.p, h.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        if (FILE* f = fopen(getenv("OTMB_V4_TIMELINE"), "wb")) {
+            fwrite(h.data(), 8, h.size(), f);
+            fclose(f);
+        }
+        tline.release();
+    }
     return OTMB_OK;
 }
 
@@ -787,6 +844,7 @@ int otmb_fused_v4_build(otmb_ctx* c, const otmb_tm_params* prm, int build) {
     const bool up = prm->upwind != 0;
     if (c->have_rho3d) return up ? launch_v4<true, true, 352, 2>(c, P) : launch_v4<true, false, 352, 2>(c, P);
     if (!up) return launch_v4<false, false, 352, 2>(c, P);
+    if (getenv("OTMB_V4_TIMELINE")) return launch_v4<false, true, 352, 2, 2, true, true, true>(c, P);   // per-tile phase stamps
     switch (variant) {   // launch geometries / schedules kept for A/B runs (profiles/bench_variants.sh)
         case 1: return launch_v4<false, true, 224, 3>(c, P);
         case 2: return launch_v4<false, true, 416, 2>(c, P);   // 72 registers
