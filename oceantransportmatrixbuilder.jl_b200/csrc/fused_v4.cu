@@ -114,7 +114,6 @@ struct Smem {
     double val[TILE / 32][WCAP];   // warp-private staging: values
     double Tv[7][TILE];            // running T = ((Tadv + TκH) + TκVML) + TκVdeep, by candidate
     int row[TILE / 32][WCAP];      // warp-private staging: row indices (+ index base)
-    int Lc[7][TILE];               // linear index of candidate c (clamped to a valid cell)
     int rk[7][TILE];               // row index (+ index base) of candidate c
     u64 lexcl[TILE];               // in-warp exclusive offsets of the column, five 12-bit fields
     u64 warp[TILE / 32];           // entries of each warp, five 12-bit fields
@@ -321,7 +320,6 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
 #pragma unroll
         for (int c = 0; c < 7; ++c) {
             if (c != cC && r[c] >= 0) wetm |= 1u << c;
-            S.Lc[c][tid] = Lc[c];
             S.rk[c][tid] = r[c] + P.base;
         }
         // face flux each neighbour carries through the face it shares with this cell (the value the
@@ -376,10 +374,25 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
     } else {
 #pragma unroll
         for (int c = 0; c < 7; ++c) {
-            S.Lc[c][tid] = 0;
             S.rk[c][tid] = 0;
         }
     }
+
+    // Linear index of candidate c (clamped to a valid cell), recomputed from L, k, p2 and the class where it is needed:
+    // two or three integer instructions each.  It used to be kept in shared memory; without that array two blocks fit
+    // the 132 KB shared-memory carve-out instead of 164 KB, which leaves L1 124 KB instead of 92 KB.
+    if (!valid) ord = ORD1;   // L = 0: keeps every neighbour index of an idle thread inside the arrays
+    // first / last cell of a grid row, from the class: ORD1 = west seam; ORD2 = east seam unless the row has one cell
+    const bool atW = ord == ORD1, atE = ord == ORD2 || g.nx == 1;
+    auto Lc_of = [&](const int c) -> int {
+        return c == cT   ? (k > 0 ? L - PP : L)
+               : c == cB ? (k < g.nz - 1 ? L + PP : L)
+               : c == cS ? (p2 >= g.nx ? L - g.nx : L)
+               : c == cW ? (atW ? L + (g.nx - 1) : L - 1)
+               : c == cE ? (atE ? L - (g.nx - 1) : L + 1)
+               : c == cN ? (p2 < PP - g.nx ? L + g.nx : (fold ? L + (g.nx - 1 - 2 * (p2 - (g.ny - 1) * g.nx)) : L))
+                         : L;
+    };
 
     // ================= tile scan + decoupled look-back =================
     u64 incl = packed;
@@ -408,7 +421,7 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
         int g_Lc[7], g_r[7];
         unsigned g_err = 0;
         for (int c = 0; c < 7; ++c) {
-            g_Lc[c] = S.Lc[c][tid];
+            g_Lc[c] = c == 0 ? Lc_of(0) : c == 1 ? Lc_of(1) : c == 2 ? Lc_of(2) : c == 3 ? Lc_of(3) : c == 4 ? Lc_of(4) : c == 5 ? Lc_of(5) : Lc_of(6);
             g_r[c] = S.rk[c][tid] - P.base;
             const bool mx = c == cT || c == cE || (c == cN && !fold);
             const double f = c == cC ? 0.0 : upflux(__ldg(P.phi_nb[(c == cN && fold) ? 7 : c] + g_Lc[c]), mx, up);
@@ -491,7 +504,7 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
 #pragma unroll
             for (int c = 0; c < 7; ++c) {
                 if (c == cC) continue;
-                const int Lc = S.Lc[c][tid];
+                const int Lc = Lc_of(c);
                 const double* ph = c == cT ? P.pb : c == cS ? P.pn : c == cW ? P.pe : c == cE ? P.pw : c == cB ? P.pt
                                                                                                : (fold ? P.pn : P.ps);
                 xs[c] = __ldg(ph + Lc);
@@ -570,7 +583,7 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
                 const int q = q0 + u;
                 const int c = q == 0 ? cW : q == 1 ? cE : q == 2 ? cS : cN;
                 const int own = c == cW ? OTMB_DIR_WEST : c == cE ? OTMB_DIR_EAST : c == cS ? OTMB_DIR_SOUTH : OTMB_DIR_NORTH;
-                const int Lc = S.Lc[c][tid];
+                const int Lc = Lc_of(c);
                 const int q2 = Lc - k * PP;
                 // unconditional loads (clamped indices)
                 e_own[u] = __ldg(P.edge + own * PP + p2);
@@ -609,8 +622,8 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
         const double ztC = __ldg(P.zt + k);
         vt_dB = fabs(ztC - __ldg(P.zt + (k < g.nz - 1 ? k + 1 : k)));
         vt_dT = fabs(ztC - __ldg(P.zt + (k > 0 ? k - 1 : k)));
-        vt_vB = __ldg(P.v3D + S.Lc[cB][tid]);
-        vt_vT = __ldg(P.v3D + S.Lc[cT][tid]);
+        vt_vB = __ldg(P.v3D + Lc_of(cB));
+        vt_vT = __ldg(P.v3D + Lc_of(cT));
     }
 
     // meet the scan warp's offsets (S.excl) at this warp's own barrier; it has normally arrived long ago
@@ -662,7 +675,7 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
                     const int c = q == 0 ? cB : cT;
                     if (!(wetm >> c & 1)) continue;
                     const double d = VAH ? (c == cT ? vt_dT : vt_dB) : fabs(ztC - __ldg(P.zt + (c == cT ? k - 1 : k + 1)));
-                    const double qs = d * vC, qn = d * (VAH ? (c == cT ? vt_vT : vt_vB) : __ldg(P.v3D + S.Lc[c][tid]));
+                    const double qs = d * vC, qn = d * (VAH ? (c == cT ? vt_vT : vt_vB) : __ldg(P.v3D + Lc_of(c)));
                     if (m_dp) {
                         const double ka = P.kVdeep * area;
                         const double ts = ka / qs, tn = ka / qn;
@@ -766,6 +779,8 @@ int launch_v4(otmb_ctx* c, V4Params& P) {
     }
     P.timeline = tline.as<long long>();
     const size_t smem = sizeof(Smem<TILE>);
+    if (const char* e = getenv("OTMB_V4_CARVEOUT"))   // experiment: shared-memory carve-out in % of the maximum
+        CU_TRY(c, cudaFuncSetAttribute(k_fused_v4<RHO3D, UP, TILE, MINB, KHB, VAH, VC0, TLINE>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
     CU_TRY(c, cudaFuncSetAttribute(k_fused_v4<RHO3D, UP, TILE, MINB, KHB, VAH, VC0, TLINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_fused_v4<RHO3D, UP, TILE, MINB, KHB, VAH, VC0, TLINE><<<ntiles, TILE + 32, smem, c->stream>>>(P);
     LAUNCHED(c);
