@@ -5,8 +5,10 @@
 // (history in profiles/README.md).  The fully unrolled predecessor (fused_v2.cu) was 8 000 SASS instructions
 // of straight-line code at 128 registers; a version with rolled loops over the candidates fixed the
 // instruction-cache misses but paid for the warps that held a seam / fold cell.  What is here:
-//   * per-thread candidate arrays (neighbour linear index, row index, running T value) live in shared memory,
-//     [candidate][thread], conflict-free, so that only scalars stay in registers (80, two blocks per SM);
+//   * per-thread candidate arrays (row index, running T value) live in shared memory, [candidate][thread],
+//     conflict-free, so that only scalars stay in registers (80, two blocks per SM); the candidates' linear indices
+//     are recomputed where needed — shared memory is paid for in L1 here: 64.75 KB per block lets two blocks use the
+//     132 KB carve-out (L1 124 KB), with the index array it was the 164 KB one and 3.5 % slower;
 //   * the row order inside a column is a function of the cell's CLASS only (regular T S W C E N B; west seam
 //     T S C E W N B; east seam T S E W C N B; right half of the tripolar fold row T S N W C E B).  Each class
 //     is four bit masks "rows that precede candidate c"; the staging position of an entry is a popcount of
