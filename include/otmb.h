@@ -164,6 +164,9 @@ int otmb_transportmatrix_fetch(otmb_ctx* ctx, int which, int64_t* colptr, int64_
  * flight; matrices with 2^31 or more rows / entries are copied as they are.  Both calls return identical arrays. */
 int otmb_transportmatrix_fetch_all(otmb_ctx* ctx, int mask, int64_t* const colptr[5], int64_t* const rowval[5],
                                    double* const nzval[5]);
+/* host half of that pipeline alone (no GPU needed): sign-extend n Int32 indices into Int64 on `threads` pool
+ * threads (0 = the calling thread). */
+int otmb_host_widen(const int32_t* src, int64_t* dst, int64_t n, int32_t threads);
 /* a pre-built operator passed by the caller (the Tadv/TκH/TκVML/TκVdeep kwargs, :133-143);
  * indices in params.index_base of the next build */
 int otmb_set_operator(otmb_ctx* ctx, int which, int64_t nnz, const int64_t* colptr, const int64_t* rowval,

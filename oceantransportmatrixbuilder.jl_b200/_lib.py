@@ -19,7 +19,7 @@ EXPORTS = [
     "otmb_version", "otmb_device_count", "otmb_status_string", "otmb_create", "otmb_destroy", "otmb_last_error",
     "otmb_host_alloc", "otmb_host_free", "otmb_set_grid", "otmb_makeindices", "otmb_get_indices",
     "otmb_gridmetrics", "otmb_set_gridmetrics", "otmb_facefluxes", "otmb_set_facefluxes", "otmb_set_mlotst",
-    "otmb_set_rho3d", "otmb_transportmatrix_build", "otmb_transportmatrix_fetch", "otmb_transportmatrix_fetch_all", "otmb_set_operator",
+    "otmb_set_rho3d", "otmb_transportmatrix_build", "otmb_transportmatrix_fetch", "otmb_transportmatrix_fetch_all", "otmb_host_widen", "otmb_set_operator",
     "otmb_sparse_build", "otmb_sparse_fetch", "otmb_spadd_build", "otmb_spadd_fetch", "otmb_triad_derivative",
     "otmb_dyad_derivative", "otmb_bolus_gm_velocity", "otmb_timer_start", "otmb_timer_stop", "otmb_l2_flush",
     "otmb_launch_count", "otmb_last_build_ms", "otmb_synchronize", "otmb_set_slab", "otmb_slab_counts",
@@ -67,6 +67,7 @@ def load():
         "otmb_transportmatrix_build": ([vp, C.POINTER(TMParams), pi64], C.c_int),
         "otmb_transportmatrix_fetch": ([vp, C.c_int, vp, vp, vp], C.c_int),
         "otmb_transportmatrix_fetch_all": ([vp, C.c_int, vp, vp, vp], C.c_int),
+        "otmb_host_widen": ([vp, vp, i64, i32], C.c_int),
         "otmb_set_operator": ([vp, C.c_int, i64, vp, vp, vp, i32], C.c_int),
         "otmb_sparse_build": ([vp, i64, vp, vp, vp, i64, pi64], C.c_int),
         "otmb_sparse_fetch": ([vp, vp, vp, vp], C.c_int),

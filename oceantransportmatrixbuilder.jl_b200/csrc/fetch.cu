@@ -244,3 +244,14 @@ int otmb_transportmatrix_fetch_all(otmb_ctx* c, int mask, int64_t* const colptr[
         if (mask >> m & 1) OT_TRY(otmb_need(c, c->have_mat[m], "otmb_transportmatrix_build"));
     return fetch_impl(c, mask, colptr, rowval, nzval);
 }
+
+// the host half of the pipeline on its own (no device involved): widen n Int32 indices into Int64 with `threads`
+// pool threads (0 = the calling thread only) — what the CPU test suite exercises
+int otmb_host_widen(const int32_t* src, int64_t* dst, int64_t n, int32_t threads) {
+    if (n < 0 || threads < 0 || threads > 64 || (n > 0 && (!src || !dst))) return OTMB_ERR_BADARG;
+    WidenPool pool(threads);
+    const size_t step = (size_t)3 << 20;   // several jobs through the same pool, like the chunks of a fetch
+    for (size_t lo = 0; lo < (size_t)n; lo += step) pool.run(src + lo, dst + lo, std::min(step, (size_t)n - lo));
+    return OTMB_OK;
+}
+

@@ -130,3 +130,22 @@ def test_bench_reference_arm_prints_contract_line():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "nnz(T)/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+@pytest.mark.parametrize("threads", [0, 1, 3, 8])
+def test_host_widening_of_the_fetch_pipeline(threads):
+    """The host half of otmb_transportmatrix_fetch_all (csrc/fetch.cu): Int32 indices that crossed the link are
+    sign-extended into the caller's Int64 arrays by a pool of threads (AVX2 + scalar head / tail).  No GPU involved."""
+    lib = _lib.load()
+    rng = np.random.default_rng(threads)
+    for n in (0, 1, 7, 65535, 65536, 65537, (1 << 22) + 13, (7 << 20) + 5):
+        src = rng.integers(-2**31, 2**31 - 1, size=n, dtype=np.int64).astype(np.int32)
+        if n > 2:
+            src[:3] = (np.iinfo(np.int32).max, np.iinfo(np.int32).min, -1)
+        for shift in (0, 1):                        # destination 32-byte aligned or not
+            buf = np.full(n + 4, -99, np.int64)
+            dst = buf[shift:shift + n]
+            assert lib.otmb_host_widen(src.ctypes.data_as(C.c_void_p), dst.ctypes.data_as(C.c_void_p), n, threads) == 0
+            assert np.array_equal(dst, src.astype(np.int64))
+            assert (buf[:shift] == -99).all() and (buf[shift + n:] == -99).all()      # nothing written outside
+    assert lib.otmb_host_widen(None, None, -1, 0) != 0
