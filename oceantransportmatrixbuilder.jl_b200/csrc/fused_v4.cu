@@ -781,9 +781,22 @@ int launch_v4(otmb_ctx* c, V4Params& P) {
     }
     P.timeline = tline.as<long long>();
     const size_t smem = sizeof(Smem<TILE>);
-    if (const char* e = getenv("OTMB_V4_CARVEOUT"))   // experiment: shared-memory carve-out in % of the maximum
-        CU_TRY(c, cudaFuncSetAttribute(k_fused_v4<RHO3D, UP, TILE, MINB, KHB, VAH, VC0, TLINE>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
     CU_TRY(c, cudaFuncSetAttribute(k_fused_v4<RHO3D, UP, TILE, MINB, KHB, VAH, VC0, TLINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // Shared memory is paid for in L1 on this kernel (3 - 4 % per 32 KB, profiles/README.md): ask for the smallest
+    // carve-out that still holds MINB blocks (sm_100: 0/8/16/32/64/100/132/164/196/228 KB; the driver rounds a
+    // percentage UP to the next of these, so the request is rounded down).  OTMB_V4_CARVEOUT=<percent> overrides.
+    {
+        static const int kb[] = {0, 8, 16, 32, 64, 100, 132, 164, 196, 228};
+        const size_t need = (size_t)MINB * (smem + 1024);
+        int pct = 100;
+        for (int q = 0; q < 10; ++q)
+            if ((size_t)kb[q] * 1024 >= need) {
+                pct = kb[q] * 100 / 228;
+                break;
+            }
+        if (const char* e = getenv("OTMB_V4_CARVEOUT")) pct = atoi(e);
+        CU_TRY(c, cudaFuncSetAttribute(k_fused_v4<RHO3D, UP, TILE, MINB, KHB, VAH, VC0, TLINE>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    }
     k_fused_v4<RHO3D, UP, TILE, MINB, KHB, VAH, VC0, TLINE><<<ntiles, TILE + 32, smem, c->stream>>>(P);
     LAUNCHED(c);
     CU_TRY(c, cudaGetLastError());
