@@ -156,7 +156,12 @@ int fetch_state(otmb_ctx* c, FetchState** out, size_t entries) {
         if (f->stage) cudaFreeHost(f->stage);
         f->stage = nullptr, f->stage_cap = 0;
         const size_t cap = entries + entries / 8 + 1024;
-        CU_TRY(c, cudaMallocHost((void**)&f->stage, cap * sizeof(int)));
+        if (cudaMallocHost((void**)&f->stage, cap * sizeof(int)) != cudaSuccess) {   // no pinnable memory left:
+            cudaGetLastError();                                                      // the caller copies directly
+            f->stage = nullptr;
+            *out = nullptr;
+            return OTMB_OK;
+        }
         f->stage_cap = cap;
     }
     const int need = (int)((entries + CHUNK - 1) / CHUNK);
@@ -181,16 +186,19 @@ int fetch_impl(otmb_ctx* c, int mask, int64_t* const colptr[5], int64_t* const r
         if (rowval && rowval[m] && c->nnz[m] > 0)
             segs.push_back({c->rowval[m].as<i64>(), rowval[m], total, (size_t)c->nnz[m]}), total += (size_t)c->nnz[m];
     }
-    if (!fits || total > STAGE_CAP || (total + CHUNK - 1) / CHUNK > (size_t)MAX_EVENTS) {   // indices beyond 32 bits (or more than the staging cap): as they are
+    auto direct = [&]() -> int {   // the arrays cross the link as they are
         for (const Segment& s : segs) CU_TRY(c, cudaMemcpyAsync(s.host, s.dev, s.len * 8, cudaMemcpyDeviceToHost, c->stream));
         for (int m = 0; m < 5; ++m)
             if ((mask >> m & 1) && nzval && nzval[m] && c->nnz[m] > 0)
                 CU_TRY(c, cudaMemcpyAsync(nzval[m], c->nzval[m].p, (size_t)c->nnz[m] * 8, cudaMemcpyDeviceToHost, c->stream));
         CU_TRY(c, cudaStreamSynchronize(c->stream));
         return OTMB_OK;
-    }
+    };
+    // indices beyond 32 bits, or more of them than the staging cap
+    if (!fits || total > STAGE_CAP || (total + CHUNK - 1) / CHUNK > (size_t)MAX_EVENTS) return direct();
     FetchState* f = nullptr;
     OT_TRY(fetch_state(c, &f, total));
+    if (!f) return direct();
     // indices: narrow on the device, cross the link first, chunk by chunk into pinned staging ...
     CU_TRY(c, f->narrow.ensure(std::max<size_t>(total, 1) * sizeof(int)));
     int* const nar = f->narrow.as<int>();
