@@ -123,7 +123,7 @@ struct Smem {
 };
 
 // ---------------------------------------------------------------------------------------
-template <bool RHO3D, bool UP, int TILE, int MINB, int KHB = 2, bool VAH = true, bool VC0 = true, bool TLINE = false>
+template <bool RHO3D, bool UP, int TILE, int MINB, int KHB = 2, bool VAH = true, bool VC0 = true, bool TLINE = false, bool XSM = true>
 // __grid_constant__: P is indexed dynamically and its address is taken by the generic branch
 __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_constant__ V4Params P) {
     constexpr int NW = TILE / 32;   // column warps; warp NW is the scan warp
@@ -309,6 +309,9 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
         const double xB = __ldg(P.pt + Lc[cB]);                       // emitter below: its Top slot, min
         const double oW = __ldg(P.pw + L), oE = __ldg(P.pe + L), oS = __ldg(P.ps + L), oN = __ldg(P.pn + L),
                      oB = __ldg(P.pb + L), oT = __ldg(P.pt + L);   // own faces, for the dry-neighbour check below
+        if (XSM) {   // the neighbours' fluxes wait for Tadv in the (still unused) running-T slots instead of being re-loaded
+            S.Tv[cT][tid] = xT, S.Tv[cS][tid] = xS, S.Tv[cW][tid] = xW, S.Tv[cE][tid] = xE, S.Tv[cN][tid] = xN, S.Tv[cB][tid] = xB;
+        }
         const double ml = __ldg(P.mlotst + p2);
         if (VC0) vC0 = __ldg(P.v3D + L);
         const double z0 = __ldg(P.zt + k), zT = __ldg(P.zt + (hasT ? k - 1 : k)), zB = __ldg(P.zt + (hasB ? k + 1 : k));
@@ -509,7 +512,7 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
                 const int Lc = Lc_of(c);
                 const double* ph = c == cT ? P.pb : c == cS ? P.pn : c == cW ? P.pe : c == cE ? P.pw : c == cB ? P.pt
                                                                                                : (fold ? P.pn : P.ps);
-                xs[c] = __ldg(ph + Lc);
+                xs[c] = XSM ? S.Tv[c][tid] : __ldg(ph + Lc);
                 vn[c] = __ldg(P.v3D + Lc);
                 rn[c] = RHO3D ? __ldg(P.rho3d + Lc) : P.rho;
             }
@@ -767,7 +770,7 @@ FastDiv make_fastdiv(unsigned d) {
     return f;
 }
 
-template <bool RHO3D, bool UP, int TILE, int MINB, int KHB = 2, bool VAH = true, bool VC0 = true, bool TLINE = false>
+template <bool RHO3D, bool UP, int TILE, int MINB, int KHB = 2, bool VAH = true, bool VC0 = true, bool TLINE = false, bool XSM = true>
 int launch_v4(otmb_ctx* c, V4Params& P) {
     const int ntiles = (int)(((i64)P.ncols + TILE - 1) / TILE);
     P.ntiles = ntiles;
@@ -781,7 +784,7 @@ int launch_v4(otmb_ctx* c, V4Params& P) {
     }
     P.timeline = tline.as<long long>();
     const size_t smem = sizeof(Smem<TILE>);
-    CU_TRY(c, cudaFuncSetAttribute(k_fused_v4<RHO3D, UP, TILE, MINB, KHB, VAH, VC0, TLINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_TRY(c, cudaFuncSetAttribute(k_fused_v4<RHO3D, UP, TILE, MINB, KHB, VAH, VC0, TLINE, XSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // Shared memory is paid for in L1 on this kernel (3 - 4 % per 32 KB, profiles/README.md): ask for the smallest
     // carve-out that still holds MINB blocks (sm_100: 0/8/16/32/64/100/132/164/196/228 KB; the driver rounds a
     // percentage UP to the next of these, so the request is rounded down).  OTMB_V4_CARVEOUT=<percent> overrides.
@@ -795,9 +798,9 @@ int launch_v4(otmb_ctx* c, V4Params& P) {
                 break;
             }
         if (const char* e = getenv("OTMB_V4_CARVEOUT")) pct = atoi(e);
-        CU_TRY(c, cudaFuncSetAttribute(k_fused_v4<RHO3D, UP, TILE, MINB, KHB, VAH, VC0, TLINE>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        CU_TRY(c, cudaFuncSetAttribute(k_fused_v4<RHO3D, UP, TILE, MINB, KHB, VAH, VC0, TLINE, XSM>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     }
-    k_fused_v4<RHO3D, UP, TILE, MINB, KHB, VAH, VC0, TLINE><<<ntiles, TILE + 32, smem, c->stream>>>(P);
+    k_fused_v4<RHO3D, UP, TILE, MINB, KHB, VAH, VC0, TLINE, XSM><<<ntiles, TILE + 32, smem, c->stream>>>(P);
     LAUNCHED(c);
     CU_TRY(c, cudaGetLastError());
     if (TLINE) {   // raw dump: ntiles x 64 int64 (profiles/timeline.py)
@@ -876,7 +879,7 @@ int otmb_fused_v4_build(otmb_ctx* c, const otmb_tm_params* prm, int build) {
     if (!up) return launch_v4<false, false, 352, 2>(c, P);
     if (getenv("OTMB_V4_TIMELINE")) return launch_v4<false, true, 352, 2, 2, true, true, true>(c, P);   // per-tile phase stamps
     switch (variant) {   // launch geometries / schedules kept for A/B runs (profiles/bench_variants.sh)
-        case 1: return launch_v4<false, true, 224, 3>(c, P);
+        case 1: return launch_v4<false, true, 352, 2, 2, true, true, false, false>(c, P);   // Tadv re-loads the neighbours' fluxes
         case 2: return launch_v4<false, true, 416, 2>(c, P);   // 72 registers
         case 3: return launch_v4<false, true, 352, 2, 1>(c, P);   // TκH loads direction by direction
         case 4: return launch_v4<false, true, 352, 2, 2, false, false>(c, P);   // vertical inputs and own volume loaded where they are used
