@@ -243,6 +243,7 @@ def run_sharded(args, rank, local_rank, world):
                        "parallelism": f"k-slab x{world}; NCCL only for the face-flux carry planes (setup, not in the timed region)",
                        "l2": "no flush: per-step working set >> 126 MB L2", "prepare_s": t_prep},
             "kernel_ms": k_ms,
+        "kernel_ms_min_median_max": [min(kernel_ms), sorted(kernel_ms)[len(kernel_ms) // 2], max(kernel_ms)],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes": b_in + b_out, "algorithmic_bytes_slowest_rank": b_rank,
                          "kernel": "k_fused_v4 (slowest rank's slab)"},
@@ -431,6 +432,7 @@ def main():
                    "parallelism": f"batch: one matrix per GPU x{world}, no collective",
                    "l2": f"no flush: per-step working set {(b_in + b_out) / 1e6:.0f} MB > 126 MB L2"},
         "kernel_ms": k_ms,
+        "kernel_ms_min_median_max": [min(kernel_ms), sorted(kernel_ms)[len(kernel_ms) // 2], max(kernel_ms)],
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": b_in + b_out,
                      "kernel": "k_fused_v4 (whole transportmatrix in one launch)" if args.path == "fused" else args.path,
