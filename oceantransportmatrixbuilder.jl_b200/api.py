@@ -363,7 +363,9 @@ def transportmatrix(*, ϕ, mlotst, gridmetrics, indices, ρ, κH=500.0, κVML=0.
     for m, v in preset.items():
         if v is not None:
             v = sp.csc_matrix(v)
-            cp, rv, nz = v.indptr.astype(np.int64), v.indices.astype(np.int64), v.data.astype(np.float64)
+            # no copies when the operator already has the API's types (e.g. a result of an earlier call, still page-locked)
+            cp, rv, nz = (np.ascontiguousarray(v.indptr, np.int64), np.ascontiguousarray(v.indices, np.int64),
+                          np.ascontiguousarray(v.data, np.float64))
             ctx.check(lib.otmb_set_operator(ctx.h, m, len(rv), _ptr(cp), _ptr(rv), _ptr(nz), 0))
     prm = _L.TMParams(float(κH), float(κVML), float(κVdeep), float(ρ) if np.isscalar(ρ) else 0.0, int(bool(upwind)), 0,
                       _L.PATH[path], mask)
