@@ -372,8 +372,12 @@ def main():
         h2d = 6 * M * 8 + P * 8
         # bytes that cross the link: values as Float64, indices narrowed to Int32 on the device and widened into the
         # Int64 host arrays by the library (fetch.cu); the host arrays filled are sum(8 (N+1) + 16 nnz) bytes
-        d2h = sum(4 * (N + 1) + 12 * nnz_list[m] for m in range(5))
         host_out = sum(8 * (N + 1) + 16 * nnz_list[m] for m in range(5))
+        # the library's own policy (csrc/fetch.cu): Int32 indices only when at least four host threads per rank are free
+        lws = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
+        nthreads = min(8, max(1, (os.cpu_count() or 1) // (2 * lws)))
+        narrow = "OTMB_FETCH_DIRECT" not in os.environ and ("OTMB_HOST_THREADS" in os.environ or nthreads >= 4)
+        d2h = sum(4 * (N + 1) + 12 * nnz_list[m] for m in range(5)) if narrow else host_out
 
         def e2e_step():
             ctx.check(lib.otmb_set_facefluxes(ctx.h, ptrs))
@@ -443,7 +447,8 @@ def main():
     if e2e_ms is not None:
         line["e2e"] = {"value": nnzT_total / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                        "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "host_bytes_out_per_step": host_out,
-                       "note": "indices cross PCIe as Int32 and are widened to the API's Int64 by host threads inside the call"}
+                       "note": ("indices cross PCIe as Int32 and are widened to the API's Int64 by host threads inside the call"
+                                if d2h != host_out else "plain 8-byte copies (too few host threads per rank for the Int32 path)")}
     if world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
         v3D, area = O.clean_missing(oc.volcello), O.clean_missing(oc.areacello)

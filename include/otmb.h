@@ -160,8 +160,9 @@ int otmb_transportmatrix_fetch(otmb_ctx* ctx, int which, int64_t* colptr, int64_
 /* the same for several results at once (bit m of mask = matrix OTMB_MAT_m, 0 = all five; NULL entries are
  * skipped): what the shim calls to fill the NamedTuple (; T, Tadv, TκH, TκVML, TκVdeep) of
  * src/matrixbuilding.jl:149.  One pipeline for all arrays: the Int64 indices cross PCIe as Int32 and are widened
- * into the caller's arrays by host threads (OTMB_HOST_THREADS, default min(8, cores/2)) while the values are in
- * flight; matrices with 2^31 or more rows / entries are copied as they are.  Both calls return identical arrays. */
+ * into the caller's arrays by host threads (OTMB_HOST_THREADS, default min(8, cores / (2 LOCAL_WORLD_SIZE))) while the
+ * values are in flight; matrices with 2^31 or more rows / entries, or ranks with fewer than four such threads to
+ * spare, copy the 8-byte arrays as they are.  Both calls return identical arrays. */
 int otmb_transportmatrix_fetch_all(otmb_ctx* ctx, int mask, int64_t* const colptr[5], int64_t* const rowval[5],
                                    double* const nzval[5]);
 /* host half of that pipeline alone (no GPU needed): sign-extend n Int32 indices into Int64 on `threads` pool
