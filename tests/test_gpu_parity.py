@@ -396,3 +396,32 @@ def test_fetch_paths_return_identical_arrays(monkeypatch):
         assert np.array_equal(cp, direct[0][m]) and np.array_equal(rv, direct[1][m]) and np.array_equal(bits(nz), bits(direct[2][m]))
         M = getattr(g["tm"], name)        # 0-based scipy view of the same build
         assert np.array_equal(cp - cp[0], M.indptr) and np.array_equal(rv - cp[0], M.indices)
+
+
+# ------------------------------------------------------------------------------------------ subnormal fluxes
+@pytest.mark.parametrize("upwind", [True, False])
+def test_subnormal_fluxes_match_oracle(upwind):
+    """Fluxes of one to three units of the smallest subnormal.  Centred scheme: ϕ/2 rounds to zero for one unit (no
+    entry, src/matrixbuilding.jl:245) and to one / two units otherwise — the kernel's sign tests never form ϕ/2, this
+    pins that they decide the same.  Upwind: every Tadv value underflows to an explicit zero, which `sparse` keeps
+    and the sum `T = Tadv + ...` drops (:147: the compaction pass); the divisions take their slow path."""
+    oc = synthetic.make_config("C1t", seed=5)
+    o = oracle_pipeline(oc)
+    tiny = np.float64(5e-324)
+    phi = {}
+    for name, a in o["phi"].items():
+        units = 1 + (np.arange(a.size).reshape(a.shape, order="F") % 3)
+        phi[name] = np.asfortranarray(np.sign(a) * units * tiny)
+    gm = o["gm"]
+    want = O.transportmatrix(phi, oc.mlotst, o["v3D"], gm["thkcello"], o["area"], oc.lev, gm["edge"], gm["dnbr"], o["topo"],
+                             1035.0, upwind=upwind)
+    for path in ("fused", "fused2", "coo"):
+        tm, _ = transport_from_oracle_inputs(dict(o, phi=phi), oc, path=path, upwind=upwind)
+        for oname, gname in NAMES.items():
+            assert_csc_equal(getattr(tm, gname), want[oname], f"subnormal {path} {oname} upwind={upwind}", exact=True)
+    # the one-unit faces really are absent from the centred operator (and only from it)
+    two = {name: np.asfortranarray(np.sign(a) * 2 * tiny) for name, a in o["phi"].items()}
+    full = O.transportmatrix(two, oc.mlotst, o["v3D"], gm["thkcello"], o["area"], oc.lev, gm["edge"], gm["dnbr"], o["topo"],
+                             1035.0, upwind=upwind)
+    assert want["Tadv"].nzval.size > 0
+    assert (want["Tadv"].nzval.size == full["Tadv"].nzval.size) == bool(upwind)
