@@ -67,6 +67,20 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def _freeze(*arrays):
+    """Mark arrays this module hands out as read-only.  Device residency is keyed on object identity, so an array
+    whose content is resident must not change behind the library's back: an in-place update of a result of
+    makegridmetrics / facefluxes raises in numpy instead of silently assembling from the stale device copy.
+    Arrays the CALLER owns (writeable) are never trusted to be unchanged: they are uploaded on every call, like
+    the reference, which reads its arguments at call time."""
+    for a in arrays:
+        a.flags.writeable = False
+
+
+def _same_frozen(a, b):
+    return a is b and isinstance(a, np.ndarray) and not a.flags.writeable
+
+
 class Context:
     """One otmb_ctx (one GPU).  Holds the device-resident grid, indices, metrics and ϕ."""
 
@@ -232,7 +246,7 @@ class _Lazy:
 def _ensure_indices(ctx, v3D, topo_kind):
     """Make v3D / mask / ranks resident (otmb_set_grid + otmb_makeindices) unless they already are."""
     key = ("v3D", id(v3D), topo_kind)
-    if ctx.resident.get("v3D_key") == key and ctx.resident.get("v3D") is v3D:
+    if ctx.resident.get("v3D_key") == key and _same_frozen(ctx.resident.get("v3D"), v3D):
         return ctx.resident["N"]
     nx, ny, nz = v3D.shape
     ctx.check(ctx.lib.otmb_set_grid(ctx.h, nx, ny, nz, _L.TOPO[topo_kind]))
@@ -249,7 +263,7 @@ def makegridmetrics(*, areacello, volcello, lon, lat, lev, lon_vertices, lat_ver
     fills = [x.properties["_FillValue"] for x in (areacello, volcello) if "_FillValue" in _props(x)]
     v3D = _clean_missing(volcello, fills)
     area2D = _clean_missing(areacello, fills)
-    zt = np.ascontiguousarray(_data(lev), dtype=np.float64)
+    zt = np.array(_data(lev), dtype=np.float64, order="C", copy=True)      # own copy: it is frozen below
     lat_a, lon_a = _f64(_data(lat)), _f64(_data(lon))
     lonv, latv = _f64(_data(lon_vertices)), _f64(_data(lat_vertices))
     perm = vertexpermutation(lonv, latv)
@@ -263,9 +277,9 @@ def makegridmetrics(*, areacello, volcello, lon, lat, lev, lon_vertices, lat_ver
     dnbr = np.empty((nx, ny, 4), order="F")
     ctx.check(ctx.lib.otmb_gridmetrics(ctx.h, _ptr(area2D), _ptr(lon_a), _ptr(lat_a), _ptr(lonv), _ptr(latv), _ptr(zt),
                                        _ptr(thk), _ptr(Z3D), _ptr(edge), _ptr(dedge), _ptr(dnbr)))
+    _freeze(v3D, area2D, thk, Z3D, zt, edge, dedge, dnbr)      # resident: see _freeze
     as_dict = lambda a: {d: a[:, :, q] for q, d in enumerate(DIRS)}
     gm = GridMetrics(area2D, v3D, thk, lonv, latv, lon_a, lat_a, Z3D, zt, as_dict(edge), as_dict(dedge), as_dict(dnbr), topo)
-    ctx.resident["metrics"] = (area2D, thk, zt, edge, dnbr)
     ctx.resident["metrics_src"] = (gm.area2D, gm.thkcello, gm.zt, gm.edge_length_2D, gm.distance_to_neighbour_2D)
     _owner[id(v3D)] = ctx
     return gm
@@ -275,7 +289,7 @@ def makeindices(v3D, ctx=None, topology="bipolar") -> Indices:
     """makeindices(v3D), src/matrixbuilding.jl:10-24.  Lwet3D uses 0 for `missing`."""
     v3D = v3D if (isinstance(v3D, np.ndarray) and v3D.flags.f_contiguous and v3D.dtype == np.float64) else _f64(v3D)
     ctx = _ctx_of(v3D, ctx=ctx)
-    kind = ctx.resident["v3D_key"][2] if ctx.resident.get("v3D") is v3D else topology
+    kind = ctx.resident["v3D_key"][2] if _same_frozen(ctx.resident.get("v3D"), v3D) else topology
     N = _ensure_indices(ctx, v3D, kind)
     M = v3D.size
     chunks = np.zeros((M + 63) // 64, np.uint64)
@@ -308,10 +322,14 @@ def facefluxes(umo, vmo, gridmetrics, indices, *, FillValue, ctx=None) -> FaceFl
     shape = gridmetrics.v3D.shape
     out = [ctx.pinned_empty(gridmetrics.v3D.size, np.float64, shape, "F") for _ in range(6)]
     ctx.check(ctx.lib.otmb_facefluxes(ctx.h, _ptr(umo), _ptr(vmo), float(FillValue), *[_ptr(o) for o in out]))
+    _freeze(*out)                                   # resident as ϕ: see _freeze
     phi = FaceFluxes(*out)
-    ctx.resident["phi"] = phi
     ctx.resident["phi_arrays"] = tuple(out)
     return phi
+
+
+def _metric_dicts_same(a, b):
+    return a is b and all(isinstance(v, np.ndarray) and not v.flags.writeable for v in b.values())
 
 
 def _csc(n, colptr, rowval, nzval):
@@ -330,8 +348,10 @@ def transportmatrix(*, ϕ, mlotst, gridmetrics, indices, ρ, κH=500.0, κVML=0.
     N = ctx.resident["N"]
     # grid metrics: resident if these are the very objects makegridmetrics returned on this ctx
     src = ctx.resident.get("metrics_src")
-    same = src is not None and src[0] is gridmetrics.area2D and src[1] is gridmetrics.thkcello and src[2] is gridmetrics.zt \
-        and src[3] is gridmetrics.edge_length_2D and src[4] is gridmetrics.distance_to_neighbour_2D
+    # (the dicts hold read-only views of frozen arrays; a caller who rebinds an entry gets a new dict value -> upload)
+    same = src is not None and _same_frozen(src[0], gridmetrics.area2D) and _same_frozen(src[1], gridmetrics.thkcello) \
+        and _same_frozen(src[2], gridmetrics.zt) and _metric_dicts_same(src[3], gridmetrics.edge_length_2D) \
+        and _metric_dicts_same(src[4], gridmetrics.distance_to_neighbour_2D)
     if not same:
         stack = lambda d: np.asfortranarray(np.stack([_f64(d[k]) for k in DIRS], axis=-1))
         edge, dnbr = stack(gridmetrics.edge_length_2D), stack(gridmetrics.distance_to_neighbour_2D)
@@ -339,19 +359,18 @@ def transportmatrix(*, ϕ, mlotst, gridmetrics, indices, ρ, κH=500.0, κVML=0.
         ctx.check(lib.otmb_set_gridmetrics(ctx.h, _ptr(_f64(gridmetrics.area2D)), _ptr(_f64(gridmetrics.thkcello)), _ptr(zt),
                                            _ptr(edge), _ptr(dnbr), _ptr(_f64(gridmetrics.Z3D)), _ptr(_f64(gridmetrics.lon)),
                                            _ptr(_f64(gridmetrics.lat))))
-        ctx.resident["metrics_src"] = (gridmetrics.area2D, gridmetrics.thkcello, gridmetrics.zt,
-                                       gridmetrics.edge_length_2D, gridmetrics.distance_to_neighbour_2D)
+        ctx.resident["metrics_src"] = None          # caller-owned arrays: never assumed unchanged
     preset = {1: Tadv, 2: TκH, 3: TκVML, 4: TκVdeep}
     mask = 32 | sum(1 << m for m, v in preset.items() if v is None)   # bit 5: the mask is explicit
     if mask & 2:
         get = (lambda k: ϕ[k]) if isinstance(ϕ, dict) else (lambda k: getattr(ϕ, k))
         arrs = tuple(get(k) for k in FACES)
         res = ctx.resident.get("phi_arrays")
-        if not (res is not None and all(a is b for a, b in zip(arrs, res))):
+        if not (res is not None and all(_same_frozen(a, b) for a, b in zip(arrs, res))):
             arrs = tuple(_f64(a) for a in arrs)
             ptrs = (C.c_void_p * 6)(*[a.ctypes.data for a in arrs])
             ctx.check(lib.otmb_set_facefluxes(ctx.h, ptrs))
-            ctx.resident["phi_arrays"] = arrs
+            ctx.resident["phi_arrays"] = None
         if np.isscalar(ρ):
             ctx.check(lib.otmb_set_rho3d(ctx.h, None))
         else:
@@ -531,15 +550,14 @@ def resident_matvec(name, x, *, transpose=False, ctx=None):
 # ---- Redi/GM helpers (experimental and non-exported in the reference) -------------------------
 def _ensure_z(ctx, gridmetrics):
     _ensure_grid(ctx, gridmetrics)
-    if ctx.resident.get("metrics_src") is None or ctx.resident["metrics_src"][1] is not gridmetrics.thkcello:
+    if ctx.resident.get("metrics_src") is None or not _same_frozen(ctx.resident["metrics_src"][1], gridmetrics.thkcello):
         stack = lambda d: np.asfortranarray(np.stack([_f64(d[k]) for k in DIRS], axis=-1))
         zt = np.ascontiguousarray(gridmetrics.zt, dtype=np.float64)
         ctx.check(ctx.lib.otmb_set_gridmetrics(
             ctx.h, _ptr(_f64(gridmetrics.area2D)), _ptr(_f64(gridmetrics.thkcello)), _ptr(zt),
             _ptr(stack(gridmetrics.edge_length_2D)), _ptr(stack(gridmetrics.distance_to_neighbour_2D)),
             _ptr(_f64(gridmetrics.Z3D)), _ptr(_f64(gridmetrics.lon)), _ptr(_f64(gridmetrics.lat))))
-        ctx.resident["metrics_src"] = (gridmetrics.area2D, gridmetrics.thkcello, gridmetrics.zt,
-                                       gridmetrics.edge_length_2D, gridmetrics.distance_to_neighbour_2D)
+        ctx.resident["metrics_src"] = None
 
 
 def globalverticalfacetriadderivative(χ, gridmetrics, indices, dir, ctx=None):

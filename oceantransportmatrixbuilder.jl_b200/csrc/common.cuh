@@ -45,8 +45,10 @@ struct DevFlags {
     int nan_adv, nan_kh, nan_kvml, nan_kvdeep, nan_rho;
     int any_valid_u, any_valid_v;
     int generic_columns;   // columns that took the coincidence (generic) branch
-    int zero_dropped;      // fused v2: an exactly-zero T entry was stored and must be compacted away
-    int pad[6];
+    int zero_dropped;      // an exactly-zero T entry was stored and must be compacted away
+    unsigned tiles_done;   // k_fused_v4: tiles that have finished (the last one publishes the host record)
+    int lookback_timeout;  // k_fused_v4: a look-back spun past its bound (diagnostic instead of a hang)
+    int pad[4];
     u64 nnz[5];
     u64 ticket;            // dynamic tile id for the look-back kernel
     u64 pad2[2];
@@ -85,6 +87,18 @@ struct otmb_ctx {
     // scratch
     DevBuf flags;        // DevFlags
     DevFlags* h_flags = nullptr;  // pinned
+    // completion record of k_fused_v4 in mapped pinned memory: the last tile stores the flags + nnz there and
+    // then the launch's serial number, the host polls it (no memcpy, no stream synchronise per build)
+    struct HostDone {
+        volatile u64 seq;
+        u64 pad[7];
+        DevFlags snap;
+    };
+    HostDone* h_done = nullptr;
+    HostDone* d_done = nullptr;   // device alias of h_done
+    bool flags_clean = false;     // the device flag block is known to be all zero (k_fused_v4 re-zeroes it itself)
+    u64 v4_serial = 0;            // launches of k_fused_v4 on this context (epoch of the look-back descriptors)
+    size_t ts_zeroed = 0;         // bytes of tile_state known to hold no descriptor of a conflicting epoch
     DevBuf tile_state;   // look-back descriptors / block totals
     DevBuf scan_tmp;     // block sums for the generic scan
     DevBuf coo[12];      // COO path scratch
@@ -107,6 +121,7 @@ struct otmb_ctx {
 
     i64 launches = 0;
     float last_build_ms = 0.f;
+    bool build_ms_valid = false;  // ev_b0 / ev_b1 bracket a finished build whose duration has not been read yet
 };
 
 inline int otmb_fail(otmb_ctx* c, int code, const std::string& msg) {
@@ -174,7 +189,6 @@ int otmb_scan_u32_to_i64(otmb_ctx* ctx, const uint32_t* in, i64* out, i64 n, u64
 int otmb_need(otmb_ctx* ctx, bool cond, const char* what);
 int otmb_upload3d(otmb_ctx* ctx, DevBuf& buf, const double* host);   // whole (nx,ny,nz) array, or only the slab window
 int otmb_fused_build(otmb_ctx* ctx, const otmb_tm_params* prm, int mask, bool two_pass);
-int otmb_fused_v2_build(otmb_ctx* ctx, const otmb_tm_params* prm, int mask);
 int otmb_fused_v4_build(otmb_ctx* ctx, const otmb_tm_params* prm, int mask);
 int otmb_drop_zeros(otmb_ctx* ctx, int m, int base);
 int otmb_coo_build(otmb_ctx* ctx, const otmb_tm_params* prm, int mask);

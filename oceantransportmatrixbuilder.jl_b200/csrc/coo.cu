@@ -510,3 +510,69 @@ int otmb_coo_build(otmb_ctx* c, const otmb_tm_params* prm, int build) {
     }
     return OTMB_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// Zero-dropping compaction of one result matrix.  Sparse `+` does not store results equal to zero
+// (/root/reference/src/matrixbuilding.jl:147); the fused kernels store T's union pattern and flag an exact zero
+// when one occurs (e.g. κ = 0), and only then this pass rewrites the matrix: per-column count of the surviving
+// entries, exclusive scan -> new colptr, ordered copy.
+// ---------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) k_count_nonzero(const i64* __restrict__ colptr, const double* __restrict__ nzv, i64 n,
+                                                       int base, uint32_t* __restrict__ cnt) {
+    const i64 col = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col > n) return;
+    uint32_t kept = 0;
+    if (col < n) {
+        const i64 e1 = colptr[col + 1] - base;
+        for (i64 e = colptr[col] - base; e < e1; ++e) kept += nzv[e] != 0.0 ? 1u : 0u;
+    }
+    cnt[col] = kept;   // entry n: 0, so that the scan's last output is the total
+}
+__global__ void __launch_bounds__(256) k_copy_nonzero(const i64* __restrict__ colptr, const i64* __restrict__ rowval,
+                                                      const double* __restrict__ nzv, i64 n, int base,
+                                                      const i64* __restrict__ new_start, i64* __restrict__ out_colptr,
+                                                      i64* __restrict__ out_rowval, double* __restrict__ out_nzv) {
+    const i64 col = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col > n) return;
+    i64 dst = new_start[col];
+    out_colptr[col] = dst + base;
+    if (col == n) return;
+    const i64 e1 = colptr[col + 1] - base;
+    for (i64 e = colptr[col] - base; e < e1; ++e) {
+        const double v = nzv[e];
+        if (v != 0.0) {
+            out_rowval[dst] = rowval[e];
+            out_nzv[dst] = v;
+            ++dst;
+        }
+    }
+}
+}  // namespace
+
+int otmb_drop_zeros(otmb_ctx* c, int m, int base) {
+    const i64 n = c->ncols;
+    DevBuf &cnt = c->coo[3], &start = c->coo[11];
+    CU_TRY(c, cnt.ensure((size_t)(n + 1) * 4));
+    CU_TRY(c, start.ensure((size_t)(n + 1) * 8));
+    c->flags_clean = false;   // the scan below leaves the new nnz in the flag block
+    k_count_nonzero<<<grid_for(n + 1, 256), 256, 0, c->stream>>>(c->colptr[m].as<i64>(), c->nzval[m].as<double>(), n, base,
+                                                                  cnt.as<uint32_t>());
+    LAUNCHED(c);
+    OT_TRY(otmb_scan_u32_to_i64(c, cnt.as<uint32_t>(), start.as<i64>(), n + 1, &c->flags.as<DevFlags>()->nnz[m]));
+    CU_TRY(c, c->add_tmp[0].ensure(c->colptr[m].cap));
+    CU_TRY(c, c->add_tmp[1].ensure(c->rowval[m].cap));
+    CU_TRY(c, c->add_tmp[2].ensure(c->nzval[m].cap));
+    k_copy_nonzero<<<grid_for(n + 1, 256), 256, 0, c->stream>>>(c->colptr[m].as<i64>(), c->rowval[m].as<i64>(),
+                                                                 c->nzval[m].as<double>(), n, base, start.as<i64>(),
+                                                                 c->add_tmp[0].as<i64>(), c->add_tmp[1].as<i64>(),
+                                                                 c->add_tmp[2].as<double>());
+    LAUNCHED(c);
+    CU_TRY(c, cudaGetLastError());
+    OT_TRY(otmb_fetch_flags(c));
+    std::swap(c->colptr[m], c->add_tmp[0]);
+    std::swap(c->rowval[m], c->add_tmp[1]);
+    std::swap(c->nzval[m], c->add_tmp[2]);
+    c->nnz[m] = (i64)c->h_flags->nnz[m];
+    return OTMB_OK;
+}

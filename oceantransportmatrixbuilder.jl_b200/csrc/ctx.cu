@@ -104,6 +104,7 @@ int otmb_need(otmb_ctx* ctx, bool cond, const char* what) {
 }
 
 int otmb_reset_flags(otmb_ctx* ctx) {
+    ctx->flags_clean = false;   // whoever asked for the reset is about to write them
     CU_TRY(ctx, cudaMemsetAsync(ctx->flags.p, 0, sizeof(DevFlags), ctx->stream));
     return OTMB_OK;
 }
@@ -167,12 +168,16 @@ int otmb_create(otmb_ctx** out, int device) {
         cudaEventCreate(&c->ev_t0) != cudaSuccess || cudaEventCreate(&c->ev_t1) != cudaSuccess ||
         cudaEventCreate(&c->ev_b0) != cudaSuccess || cudaEventCreate(&c->ev_b1) != cudaSuccess ||
         c->flags.ensure(sizeof(DevFlags)) != cudaSuccess ||
-        cudaMallocHost((void**)&c->h_flags, sizeof(DevFlags)) != cudaSuccess) {
+        cudaMallocHost((void**)&c->h_flags, sizeof(DevFlags)) != cudaSuccess ||
+        cudaHostAlloc((void**)&c->h_done, sizeof(otmb_ctx::HostDone), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&c->d_done, c->h_done, 0) != cudaSuccess) {
         cudaGetLastError();
         delete c;
         return OTMB_ERR_CUDA;
     }
     cudaMemset(c->flags.p, 0, sizeof(DevFlags));
+    memset(c->h_done, 0, sizeof(otmb_ctx::HostDone));
+    c->flags_clean = true;
     *out = c;
     return OTMB_OK;
 }
@@ -201,6 +206,7 @@ int otmb_destroy(otmb_ctx* c) {
     }
     if (c->fetch_state && c->fetch_state_free) c->fetch_state_free(c->fetch_state);
     if (c->h_flags) cudaFreeHost(c->h_flags);
+    if (c->h_done) cudaFreeHost(c->h_done);
     cudaEventDestroy(c->ev_t0);
     cudaEventDestroy(c->ev_t1);
     cudaEventDestroy(c->ev_b0);
@@ -451,6 +457,12 @@ int otmb_launch_count(otmb_ctx* c, int64_t* launches) {
 }
 int otmb_last_build_ms(otmb_ctx* c, float* ms) {
     if (!c || !ms) return OTMB_ERR_BADARG;
+    if (c->build_ms_valid) {
+        CU_TRY(c, cudaSetDevice(c->device));
+        CU_TRY(c, cudaEventSynchronize(c->ev_b1));
+        CU_TRY(c, cudaEventElapsedTime(&c->last_build_ms, c->ev_b0, c->ev_b1));
+        c->build_ms_valid = false;
+    }
     *ms = c->last_build_ms;
     return OTMB_OK;
 }

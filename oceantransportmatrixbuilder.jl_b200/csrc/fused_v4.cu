@@ -37,6 +37,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
+#include <atomic>
 #include <type_traits>
 
 #include "fused_generic.cuh"
@@ -45,7 +46,13 @@ using namespace fusedg;
 
 namespace {
 
-constexpr u64 ST_AGG = 1ull << 62, ST_PRE = 2ull << 62, ST_MASK = (1ull << 62) - 1;
+// look-back descriptor: [flag:2][epoch:20][count:42].  flag 1 = the tile's own aggregate, 2 = inclusive prefix; the
+// epoch is the launch's serial number, so descriptors left behind by earlier launches read as "not published yet"
+// and the array needs no memset per launch (it is zeroed when it is allocated and when the epoch wraps).
+constexpr int ST_SHIFT = 42;
+constexpr u64 ST_MASK = (1ull << ST_SHIFT) - 1;
+constexpr unsigned ST_EPOCHS = 1u << 20;
+__host__ __device__ constexpr u64 st_tag(unsigned flag, unsigned epoch) { return ((u64)((flag << 20) | epoch)) << ST_SHIFT; }
 constexpr int WDATA = 7 * 32;       // staged entries per warp: 7 per column
 constexpr int WCAP = WDATA + 32;    // + one dump slot per lane for absent entries (branch-free staging)
 // candidates in ascending row order, one nibble each, per class
@@ -81,6 +88,9 @@ struct V4Params {
     double* nzval[5];
     DevFlags* flags;
     u64* tile_state;
+    unsigned epoch;                  // look-back epoch of this launch (serial mod 2^20)
+    u64 serial;                      // stored to host_done->seq by the last tile
+    otmb_ctx::HostDone* host_done;   // mapped pinned memory
     long long* timeline;   // TLINE instantiation only (OTMB_V4_TIMELINE): 64 stamps per tile, see profiles/timeline.py
 };
 
@@ -120,6 +130,7 @@ struct Smem {
     u64 lexcl[TILE];               // in-warp exclusive offsets of the column, five 12-bit fields
     u64 warp[TILE / 32];           // entries of each warp, five 12-bit fields
     u64 excl[5];
+    int done;                      // warps of this block that have finished
 };
 
 // ---------------------------------------------------------------------------------------
@@ -127,6 +138,7 @@ template <bool RHO3D, bool UP, int TILE, int MINB, int KHB = 2, bool VAH = true,
 // __grid_constant__: P is indexed dynamically and its address is taken by the generic branch
 __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_constant__ V4Params P) {
     constexpr int NW = TILE / 32;   // column warps; warp NW is the scan warp
+    static_assert(TILE * 7 < 4096, "per-warp / per-tile entry counts are kept in 12-bit fields");
     constexpr int BG = (NW + 13) / 14;          // column warps per release barrier (ids 2 .. 15)
     constexpr int NBG = (NW + BG - 1) / BG;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -134,6 +146,29 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int tile = blockIdx.x;
+    if (tid == 0) S.done = 0;   // ordered before every use by barrier 1 (this warp arrives after it)
+    // ---- completion.  Every warp ends here; the last warp of the last tile to finish copies the flag block and the
+    // five nnz into the host-mapped record, re-zeroes the device block for the next launch and stores the launch's
+    // serial number: the host polls that word instead of issuing a copy and a stream synchronise per build.
+    auto finish = [&]() {
+        __syncwarp();
+        if (lane != 0) return;
+        __threadfence();
+        if (atomicAdd(&S.done, 1) != NW) return;
+        __threadfence();
+        if (atomicAdd(&P.flags->tiles_done, 1u) != (unsigned)(P.ntiles - 1)) return;
+        __threadfence();
+        volatile int* src = reinterpret_cast<volatile int*>(P.flags);
+        volatile int* dst = reinterpret_cast<volatile int*>(&P.host_done->snap);
+        constexpr int NI = (int)(sizeof(DevFlags) / sizeof(int));
+#pragma unroll 1
+        for (int q = 0; q < NI; ++q) {
+            dst[q] = src[q];
+            src[q] = 0;
+        }
+        __threadfence_system();
+        *reinterpret_cast<volatile u64*>(&P.host_done->seq) = P.serial;
+    };
     // timeline instrumentation (debug instantiation): SM clock stamps of one tile's phases
     long long* const tl = TLINE ? P.timeline + (size_t)tile * 64 : nullptr;
     // (a clock read right behind BAR.SYNC.DEFER_BLOCKING issues before the barrier resolves: stamps behind a barrier
@@ -173,7 +208,8 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
             const unsigned tot = __reduce_add_sync(0xffffffffu, (unsigned)((pk >> (12 * m)) & 0xfffull));
             if (lane == m) agg_m = tot;
         }
-        if (lane < 5) st_vol(P.tile_state + (size_t)tile * 8 + lane, (tile == 0 ? ST_PRE : ST_AGG) | (u64)agg_m);
+        const unsigned tagA = (1u << 20) | P.epoch, tagP = (2u << 20) | P.epoch;   // the descriptor's top 22 bits
+        if (lane < 5) st_vol(P.tile_state + (size_t)tile * 8 + lane, ((u64)(tile == 0 ? tagP : tagA) << ST_SHIFT) | (u64)agg_m);
         stamp(3);
         int rounds = 0;
         u64 excl[5] = {0, 0, 0, 0, 0};
@@ -188,21 +224,37 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
 #pragma unroll
             for (int s = 0; s < LB_SUB; ++s)
 #pragma unroll
-                for (int m = 0; m < 5; ++m) wv[s][m] = (look - 32 * s - lane) >= 0 ? 0ull : ST_PRE;   // before the first tile: prefix 0
+                for (int m = 0; m < 5; ++m) wv[s][m] = (look - 32 * s - lane) >= 0 ? 0ull : ((u64)tagP << ST_SHIFT);   // before the first tile: prefix 0
             bool again;
+            unsigned spins = 0;
+            // published by THIS launch: the epoch matches and the flag is set
+            auto ready = [&](const u64 v) {
+                const unsigned hi = (unsigned)(v >> ST_SHIFT);
+                return hi == tagA || hi == tagP;
+            };
             do {   // the five descriptors of a tile share a 64-byte line
 #pragma unroll
                 for (int s = 0; s < LB_SUB; ++s)
 #pragma unroll
                     for (int m = 0; m < 5; ++m)
-                        if ((pending >> m & 1) && (wv[s][m] >> 62) == 0)
+                        if ((pending >> m & 1) && !ready(wv[s][m]))
                             wv[s][m] = ld_vol(P.tile_state + (size_t)(look - 32 * s - lane) * 8 + m);
                 again = false;
 #pragma unroll
                 for (int s = 0; s < LB_SUB; ++s)
 #pragma unroll
-                    for (int m = 0; m < 5; ++m) again |= (pending >> m & 1) && (wv[s][m] >> 62) == 0;
+                    for (int m = 0; m < 5; ++m) again |= (pending >> m & 1) && !ready(wv[s][m]);
+                // Lower tiles are resident or finished (blocks start in index order), so this terminates; the bound
+                // (seconds) turns a broken assumption into an error code instead of a hang.
+                if (++spins > (1u << 24)) break;
             } while (__any_sync(0xffffffffu, again));
+            if (__any_sync(0xffffffffu, spins > (1u << 24))) {
+                // give up: report it, and zero the warps' entry counts so that no column warp flushes anything
+                // (the offsets are meaningless); the host turns the flag into an error code
+                if (lane == 0) atomicOr(&P.flags->lookback_timeout, 1);
+                if (lane < NW) S.warp[lane] = 0ull;
+                break;
+            }
 #pragma unroll
             for (int s = 0; s < LB_SUB; ++s) {   // nearest window first; a counter stops at its first inclusive prefix
 #pragma unroll
@@ -210,7 +262,7 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
                     if (!(pending >> m & 1)) continue;
                     // a tile's aggregate fits 13 bits, 32 of them one redux.sync; only an inclusive prefix needs 62 bits
                     const u64 val = wv[s][m] & ST_MASK;
-                    const unsigned pm = __ballot_sync(0xffffffffu, (wv[s][m] >> 62) == 2);
+                    const unsigned pm = __ballot_sync(0xffffffffu, (unsigned)(wv[s][m] >> ST_SHIFT) == tagP);
                     if (pm) {
                         const int first = __ffs(pm) - 1;
                         excl[m] += (u64)__reduce_add_sync(0xffffffffu, lane < first ? (unsigned)val : 0u) + __shfl_sync(0xffffffffu, val, first);
@@ -228,7 +280,7 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
         const u64 mine = lane == 0 ? excl[0] : lane == 1 ? excl[1] : lane == 2 ? excl[2] : lane == 3 ? excl[3] : excl[4];
         if (lane < 5) {
             const u64 agg = agg_m;
-            if (tile > 0) st_vol(P.tile_state + (size_t)tile * 8 + lane, ST_PRE | (mine + agg));
+            if (tile > 0) st_vol(P.tile_state + (size_t)tile * 8 + lane, ((u64)tagP << ST_SHIFT) | (mine + agg));
             S.excl[lane] = mine;
             if (tile == P.ntiles - 1) {
                 P.flags->nnz[lane] = mine + agg;
@@ -244,6 +296,7 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
             const int members = (gq + 1) * BG <= NW ? BG : NW - gq * BG;
             asm volatile("bar.arrive %0, %1;" ::"r"(2 + gq), "r"(32 * members + 32) : "memory");
         }
+        finish();
         return;
     }
     const GridDims g = P.g;
@@ -759,6 +812,7 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
             }
         }
     }
+    finish();
 }
 
 FastDiv make_fastdiv(unsigned d) {
@@ -774,9 +828,21 @@ template <bool RHO3D, bool UP, int TILE, int MINB, int KHB = 2, bool VAH = true,
 int launch_v4(otmb_ctx* c, V4Params& P) {
     const int ntiles = (int)(((i64)P.ncols + TILE - 1) / TILE);
     P.ntiles = ntiles;
-    CU_TRY(c, c->tile_state.ensure((size_t)ntiles * 8 * sizeof(u64)));
+    // look-back descriptors: zeroed when the array grows and when the 20-bit epoch wraps, otherwise left as they are
+    // (a descriptor of an earlier launch carries another epoch and reads as "not published")
+    const size_t ts_bytes = (size_t)ntiles * 8 * sizeof(u64);
+    c->v4_serial++;
+    P.epoch = (unsigned)(c->v4_serial % ST_EPOCHS);
+    P.serial = c->v4_serial;
+    if (ts_bytes > c->tile_state.cap || !c->tile_state.p) c->ts_zeroed = 0;
+    CU_TRY(c, c->tile_state.ensure(ts_bytes));
+    if (P.epoch == 0) c->ts_zeroed = 0;
+    if (c->ts_zeroed < ts_bytes) {
+        CU_TRY(c, cudaMemsetAsync(c->tile_state.p, 0, c->tile_state.cap, c->stream));
+        c->ts_zeroed = c->tile_state.cap;
+    }
     P.tile_state = c->tile_state.as<u64>();
-    CU_TRY(c, cudaMemsetAsync(P.tile_state, 0, (size_t)ntiles * 8 * sizeof(u64), c->stream));
+    P.host_done = c->d_done;
     DevBuf tline;
     if (TLINE) {
         CU_TRY(c, tline.ensure((size_t)ntiles * 64 * 8));
@@ -784,11 +850,14 @@ int launch_v4(otmb_ctx* c, V4Params& P) {
     }
     P.timeline = tline.as<long long>();
     const size_t smem = sizeof(Smem<TILE>);
-    CU_TRY(c, cudaFuncSetAttribute(k_fused_v4<RHO3D, UP, TILE, MINB, KHB, VAH, VC0, TLINE, XSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // Shared memory is paid for in L1 on this kernel (3 - 4 % per 32 KB, profiles/README.md): ask for the smallest
-    // carve-out that still holds MINB blocks (sm_100: 0/8/16/32/64/100/132/164/196/228 KB; the driver rounds a
-    // percentage UP to the next of these, so the request is rounded down).  OTMB_V4_CARVEOUT=<percent> overrides.
-    {
+    auto kern = k_fused_v4<RHO3D, UP, TILE, MINB, KHB, VAH, VC0, TLINE, XSM>;
+    // function attributes once per instantiation and device
+    static std::atomic<unsigned long long> configured{0};
+    if (!(configured.load(std::memory_order_acquire) >> (c->device & 63) & 1ull)) {
+        CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // Shared memory is paid for in L1 on this kernel (3 - 4 % per 32 KB, profiles/README.md): ask for the smallest
+        // carve-out that still holds MINB blocks (sm_100: 0/8/16/32/64/100/132/164/196/228 KB; the driver rounds a
+        // percentage UP to the next of these, so the request is rounded down).
         static const int kb[] = {0, 8, 16, 32, 64, 100, 132, 164, 196, 228};
         const size_t need = (size_t)MINB * (smem + 1024);
         int pct = 100;
@@ -797,12 +866,16 @@ int launch_v4(otmb_ctx* c, V4Params& P) {
                 pct = kb[q] * 100 / 228;
                 break;
             }
+#ifdef OTMB_AB
         if (const char* e = getenv("OTMB_V4_CARVEOUT")) pct = atoi(e);
-        CU_TRY(c, cudaFuncSetAttribute(k_fused_v4<RHO3D, UP, TILE, MINB, KHB, VAH, VC0, TLINE, XSM>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+#endif
+        CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        configured.fetch_or(1ull << (c->device & 63), std::memory_order_release);
     }
-    k_fused_v4<RHO3D, UP, TILE, MINB, KHB, VAH, VC0, TLINE, XSM><<<ntiles, TILE + 32, smem, c->stream>>>(P);
+    kern<<<ntiles, TILE + 32, smem, c->stream>>>(P);
     LAUNCHED(c);
     CU_TRY(c, cudaGetLastError());
+#ifdef OTMB_AB
     if (TLINE) {   // raw dump: ntiles x 64 int64 (profiles/timeline.py)
         std::vector<long long> h((size_t)ntiles * 64);
         CU_TRY(c, cudaMemcpyAsync(h.data(), tline.p, h.size() * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -813,6 +886,7 @@ int launch_v4(otmb_ctx* c, V4Params& P) {
         }
         tline.release();
     }
+#endif
     return OTMB_OK;
 }
 
@@ -854,7 +928,10 @@ int otmb_fused_v4_build(otmb_ctx* c, const otmb_tm_params* prm, int build) {
     P.upwind = prm->upwind;
     P.base = prm->index_base;
     P.build = build;
-    P.prefetch = getenv("OTMB_V4_NOPREFETCH") ? 0 : 1;
+    P.prefetch = 1;
+#ifdef OTMB_AB
+    if (getenv("OTMB_V4_NOPREFETCH")) P.prefetch = 0;
+#endif
     P.w0 = (int)c->w0;
     P.ncols = (int)c->ncols;
     P.flags = c->flags.as<DevFlags>();
@@ -872,18 +949,19 @@ int otmb_fused_v4_build(otmb_ctx* c, const otmb_tm_params* prm, int build) {
         P.rowval[m] = c->rowval[m].as<i64>();
         P.nzval[m] = c->nzval[m].as<double>();
     }
-    static const int variant = getenv("OTMB_V4_VARIANT") ? atoi(getenv("OTMB_V4_VARIANT")) : 0;
     // TILE column threads + one scan warp per block
     const bool up = prm->upwind != 0;
     if (c->have_rho3d) return up ? launch_v4<true, true, 352, 2>(c, P) : launch_v4<true, false, 352, 2>(c, P);
     if (!up) return launch_v4<false, false, 352, 2>(c, P);
-    if (getenv("OTMB_V4_TIMELINE")) return launch_v4<false, true, 352, 2, 2, true, true, true>(c, P);   // per-tile phase stamps
-    switch (variant) {   // launch geometries / schedules kept for A/B runs (profiles/bench_variants.sh)
+#ifdef OTMB_AB   // measurement builds only (nvcc -DOTMB_AB): launch geometries / schedules for A/B runs, per-tile phase stamps
+    if (getenv("OTMB_V4_TIMELINE")) return launch_v4<false, true, 352, 2, 2, true, true, true>(c, P);
+    switch (getenv("OTMB_V4_VARIANT") ? atoi(getenv("OTMB_V4_VARIANT")) : 0) {
         case 1: return launch_v4<false, true, 352, 2, 2, true, true, false, false>(c, P);   // Tadv re-loads the neighbours' fluxes
         case 2: return launch_v4<false, true, 416, 2>(c, P);   // 72 registers
         case 3: return launch_v4<false, true, 352, 2, 1>(c, P);   // TκH loads direction by direction
         case 4: return launch_v4<false, true, 352, 2, 2, false, false>(c, P);   // vertical inputs and own volume loaded where they are used
-        case 7: return launch_v4<false, true, 608, 1>(c, P);   // one block per SM
-        default: return launch_v4<false, true, 352, 2>(c, P);   // measured best on C2 (profiles/README.md)
+        default: break;
     }
+#endif
+    return launch_v4<false, true, 352, 2>(c, P);   // measured best on C2 (profiles/README.md)
 }

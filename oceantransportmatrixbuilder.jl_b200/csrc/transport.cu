@@ -1,5 +1,9 @@
 // transport.cu — C-ABI entry points for transportmatrix and the generic sparse helpers.
 // transportmatrix: /root/reference/src/matrixbuilding.jl:128-150.
+#include <immintrin.h>
+
+#include <atomic>
+#include <chrono>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -18,6 +22,34 @@ int check_flags(otmb_ctx* c, int build) {
     if ((build & 4) && f.nan_kh) return otmb_fail(c, OTMB_ERR_TKH_NAN, otmb_status_string(OTMB_ERR_TKH_NAN));
     if ((build & 8) && f.nan_kvml) return otmb_fail(c, OTMB_ERR_TKVML_NAN, otmb_status_string(OTMB_ERR_TKVML_NAN));
     if ((build & 16) && f.nan_kvdeep) return otmb_fail(c, OTMB_ERR_TKVDEEP_NAN, otmb_status_string(OTMB_ERR_TKVDEEP_NAN));
+    return OTMB_OK;
+}
+
+// k_fused_v4 publishes its flag block and the five nnz in mapped pinned memory and then the launch's serial
+// number (fused_v4.cu, `finish`): poll that word.  After a while the stream is queried as well, which is what
+// surfaces a faulted kernel; a kernel that ended without publishing is an error, not a hang.
+int wait_v4(otmb_ctx* c) {
+    const u64 want = c->v4_serial;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (unsigned it = 1;; ++it) {
+        if (c->h_done->seq == want) break;
+        _mm_pause();
+        if ((it & 255u) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(300)) {
+            const cudaError_t e = cudaStreamQuery(c->stream);
+            if (e == cudaSuccess) {
+                if (c->h_done->seq == want) break;
+                return otmb_fail(c, OTMB_ERR_CUDA, "assembly kernel ended without publishing its completion record");
+            }
+            if (e != cudaErrorNotReady) CU_TRY(c, e);
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    memcpy(c->h_flags, (const void*)&c->h_done->snap, sizeof(DevFlags));
+    c->flags_clean = true;   // the kernel re-zeroed the device block
+    if (c->h_flags->lookback_timeout) {
+        c->ts_zeroed = 0;
+        return otmb_fail(c, OTMB_ERR_CUDA, "assembly kernel: a tile's look-back did not resolve (blocks not scheduled in index order?)");
+    }
     return OTMB_OK;
 }
 
@@ -58,9 +90,18 @@ int otmb_transportmatrix_build(otmb_ctx* c, const otmb_tm_params* prm, int64_t n
     }
     c->out_base = prm->index_base;
     c->build_serial++;
-    OT_TRY(otmb_reset_flags(c));
-    CU_TRY(c, cudaEventRecord(c->ev_b0, c->stream));
     const bool all4 = ops == 30;
+    // results about to be rebuilt are invalid until this build has passed its checks: a failed build must not
+    // leave an earlier build's sizes behind for fetch / spmv / lump to pair with the new contents
+    for (int m = 0; m < 5; ++m)
+        if (m == 0 || (ops >> m & 1)) {
+            c->have_mat[m] = false;
+            c->nnz[m] = 0;
+        }
+    const bool v4 = c->ncols != 0 && ops != 0 && prm->path == OTMB_PATH_FUSED;
+    if (!(v4 && c->flags_clean)) OT_TRY(otmb_reset_flags(c));   // k_fused_v4 leaves the flag block zeroed
+    c->build_ms_valid = false;
+    CU_TRY(c, cudaEventRecord(c->ev_b0, c->stream));
     int st = OTMB_OK;
     if (c->ncols == 0) {
         // empty ocean: five empty matrices
@@ -84,15 +125,13 @@ int otmb_transportmatrix_build(otmb_ctx* c, const otmb_tm_params* prm, int64_t n
         OT_TRY(otmb_sum_operators(c, prm->index_base));
     } else {
         const int build = ops | (all4 ? 1 : 0);
-        // OTMB_FUSED_IMPL=v2 selects the earlier unrolled schedule of the same column kernel (A/B measurements)
-        static const char* impl = getenv("OTMB_FUSED_IMPL");
-        const int ver = impl && impl[0] == 'v' ? atoi(impl + 1) : 4;
-        st = prm->path == OTMB_PATH_FUSED2 ? otmb_fused_build(c, prm, build, true)
-             : ver == 2                    ? otmb_fused_v2_build(c, prm, build)
-                                           : otmb_fused_v4_build(c, prm, build);
+        st = v4 ? otmb_fused_v4_build(c, prm, build) : otmb_fused_build(c, prm, build, true);
         if (st != OTMB_OK) return st;
         CU_TRY(c, cudaEventRecord(c->ev_b1, c->stream));
-        OT_TRY(otmb_fetch_flags(c));
+        if (v4)
+            OT_TRY(wait_v4(c));
+        else
+            OT_TRY(otmb_fetch_flags(c));
         OT_TRY(check_flags(c, ops));
         for (int m = 0; m < 5; ++m)
             if (build >> m & 1) {
@@ -109,9 +148,10 @@ int otmb_transportmatrix_build(otmb_ctx* c, const otmb_tm_params* prm, int64_t n
             OT_TRY(otmb_sum_operators(c, prm->index_base));
         }
     }
-    if (!(c->ncols != 0 && prm->path != OTMB_PATH_COO && all4)) CU_TRY(c, cudaEventRecord(c->ev_b1, c->stream));
-    CU_TRY(c, cudaStreamSynchronize(c->stream));
-    CU_TRY(c, cudaEventElapsedTime(&c->last_build_ms, c->ev_b0, c->ev_b1));
+    const bool fast = v4 && all4 && !c->h_flags->zero_dropped;   // one kernel, completion already observed
+    if (!(c->ncols != 0 && ops != 0 && prm->path != OTMB_PATH_COO && all4)) CU_TRY(c, cudaEventRecord(c->ev_b1, c->stream));
+    if (!fast) CU_TRY(c, cudaStreamSynchronize(c->stream));
+    c->build_ms_valid = true;   // elapsed time is read on demand (otmb_last_build_ms): no event wait per build
     if (nnz_out)
         for (int m = 0; m < 5; ++m) nnz_out[m] = c->nnz[m];
     return OTMB_OK;
@@ -123,6 +163,26 @@ int otmb_set_operator(otmb_ctx* c, int which, int64_t nnz, const int64_t* colptr
                       const double* nzval, int32_t index_base) {
     if (!c || which < 1 || which > 4 || nnz < 0 || !colptr || (nnz > 0 && (!rowval || !nzval))) return OTMB_ERR_BADARG;
     OT_TRY(otmb_need(c, c->have_indices, "otmb_makeindices"));
+    if (index_base != 0 && index_base != 1) return otmb_fail(c, OTMB_ERR_BADARG, "index_base must be 0 or 1");
+    if (c->sharded) return otmb_fail(c, OTMB_ERR_STATE, "pre-built operators are not available on a slab context");
+    // A wrong-shaped operator is a DimensionMismatch in the reference's sum (src/matrixbuilding.jl:147); here the
+    // caller's CSC must be N x N with colptr of N+1 monotone entries ending at nnz and rows ascending inside [0, N)
+    {
+        const i64 n = c->ncols;
+        bool ok = colptr[0] == index_base && colptr[n] - index_base == nnz;
+        for (i64 j = 0; ok && j < n; ++j) ok = colptr[j] <= colptr[j + 1];
+        if (!ok)
+            return otmb_fail(c, OTMB_ERR_BADARG, "DimensionMismatch: pre-built operator is not an N x N CSC matrix (colptr must hold "
+                                                 "N+1 non-decreasing entries from index_base to index_base + nnz)");
+        for (i64 j = 0; ok && j < n; ++j)
+            for (i64 e = colptr[j] - index_base; ok && e < colptr[j + 1] - index_base; ++e) {
+                const i64 r = rowval[e] - index_base;
+                ok = r >= 0 && r < n && (e == colptr[j] - index_base || rowval[e - 1] < rowval[e]);
+            }
+        if (!ok)
+            return otmb_fail(c, OTMB_ERR_BADARG, "pre-built operator: row indices must be strictly ascending inside every column and "
+                                                 "lie inside the matrix");
+    }
     CU_TRY(c, cudaSetDevice(c->device));
     CU_TRY(c, c->colptr[which].ensure((size_t)(c->ncols + 1) * 8));
     CU_TRY(c, c->rowval[which].ensure((size_t)(nnz + 1) * 8));

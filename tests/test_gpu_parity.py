@@ -425,3 +425,51 @@ def test_subnormal_fluxes_match_oracle(upwind):
                              1035.0, upwind=upwind)
     assert want["Tadv"].nzval.size > 0
     assert (want["Tadv"].nzval.size == full["Tadv"].nzval.size) == bool(upwind)
+
+
+# ------------------------------------------------------------------------------------------ residency
+def test_inplace_updates_of_caller_arrays_are_seen_and_results_are_frozen():
+    """The reference reads its arguments at call time.  Device residency is keyed on object identity, so it is
+    only granted to arrays this package handed out itself — and those are read-only.  A caller who re-uses ONE set
+    of ϕ buffers month after month (writes into them in place) must get the matrix of the new values."""
+    oc = synthetic.make_config("C1t", seed=4)
+    o = oracle_pipeline(oc)
+    tm1, gm = transport_from_oracle_inputs(o, oc)
+    assert_csc_equal(tm1.Tadv, o["tm"]["Tadv"], "before the update")
+    for k in O.FACES:
+        o["phi"][k] *= -0.5                        # in place: same objects, new content (and reversed flow)
+    gm.thkcello[...] = gm.thkcello * 1.25          # so are the metrics the caller owns
+    want = O.transportmatrix(o["phi"], oc.mlotst, o["v3D"], gm.thkcello, o["area"], oc.lev, o["gm"]["edge"], o["gm"]["dnbr"],
+                             o["topo"], 1035.0)
+    tm2, _ = transport_from_oracle_inputs(o, oc)
+    for oname, gname in NAMES.items():
+        assert_csc_equal(getattr(tm2, gname), want[oname], f"after the in-place update: {oname}")
+    assert tm2.Tadv.nnz == tm1.Tadv.nnz and not np.array_equal(tm2.Tadv.indices, tm1.Tadv.indices)
+    # what makegridmetrics / facefluxes return stays resident, and therefore cannot be written to
+    g = gpu_pipeline(oc)
+    with pytest.raises(ValueError):
+        g["phi"].east[0, 0, 0] = 1.0
+    with pytest.raises(ValueError):
+        g["gm"].thkcello[0, 0, 0] = 1.0
+    with pytest.raises(ValueError):
+        g["gm"].edge_length_2D["east"][0, 0] = 1.0
+    # a writeable copy is the caller's own again: uploaded, and its content is what counts
+    phi2 = A.FaceFluxes(*[np.array(a, order="F") * 2.0 for a in g["phi"]])
+    tm3 = otmb_b200.transportmatrix(ϕ=phi2, mlotst=oc.mlotst, gridmetrics=g["gm"], indices=g["ix"], ρ=1035.0)
+    assert np.array_equal(bits(tm3.Tadv.data), bits(g["tm"].Tadv.data * 2.0))
+
+
+def test_failed_build_invalidates_earlier_results(ctx):
+    """A build that fails its NaN check must not leave the previous build's sizes behind (fetch / spmv would pair
+    them with the new contents)."""
+    oc = synthetic.make_config("C1t", seed=2)
+    g = gpu_pipeline(oc)
+    c = A._ctx_of(g["gm"].v3D)
+    bad = np.array(oc.mlotst, order="F")
+    rho = np.array(oc.rho3d, order="F")
+    rho[np.isfinite(rho)] = np.nan
+    with pytest.raises(A.OTMBError):
+        otmb_b200.transportmatrix(ϕ=g["phi"], mlotst=bad, gridmetrics=g["gm"], indices=g["ix"], ρ=rho)
+    with pytest.raises(A.OTMBError) as e:
+        A.resident_matvec("T", np.ones(g["ix"].N), ctx=c)
+    assert e.value.code == otmb_b200._lib.ERR_STATE
