@@ -46,9 +46,13 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--path", default="fused", choices=["fused", "fused2", "coo"])
-    ap.add_argument("--mode", default="batch", choices=["batch", "sharded"],
-                    help="batch: one matrix per GPU (the contract's weak-scaling line); sharded: ONE matrix k-slab "
-                         "sharded over the GPUs (strong scaling, BASELINE configs[3])")
+    ap.add_argument("--mode", default="both", choices=["both", "batch", "sharded"],
+                    help="batch: one matrix per GPU (the contract's weak-scaling line); sharded: ONE 0.25-degree matrix "
+                         "row-slab sharded over the GPUs (strong scaling, BASELINE configs[3]); both (default): the batch "
+                         "line carrying the sharded record under the key `sharded`")
+    ap.add_argument("--sharded-workload", default="C4")
+    ap.add_argument("--chunks", type=int, default=0, help="column chunks of the pipelined carry plane (0 = library default)")
+    ap.add_argument("--no-check", action="store_true", help="skip the 1-rank re-assembly behind checksum_equals_1rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -172,96 +176,145 @@ def run_reference(args, rank):
     emit(line)
 
 
-def run_sharded(args, rank, local_rank, world):
-    """ONE matrix, k-slab sharded over the ranks (oceantransportmatrixbuilder.jl_b200/sharded.py).  Timed region:
-    the device assembly of every rank's columns, inputs resident; max over ranks."""
+def sharded_record(args, rank, local_rank, world, dist):
+    """ONE matrix of the 0.25-degree shape (BASELINE configs[3]), row-slab sharded over the ranks — strong scaling.
+    Everything between the ranks runs inside libotmb.so over its own NCCL communicator (csrc/comm.cu); torch.distributed
+    only hands out the 128-byte id and reduces the timings.  Two timed regions, inputs resident in HBM, CUDA events on
+    the library's stream, barrier on both sides, max over ranks:
+      assembly   K x otmb_transportmatrix_build on every rank's slab (no collective inside)
+      pipeline   K x [face-flux continuity chain over NCCL (chunk-pipelined carry plane) + assembly] = the per-month work
+    plus position-dependent checksums of the five matrices summed over the ranks, compared with the same matrix
+    assembled by ONE context on rank 0's GPU."""
     import otmb_b200.api as A
     from otmb_b200 import sharded, synthetic
     from _util import fields
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        ex = sharded.TorchExchange(local_rank)
-    else:
-        ex = sharded.ThreadExchange(sharded.ThreadExchange._Shared(1), 0)
-    oc = synthetic.make_config(args.workload, seed=0)
+    t_all = time.perf_counter()
+    oc = synthetic.make_config(args.sharded_workload, seed=0)
     f = fields(oc)
-    ctx0 = A.Context(local_rank)          # geometry of the whole grid (2-D fields + thkcello), computed on this GPU
+    ctx0 = A.Context(local_rank)          # geometry of the whole grid (2-D fields, thkcello), computed on this GPU
     gm = A.makegridmetrics(areacello=f["areacello"], volcello=f["volcello"], lon=f["lon"], lat=f["lat"], lev=f["lev"],
                            lon_vertices=f["lon_vertices"], lat_vertices=f["lat_vertices"], ctx=ctx0)
     ctx0.close()
+    id_bytes = None
+    if world > 1:
+        box = [sharded.NativeSharded.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        id_bytes = box[0]
     t_prep = time.perf_counter()
-    slab, w0, N, info = sharded.prepare_sharded(exchange=ex, gridmetrics=gm, umo=oc.umo, vmo=oc.vmo, FillValue=oc.fill,
-                                                device=local_rank)
-    t_prep = time.perf_counter() - t_prep
-    ctx, lib = slab.ctx, slab.ctx.lib
+    ns = sharded.NativeSharded(gridmetrics=gm, rank=rank, nranks=world, id_bytes=id_bytes, device=local_rank)
+    ns.set_masstransport(oc.umo, oc.vmo, oc.fill)
+    ns.facefluxes(args.chunks)
     kw = dict(mlotst=oc.mlotst, rho=1035.0, kH=500.0, kVML=0.1, kVdeep=1.0e-5, upwind=True)
-    nnz = slab.build(**kw)
+    nnz = ns.build(**kw)
+    t_prep = time.perf_counter() - t_prep
+    ctx, lib, slab = ns.ctx, ns.lib, ns.slab
+
+    def checksums(c, lb, col0, before):
+        out = []
+        for m in range(5):
+            cs = (C.c_uint64 * 3)()
+            c.check(lb.otmb_result_checksum(c.h, m, int(col0), int(before[m]), cs))
+            out += [int(x) for x in cs]
+        return out
+
+    def gather(values):          # host integers of every rank (library communicator; signed 64-bit on the wire)
+        mine = (C.c_int64 * len(values))(*[v - (1 << 64) if v >= (1 << 63) else v for v in values])
+        out = (C.c_int64 * (len(values) * world))()
+        ctx.check(lib.otmb_comm_allgather_i64(ctx.h, mine, len(values), out))
+        return [[int(out[r * len(values) + q]) for q in range(len(values))] for r in range(world)]
+
+    cs_rows = gather(checksums(ctx, lib, ns.w0, ns.nnz_before))
+    cs_sum = [sum(r[q] for r in cs_rows) % (1 << 64) for q in range(15)]
 
     def barrier():
         ctx.check(lib.otmb_synchronize(ctx.h))
         if dist is not None:
-            import torch
-            torch.cuda.synchronize()
             dist.barrier()
 
+    def timed(step, steps):
+        barrier()
+        ctx.check(lib.otmb_timer_start(ctx.h))
+        for _ in range(steps):
+            step()
+        ms = C.c_float()
+        ctx.check(lib.otmb_timer_stop(ctx.h, C.byref(ms)))
+        barrier()
+        return float(ms.value) / steps
+
+    asm = lambda: slab.build(upload=False, **kw)
+
+    def month():
+        ns.facefluxes_enqueue(args.chunks)
+        slab.build(upload=False, **kw)
+
+    def fluxes():
+        ns.facefluxes_enqueue(args.chunks)
+
     for _ in range(max(args.warmup, 3)):
-        slab.build(upload=False, **kw)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.25)
-    barrier()
+        month()
     launches0 = ctx.launches()
-    kernel_ms = []
-    t0 = time.perf_counter()
-    ctx.check(lib.otmb_timer_start(ctx.h))
-    for _ in range(args.steps):
-        slab.build(upload=False, **kw)
-        kernel_ms.append(ctx.last_build_ms())
-    ms = C.c_float()
-    ctx.check(lib.otmb_timer_stop(ctx.h, C.byref(ms)))
-    barrier()
-    t1 = time.perf_counter()
-    clocks = sampler.stop(t0, t1)
+    asm_ms = timed(asm, args.steps)
     launches = ctx.launches() - launches0
-    ms_per_step, k_ms = float(ms.value) / args.steps, sum(kernel_ms) / len(kernel_ms)
+    pipe_ms = timed(month, args.steps)
+    flux_ms = timed(fluxes, args.steps)
+    kernel_ms = []
+    for _ in range(args.steps):
+        asm()
+        kernel_ms.append(ctx.last_build_ms())
+    k_ms = sum(kernel_ms) / len(kernel_ms)
     nx, ny, nz = gm.v3D.shape
-    P, M = nx * ny, gm.v3D.size
-    rows = ex.allgather_ints([int(ms_per_step * 1e6), int(k_ms * 1e6), launches, slab.n_owned] + list(nnz))
-    if rank == 0:
-        ms_per_step = max(r[0] for r in rows) / 1e6
-        k_ms = max(r[1] for r in rows) / 1e6
-        launches = sum(r[2] for r in rows)
-        nnz_tot = [sum(r[4 + m] for r in rows) for m in range(5)]
-        b_in, b_out = algorithmic_bytes(M, P, nz, N, nnz_tot)
-        peak, peak_src = hbm_peak()
-        # per-GPU roofline of the slowest rank: its share of the algorithmic bytes / its kernel time
-        slow = max(range(world), key=lambda r: rows[r][1])
-        k0, k1 = info["slabs"][slow]
-        b_rank = 8 * 7 * P * (k1 - k0) + 8 * 10 * P + sum(8 * (rows[slow][3] + 1) + 16 * rows[slow][4 + m] for m in range(5))
-        achieved = b_rank / (k_ms / 1e3) / 1e9
-        line = {
-            "metric": "T assembly throughput, ONE matrix k-slab sharded (adv+kH+kVML+kVdeep)", "value": nnz_tot[0] / (ms_per_step / 1e3),
-            "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload} {nx}x{ny}x{nz} {oc.topology}, one matrix set (T, Tadv, TkH, TkVML, TkVdeep) "
-                                   f"k-slab sharded over {world} GPU(s)", "N_wet": N, "nnz": dict(zip(A.MATRICES, nnz_tot)),
-                       "slabs": info["slabs"], "wet_per_rank": info["counts"],
-                       "parallelism": f"k-slab x{world}; NCCL only for the face-flux carry planes (setup, not in the timed region)",
-                       "l2": "no flush: per-step working set >> 126 MB L2", "prepare_s": t_prep},
-            "kernel_ms": k_ms,
-        "kernel_ms_min_median_max": [min(kernel_ms), sorted(kernel_ms)[len(kernel_ms) // 2], max(kernel_ms)],
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "peak_source": peak_src, "algorithmic_bytes": b_in + b_out, "algorithmic_bytes_slowest_rank": b_rank,
-                         "kernel": "k_fused_v4 (slowest rank's slab)"},
-            "clocks": clocks, "gpu_launches": launches,
-        }
-        emit(line)
-    if dist is not None:
-        dist.destroy_process_group()
+    P = nx * ny
+    own_cells = (ns.slabs[rank][1] - ns.slabs[rank][0]) * nx
+    b_rank = 8 * 7 * own_cells + 8 * 10 * P + sum(8 * (slab.n_owned + 1) + 16 * nnz[m] for m in range(5))
+    rows = gather([int(asm_ms * 1e6), int(pipe_ms * 1e6), int(flux_ms * 1e6), int(k_ms * 1e6), launches, slab.n_owned, b_rank] + list(nnz))
+
+    # the same matrix from ONE context on rank 0's GPU (at world == 1 that is the run above)
+    same, cs_one, one_ms = None, None, None
+    if world > 1 and rank == 0 and not args.no_check:
+        one = sharded.NativeSharded(gridmetrics=gm, rank=0, nranks=1, id_bytes=None, device=local_rank)
+        one.set_masstransport(oc.umo, oc.vmo, oc.fill)
+        one.facefluxes(1)
+        nnz_one = one.build(**kw)
+        cs_one = checksums(one.ctx, one.lib, 0, [0] * 5)
+        one.slab.build(upload=False, **kw)
+        one_ms = one.ctx.last_build_ms()
+        same = cs_one == cs_sum and nnz_one == ns.nnz_total
+        one.close()
+    ns.close()
+    if rank != 0:
+        return None
+    peak, peak_src = hbm_peak()
+    slow = max(range(world), key=lambda r: rows[r][3])
+    nnz_tot = ns.nnz_total
+    M, N = gm.v3D.size, ns.N
+    b_in, b_out = algorithmic_bytes(M, P, nz, N, nnz_tot)
+    amax = max(r[0] for r in rows) / 1e6
+    pmax = max(r[1] for r in rows) / 1e6
+    fmax = max(r[2] for r in rows) / 1e6
+    kslow = rows[slow][3] / 1e6
+    wet = [r[5] for r in rows]
+    return {
+        "workload": f"{args.sharded_workload} {nx}x{ny}x{nz} {oc.topology} (ACCESS-OM2 0.25deg shape), ONE matrix set (T, Tadv, TkH, TkVML, "
+                    f"TkVdeep) row-slab sharded over {world} GPU(s)",
+        "scaling": "strong", "unit": UNIT, "n_gpus": world, "steps": args.steps, "N_wet": N,
+        "nnz": dict(zip(A.MATRICES, nnz_tot)),
+        "assembly": {"ms": amax, "value": nnz_tot[0] / (amax / 1e3), "ms_per_rank": [r[0] / 1e6 for r in rows],
+                     "timed": "K x otmb_transportmatrix_build on every rank's slab; inputs resident; max over ranks"},
+        "pipeline": {"ms": pmax, "value": nnz_tot[0] / (pmax / 1e3), "ms_per_rank": [r[1] / 1e6 for r in rows],
+                     "facefluxes_chain_ms": fmax, "chunks": args.chunks or (8 if world > 1 else 1),
+                     "timed": "K x [facefluxes continuity chain (NCCL send/recv of the chunked carry plane on the library stream) "
+                              "+ assembly]; umo/vmo resident; max over ranks"},
+        "roofline_slowest_rank": {"rank": slow, "kernel_ms": kslow, "algorithmic_bytes": rows[slow][6],
+                                  "achieved": rows[slow][6] / (kslow / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                                  "frac": rows[slow][6] / (kslow / 1e3) / 1e9 / peak, "peak_source": peak_src},
+        "algorithmic_bytes": b_in + b_out,
+        "slabs_rows": ns.slabs, "wet_per_rank": wet, "imbalance": max(wet) / (sum(wet) / world) - 1.0,
+        "checksum": [f"{x:016x}" for x in cs_sum],
+        "checksum_equals_1rank": True if world == 1 else same,
+        "one_rank_kernel_ms_same_gpu": one_ms,
+        "gpu_launches": sum(r[4] for r in rows), "prepare_s": t_prep, "total_s": time.perf_counter() - t_all,
+        "comm": "NCCL inside libotmb.so (dlopen), id broadcast by the host program" if world > 1 else "none (one rank)",
+    }
 
 
 def pinned(lib, shape, dtype):
@@ -301,16 +354,23 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank)
         return
-    if args.mode == "sharded":
-        run_sharded(args, rank, local_rank, world)
-        return
-
     dist = None
     if world > 1:
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.mode == "sharded":
+        rec = sharded_record(args, rank, local_rank, world, dist)
+        if rank == 0:
+            emit({"metric": "T assembly throughput, ONE 0.25deg matrix row-slab sharded (adv+kH+kVML+kVdeep)",
+                  "value": rec["assembly"]["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                  "warmup": max(args.warmup, 3), "ms_per_step": rec["assembly"]["ms"], "higher_is_better": True,
+                  "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                  "config": {"workload": rec["workload"]}, "sharded": rec, "gpu_launches": rec["gpu_launches"]})
+        if dist is not None:
+            dist.destroy_process_group()
+        return
 
     import otmb_b200
     import otmb_b200.api as A
@@ -423,6 +483,15 @@ def main():
         s = torch.tensor([nnz_list[0], launches], device="cuda", dtype=torch.int64)
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
         nnzT_total, launches = int(s[0]), int(s[1])
+    # ---- the north star's second half: ONE 0.25-degree matrix row-slab sharded over the same ranks --------------
+    shard = None
+    if args.mode == "both":
+        del phi, f
+        ctx.close()
+        try:
+            shard = sharded_record(args, rank, local_rank, world, dist)
+        except Exception as e:      # noqa: BLE001 - the contract line must still be printed
+            shard = {"error": f"{type(e).__name__}: {e}"}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -465,6 +534,9 @@ def main():
         line["cpu_baseline"] = {"value": otm["T"].nnz / otm["seconds"], "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": "1 full C2 matrix (360x300x50), oracle/otmb_oracle.cpp single thread "
                                           f"({otm['seconds']:.2f} s); host has {os.cpu_count()} cores; no Julia in image"}
+    if shard is not None:
+        line["sharded"] = shard
+        line["gpu_launches_sharded"] = shard.get("gpu_launches")
     emit(line)
     if dist is not None:
         dist.destroy_process_group()

@@ -46,6 +46,7 @@ enum {
                                    hits a MethodError there, src/matrixbuilding.jl:247-250 */
     OTMB_ERR_BADARG = 9,
     OTMB_ERR_STATE = 10,        /* call order: a prerequisite step has not run on this ctx */
+    OTMB_ERR_COMM = 11,         /* NCCL could not be loaded / a collective failed (sharded runs only) */
     OTMB_ERR_CUDA = 100,
     OTMB_ERR_NO_GPU = 101,
     OTMB_ERR_TOO_LARGE = 102
@@ -110,28 +111,72 @@ int otmb_set_gridmetrics(otmb_ctx* ctx, const double* area2D, const double* thkc
  * NamedTuple (east, west, north, south, top, bottom); they also stay resident as ϕ. */
 int otmb_facefluxes(otmb_ctx* ctx, const double* umo, const double* vmo, double fill_value,
                     double* east, double* west, double* north, double* south, double* top, double* bottom);
-/* ---- k-slab sharding of ONE matrix across GPUs (one context per GPU / rank) -----------------------
- * Wet ranks are ordered k-slowest, so a contiguous range of levels [k_begin, k_end) is a contiguous
- * block of rows/columns of every matrix.  A slab context keeps those levels plus one halo level on
- * either side resident, assembles the CSC COLUMNS of its owned cells (rows stay global wet ranks)
- * and returns them with local colptr offsets; the host concatenates the ranks' segments.
- * Call order: otmb_set_grid, otmb_set_slab, otmb_makeindices, [otmb_slab_counts on every rank ->
- * exclusive sum over lower ranks], otmb_set_rank_offset, metrics / fluxes / build / fetch as usual.
- * Every function still takes the FULL (nx,ny,nz) host arrays; only the slab's window is copied.
+/* ---- ONE matrix sharded across the GPUs of a box: row slabs (one context per GPU / rank) --------------------
+ * A grid row is R = j + ny*k (0-based), so a range of rows [row_begin, row_end) is a contiguous range of linear
+ * cells and — wet ranks being ordered by linear index (src/matrixbuilding.jl:14-16) — a contiguous block of
+ * rows/columns of every matrix.  A slab context keeps its rows plus one level (nx*ny cells) of halo on either side
+ * resident (device arrays are allocated for that window only, set-up kernels scan only it), assembles the CSC
+ * COLUMNS of its owned cells (row indices stay global wet ranks) and returns them with local colptr offsets; the
+ * matrix is the concatenation of the ranks' segments.  Cuts may fall inside a level (any j), which balances the
+ * ranks to within one grid row of N/R wet cells.
+ * Every function still takes the caller's FULL (nx,ny,nz) host arrays; only the window is copied.
  * The reference has no counterpart (single process); this shards its loop `for 𝑖 in eachindex(Lwet)`
- * (src/matrixbuilding.jl:237, 348, 450). */
-int otmb_set_slab(otmb_ctx* ctx, int64_t k_begin, int64_t k_end);   /* 0-based levels; (0, nz) = unsharded */
+ * (src/matrixbuilding.jl:237, 348, 450).
+ *
+ * Two ways to drive it:
+ *  (a) with the library's communicator (NCCL over NVLink, loaded on demand):
+ *        otmb_plan_slabs -> otmb_set_grid -> otmb_set_slab_rows -> otmb_comm_init -> otmb_sharded_makeindices ->
+ *        otmb_set_gridmetrics -> otmb_set_masstransport -> otmb_sharded_facefluxes -> otmb_set_mlotst ->
+ *        otmb_sharded_transportmatrix_build -> otmb_transportmatrix_fetch[_all]
+ *      The host program only has to give every rank the same 128-byte id (MPI.bcast, a file, torch.distributed, ...).
+ *  (b) with exchanges done by the host (tests on one GPU, gloo): otmb_makeindices / otmb_slab_counts /
+ *      otmb_set_rank_offset / otmb_facefluxes_slab / otmb_transportmatrix_build.                                  */
+/* host-side plan, no GPU needed: cut the ny*nz grid rows into nranks contiguous slabs of about equal wet count
+ * (wet <=> !isnan(v3D)).  level_cuts_only != 0 restricts cuts to level boundaries.  row_cuts: nranks+1 entries,
+ * rank r owns [row_cuts[r], row_cuts[r+1]); wet_per_rank (nranks, may be NULL).  Deterministic. */
+int otmb_plan_slabs(const double* v3D, int64_t nx, int64_t ny, int64_t nz, int32_t nranks, int32_t level_cuts_only,
+                    int64_t* row_cuts, int64_t* wet_per_rank);
+int otmb_set_slab_rows(otmb_ctx* ctx, int64_t row_begin, int64_t row_end);   /* (0, ny*nz) = unsharded */
+int otmb_set_slab(otmb_ctx* ctx, int64_t k_begin, int64_t k_end);   /* whole levels: rows [k_begin*ny, k_end*ny) */
 int otmb_slab_counts(otmb_ctx* ctx, int64_t* n_owned, int64_t* n_halo_above);
 int otmb_set_rank_offset(otmb_ctx* ctx, int64_t w0);   /* global wet rank (0-based) of the first owned cell */
 /* facefluxes on a slab.  The continuity scan (src/velocities.jl:234-243) runs bottom-up and is not
- * associative in floating point, so the slabs form a chain: carry_in = ϕtop of level k_end computed by
- * the slab below (NULL for the deepest slab), carry_out = ϕtop of level k_begin for the slab above.
- * carry_on_device != 0: both are DEVICE pointers of nx*ny doubles (e.g. the buffers an NCCL send/recv
- * works on).  valid_uv[0..1]: whether this slab saw any valid umo / vmo value; the caller combines the
- * ranks and raises the reference's assertion (:199-200).  Outputs: owned levels of the full-size arrays. */
+ * associative in floating point, so the slabs form a chain: carry_in[i,j] = ϕtop of the cell below this slab's
+ * deepest owned cell of column (i,j), computed by the slab below (NULL for the deepest slab), carry_out[i,j] = ϕtop of
+ * the column's first owned level, for the slab above (a column of which the slab owns nothing passes the value on).
+ * carry_on_device != 0: both are DEVICE pointers of nx*ny doubles.  valid_uv[0..1]: whether this slab saw any valid
+ * umo / vmo value; the caller combines the ranks and raises the reference's assertion (:199-200).
+ * Outputs: owned cells of the full-size arrays. */
 int otmb_facefluxes_slab(otmb_ctx* ctx, const double* umo, const double* vmo, double fill_value,
                          const double* carry_in, double* carry_out, int32_t carry_on_device, int32_t valid_uv[2],
                          double* east, double* west, double* north, double* south, double* top, double* bottom);
+
+/* the library's communicator: one rank per context / GPU.  otmb_comm_unique_id on one rank, the 128 bytes handed
+ * to every rank by the host program, otmb_comm_init on all of them (collective).  nranks == 1 needs no id and
+ * loads nothing. */
+#define OTMB_COMM_ID_BYTES 128
+int otmb_comm_unique_id(uint8_t id[OTMB_COMM_ID_BYTES]);
+int otmb_comm_init(otmb_ctx* ctx, int32_t nranks, int32_t rank, const uint8_t id[OTMB_COMM_ID_BYTES]);
+int otmb_comm_free(otmb_ctx* ctx);
+int otmb_comm_allgather_i64(otmb_ctx* ctx, const int64_t* mine, int32_t count, int64_t* all /* nranks*count */);
+/* collective steps (every rank calls them; a failure on ANY rank is returned on EVERY rank, so nobody is left
+ * waiting in a collective for a peer that has raised):
+ *  - makeindices on the slab + all-gather of the owned counts: N of the whole ocean, this rank's first wet rank
+ *    (already applied: no otmb_set_rank_offset needed) and its number of columns;
+ *  - otmb_set_masstransport uploads the window of umo / vmo (local); otmb_sharded_facefluxes runs the continuity
+ *    chain from the sea-floor rank (nranks-1) up to the surface rank (0): the carry plane is cut into `nchunks`
+ *    column chunks (0 = default) which are sent / received with NCCL on the context's stream and PIPELINED — a rank
+ *    starts on a chunk as soon as the rank below has sent it.  Outputs (may be NULL): owned cells of full-size
+ *    arrays.  The all-fill assertion (:199-200) is evaluated over all ranks.  otmb_sharded_facefluxes_enqueue is
+ *    the device-resident chain alone (no flags, no copies, does not block);
+ *  - assembly of this rank's columns + all-gather of the nnz: entries held by lower ranks (add to the local
+ *    colptr) and of the whole matrix. */
+int otmb_sharded_makeindices(otmb_ctx* ctx, const double* v3D, int64_t* N_global, int64_t* w0, int64_t* n_owned);
+int otmb_set_masstransport(otmb_ctx* ctx, const double* umo, const double* vmo, double fill_value);
+int otmb_sharded_facefluxes(otmb_ctx* ctx, int32_t nchunks, double* east, double* west, double* north, double* south,
+                            double* top, double* bottom);
+int otmb_sharded_facefluxes_enqueue(otmb_ctx* ctx, int32_t nchunks);
+/* int otmb_sharded_transportmatrix_build(...): declared below, after otmb_tm_params */
 
 /* upload caller-held ϕ (order OTMB_FACE_*) */
 int otmb_set_facefluxes(otmb_ctx* ctx, const double* const phi[6]);
@@ -155,6 +200,9 @@ typedef struct otmb_tm_params {
  * TκVdeep, upwind), src/matrixbuilding.jl:128-150, on the resident inputs.  Blocks until the
  * five matrices are complete in device memory; nnz_out[OTMB_MAT_*]. */
 int otmb_transportmatrix_build(otmb_ctx* ctx, const otmb_tm_params* params, int64_t nnz_out[5]);
+/* the collective form for a sharded run (see "ONE matrix sharded across the GPUs" above) */
+int otmb_sharded_transportmatrix_build(otmb_ctx* ctx, const otmb_tm_params* params, int64_t nnz_local[5],
+                                       int64_t nnz_before[5], int64_t nnz_total[5]);
 /* copy one result out as SparseMatrixCSC fields: colptr (N+1), rowval (nnz), nzval (nnz) */
 int otmb_transportmatrix_fetch(otmb_ctx* ctx, int which, int64_t* colptr, int64_t* rowval, double* nzval);
 /* the same for several results at once (bit m of mask = matrix OTMB_MAT_m, 0 = all five; NULL entries are
@@ -221,6 +269,13 @@ int otmb_lump_and_spray_fetch(otmb_ctx* ctx, int64_t* lump_colptr /* N+1 */, int
  * (test/online.jl:110-115) without copying the matrix to the host first.  x, y: N doubles (host).  Deterministic
  * and bit-identical to a sequential CSC product. */
 int otmb_spmv(otmb_ctx* ctx, int which, int transpose, const double* x, double* y);
+
+/* Position-dependent 64-bit checksums of the resident result `which`, taken as the segment of a larger matrix that
+ * starts at column col_offset / entry entry_offset: out[0] over colptr (first ncols entries), out[1] over rowval,
+ * out[2] over the bit patterns of nzval; each is a SUM of hashes of (global position, value), so the checksums of the
+ * ranks of a sharded run add up (mod 2^64) to those of the same matrix assembled on one GPU — how bench.py proves
+ * that the N-rank result equals the 1-rank one without moving the matrix. */
+int otmb_result_checksum(otmb_ctx* ctx, int which, int64_t col_offset, int64_t entry_offset, uint64_t out[3]);
 
 /* measurement helpers: CUDA events on the ctx stream (the stream every kernel of this
  * library is launched on), an L2 flush, and per-kernel launch counting. */

@@ -10,6 +10,7 @@ LIB_PATH = HERE / "libotmb.so"
 OK = 0
 ERR_TADV_NAN, ERR_TKH_NAN, ERR_TKVML_NAN, ERR_TKVDEEP_NAN, ERR_RHO_NAN = 1, 2, 3, 4, 5
 ERR_UNKNOWN_GRID, ERR_ALL_FILL, ERR_DRY_NEIGHBOUR, ERR_BADARG, ERR_STATE = 6, 7, 8, 9, 10
+ERR_COMM = 11
 ERR_CUDA, ERR_NO_GPU, ERR_TOO_LARGE = 100, 101, 102
 TOPO = {"bipolar": 0, "tripolar": 1, "unknown": 2}
 PATH = {"fused": 0, "fused2": 1, "coo": 2}
@@ -24,6 +25,9 @@ EXPORTS = [
     "otmb_dyad_derivative", "otmb_bolus_gm_velocity", "otmb_timer_start", "otmb_timer_stop", "otmb_l2_flush",
     "otmb_launch_count", "otmb_last_build_ms", "otmb_synchronize", "otmb_set_slab", "otmb_slab_counts",
     "otmb_set_rank_offset", "otmb_facefluxes_slab", "otmb_velocity2fluxes", "otmb_fluxes2velocity", "otmb_bgrid_to_cgrid", "otmb_lump_and_spray_build", "otmb_lump_and_spray_fetch", "otmb_spmv",
+    "otmb_plan_slabs", "otmb_set_slab_rows", "otmb_comm_unique_id", "otmb_comm_init", "otmb_comm_free", "otmb_comm_allgather_i64",
+    "otmb_sharded_makeindices", "otmb_set_masstransport", "otmb_sharded_facefluxes", "otmb_sharded_facefluxes_enqueue",
+    "otmb_sharded_transportmatrix_build", "otmb_result_checksum",
 ]
 
 
@@ -89,6 +93,18 @@ def load():
         "otmb_lump_and_spray_fetch": ([vp] * 8, C.c_int),
         "otmb_spmv": ([vp, C.c_int, C.c_int, vp, vp], C.c_int),
         "otmb_set_slab": ([vp, i64, i64], C.c_int),
+        "otmb_set_slab_rows": ([vp, i64, i64], C.c_int),
+        "otmb_result_checksum": ([vp, C.c_int, i64, i64, C.POINTER(C.c_uint64)], C.c_int),
+        "otmb_plan_slabs": ([vp, i64, i64, i64, i32, i32, pi64, pi64], C.c_int),
+        "otmb_comm_unique_id": ([vp], C.c_int),
+        "otmb_comm_init": ([vp, i32, i32, vp], C.c_int),
+        "otmb_comm_free": ([vp], C.c_int),
+        "otmb_comm_allgather_i64": ([vp, pi64, i32, pi64], C.c_int),
+        "otmb_sharded_makeindices": ([vp, vp, pi64, pi64, pi64], C.c_int),
+        "otmb_set_masstransport": ([vp, vp, vp, dbl], C.c_int),
+        "otmb_sharded_facefluxes": ([vp, i32] + [vp] * 6, C.c_int),
+        "otmb_sharded_facefluxes_enqueue": ([vp, i32], C.c_int),
+        "otmb_sharded_transportmatrix_build": ([vp, C.POINTER(TMParams), pi64, pi64, pi64], C.c_int),
         "otmb_slab_counts": ([vp, pi64, pi64], C.c_int),
         "otmb_set_rank_offset": ([vp, i64], C.c_int),
         "otmb_facefluxes_slab": ([vp, vp, vp, dbl, vp, vp, i32, C.POINTER(i32)] + [vp] * 6, C.c_int),

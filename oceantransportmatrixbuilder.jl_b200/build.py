@@ -11,7 +11,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 INCLUDE = HERE.parent / "include"
 LIB = HERE / "libotmb.so"
-SOURCES = ["ctx.cu", "scan.cu", "geometry.cu", "faceflux.cu", "fused.cu", "fused_v4.cu", "coo.cu", "transport.cu", "redigm.cu", "velocity.cu", "lump.cu", "spmv.cu", "fetch.cu"]
+SOURCES = ["ctx.cu", "scan.cu", "geometry.cu", "faceflux.cu", "fused.cu", "fused_v4.cu", "coo.cu", "transport.cu", "redigm.cu", "velocity.cu", "lump.cu", "spmv.cu", "fetch.cu", "comm.cu"]
 HEADERS = ["common.cuh", "sphere.cuh", "fused_generic.cuh"]
 
 NVCC_FLAGS = [
@@ -63,7 +63,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
     if any(rc != 0 for _, rc, _ in results):
         raise RuntimeError("nvcc failed:\n" + log)
     cmd = [nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC",
-           *[str(o) for o, _, _ in results], "-o", str(LIB)]
+           *[str(o) for o, _, _ in results], "-ldl", "-o", str(LIB)]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc link failed:\n" + r.stdout)

@@ -62,12 +62,27 @@ struct otmb_ctx {
     int sm_count = OTMB_SM_COUNT_HINT;
 
     i64 nx = 0, ny = 0, nz = 0, P = 0, M = 0, N = 0, nwords = 0;
-    // k-slab sharding (otmb_set_slab): this context owns the levels [k_own0, k_own1) and keeps one halo
-    // level on either side resident, [k_win0, k_win1).  Unsharded: own = window = [0, nz).
-    // N = wet cells in the window (local ranks 0..N), ncols = owned wet cells = columns this context
-    // assembles, h_up = wet cells of the upper halo level, w0 = global wet rank of the first owned cell.
+    // Row-slab sharding of one matrix (otmb_set_slab_rows / otmb_set_slab).  A grid row is R = j + ny*k, so a range of
+    // rows [row0, row1) is a contiguous range of linear cells [L_own0, L_own1) AND — wet ranks being ordered by linear
+    // index — a contiguous block of rows/columns of every matrix.  The context keeps one level (P cells) of halo on
+    // either side resident: the window [L_win0, L_win1).  3-D arrays are allocated for the window only and handed
+    // to the kernels through pointers biased by -L_win0 (win<T>()), so every kernel keeps using GLOBAL linear indices.
+    // Unsharded: own = window = [0, M).
+    // N = wet cells in the window (local ranks 0..N), ncols = owned wet cells = columns this context assembles,
+    // h_up = wet cells of the halo above the owned range, w0 = global wet rank of the first owned cell.
     bool sharded = false, have_rank_offset = false;
-    i64 k_own0 = 0, k_own1 = 0, k_win0 = 0, k_win1 = 0, ncols = 0, h_up = 0, w0 = 0;
+    i64 L_own0 = 0, L_own1 = 0, L_win0 = 0, L_win1 = 0, ncols = 0, h_up = 0, w0 = 0;
+    template <typename T>
+    T* win(const DevBuf& b) const { return b.as<T>() - L_win0; }                      // index with a global linear cell index
+    u64* mask_win() const { return mask.as<u64>() - (L_win0 >> 6); }                  // index with (L >> 6)
+    uint32_t* wpre_win() const { return wpre.as<uint32_t>() - (L_win0 >> 6); }
+    size_t win_cells() const { return (size_t)(L_win1 - L_win0); }
+    // NCCL communicator of a sharded run (comm.cu; the library is dlopen'ed, ncclComm_t kept opaque here)
+    void* comm = nullptr;
+    int comm_rank = 0, comm_size = 1;
+    DevBuf comm_buf;          // small device staging for the integer all-gathers
+    bool have_uv = false;     // umo / vmo are resident in stage_a / stage_b (otmb_set_masstransport)
+    double uv_fill = 0.0;
     int topo = OTMB_TOPO_UNKNOWN;
     bool have_grid = false, have_indices = false, have_metrics = false, have_phi = false, have_mlotst = false,
          have_rho3d = false, have_z3d = false, have_lonlat = false;
@@ -197,5 +212,10 @@ int otmb_dev_sparse(otmb_ctx* ctx, i64 len, const i64* dI, const i64* dJ, const 
                     int base, DevBuf& colptr, DevBuf& rowval, DevBuf& nzval, i64* nnz);
 int otmb_dev_spadd(otmb_ctx* ctx, i64 n, int base, const i64* acp, const i64* arv, const double* anz, const i64* bcp,
                    const i64* brv, const double* bnz, DevBuf& colptr, DevBuf& rowval, DevBuf& nzval, i64* nnz);
+int otmb_faceflux_begin(otmb_ctx* ctx, double fill);
+int otmb_faceflux_columns(otmb_ctx* ctx, double fill, i64 p_begin, i64 p_end, const double* d_in, double* d_out);
+int otmb_faceflux_copy_out(otmb_ctx* ctx, double* const outs[6]);
+int otmb_upload_uv(otmb_ctx* ctx, const double* umo, const double* vmo, double fill);
+void otmb_comm_release(otmb_ctx* ctx);
 int otmb_fetch_flags(otmb_ctx* ctx);
 int otmb_reset_flags(otmb_ctx* ctx);

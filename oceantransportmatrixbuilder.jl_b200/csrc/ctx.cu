@@ -6,20 +6,23 @@
 // the per-word popcounts.  wet index of cell L = wpre[L/64] + popc(mask[L/64] & lowbits(L%64)):
 // 12 bytes per 64 cells instead of the reference's 9 bytes per cell Lwet3D array, small
 // enough to live in L1/L2 for every neighbour query of the assembly kernels.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
 
 // one warp per 64-cell word: two coalesced loads per lane, two ballots -> the chunk
-__global__ void __launch_bounds__(256) k_wetmask(const double* __restrict__ v3D, i64 M, u64* __restrict__ mask,
-                                                 uint32_t* __restrict__ wcount, i64 nwords) {
+// (v3D, mask, wcount are window-biased pointers indexed by global cell / word; cells outside [L0, L1) read as dry)
+__global__ void __launch_bounds__(256) k_wetmask(const double* __restrict__ v3D, i64 L0, i64 L1, u64* __restrict__ mask,
+                                                 uint32_t* __restrict__ wcount, i64 word0, i64 word1) {
     const int lane = threadIdx.x & 31;
     const i64 gw = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
-    for (i64 w = gw; w < nwords; w += nwarps) {
+    for (i64 w = word0 + gw; w < word1; w += nwarps) {
         const i64 a = w * 64 + lane, b = a + 32;
-        const double va = a < M ? __ldg(v3D + a) : __longlong_as_double(0x7ff8000000000000ll);
-        const double vb = b < M ? __ldg(v3D + b) : __longlong_as_double(0x7ff8000000000000ll);
+        const double va = (a >= L0 && a < L1) ? __ldg(v3D + a) : __longlong_as_double(0x7ff8000000000000ll);
+        const double vb = (b >= L0 && b < L1) ? __ldg(v3D + b) : __longlong_as_double(0x7ff8000000000000ll);
         const unsigned lo = __ballot_sync(0xffffffffu, !isnan(va));
         const unsigned hi = __ballot_sync(0xffffffffu, !isnan(vb));
         if (lane == 0) {
@@ -40,10 +43,10 @@ __global__ void __launch_bounds__(256) k_fill_indices(const u64* __restrict__ ma
 }
 
 __global__ void __launch_bounds__(256) k_fill_lwet32(const u64* __restrict__ mask, const uint32_t* __restrict__ wpre,
-                                                     i64 M, int rank_offset, int* __restrict__ lwet,
+                                                     i64 L0, i64 L1, int rank_offset, int* __restrict__ lwet,
                                                      int* __restrict__ rank3d) {
-    const i64 L = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (L >= M) return;
+    const i64 L = L0 + (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (L >= L1) return;
     const bool wet = wet_at(mask, (int)L);
     const int r = rank_at(mask, wpre, (int)L);
     // the reference's Lwet3D (0-based, -1 = missing), src/matrixbuilding.jl:18-20; global rank when sharded
@@ -65,23 +68,28 @@ int upload(otmb_ctx* ctx, DevBuf& buf, const void* host, size_t bytes) {
 
 }  // namespace
 
+// `host` is the caller's FULL (nx,ny,nz) array; the device buffer holds the context's window only (win<T>())
 int otmb_upload3d(otmb_ctx* c, DevBuf& buf, const double* host) {
-    CU_TRY(c, buf.ensure((size_t)c->M * 8));
-    const size_t a = (size_t)c->k_win0 * c->P, b = (size_t)c->k_win1 * c->P;
-    CU_TRY(c, cudaMemcpyAsync((double*)buf.p + a, host + a, (b - a) * 8, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, buf.ensure(c->win_cells() * 8));
+    CU_TRY(c, cudaMemcpyAsync(buf.p, host + c->L_win0, c->win_cells() * 8, cudaMemcpyHostToDevice, c->stream));
     return OTMB_OK;
 }
 
 // number of wet cells with linear index < X (two small reads of the resident mask / prefix)
+// (counted from the window's first cell)
 static int wet_below(otmb_ctx* c, i64 X, i64* out) {
-    if (X >= c->M) {
+    if (X >= c->L_win1) {
         *out = c->N;
+        return OTMB_OK;
+    }
+    if (X <= c->L_win0) {
+        *out = 0;
         return OTMB_OK;
     }
     u64 word = 0;
     uint32_t pre = 0;
-    CU_TRY(c, cudaMemcpyAsync(&word, c->mask.as<u64>() + (X >> 6), 8, cudaMemcpyDeviceToHost, c->stream));
-    CU_TRY(c, cudaMemcpyAsync(&pre, c->wpre.as<uint32_t>() + (X >> 6), 4, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(&word, c->mask_win() + (X >> 6), 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(&pre, c->wpre_win() + (X >> 6), 4, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     *out = (i64)pre + __builtin_popcountll(word & ((1ull << (X & 63)) - 1ull));
     return OTMB_OK;
@@ -89,9 +97,10 @@ static int wet_below(otmb_ctx* c, i64 X, i64* out) {
 
 static int fill_ranks(otmb_ctx* c) {
     CU_TRY(c, c->lwet.ensure((size_t)(c->N + 1) * 4));
-    CU_TRY(c, c->rank3d.ensure((size_t)(c->M + 1) * 4));
-    k_fill_lwet32<<<grid_for(c->M, 256), 256, 0, c->stream>>>(c->mask.as<u64>(), c->wpre.as<uint32_t>(), c->M,
-                                                               (int)(c->w0 - c->h_up), c->lwet.as<int>(), c->rank3d.as<int>());
+    CU_TRY(c, c->rank3d.ensure((c->win_cells() + 1) * 4));
+    k_fill_lwet32<<<grid_for((i64)c->win_cells(), 256), 256, 0, c->stream>>>(c->mask_win(), c->wpre_win(), c->L_win0, c->L_win1,
+                                                                             (int)(c->w0 - c->h_up), c->lwet.as<int>(),
+                                                                             c->win<int>(c->rank3d));
     LAUNCHED(c);
     CU_TRY(c, cudaGetLastError());
     c->have_rank_offset = true;
@@ -142,6 +151,7 @@ const char* otmb_status_string(int s) {
         case OTMB_ERR_DRY_NEIGHBOUR: return "non-zero flux from a dry or absent neighbour";
         case OTMB_ERR_BADARG: return "bad argument";
         case OTMB_ERR_STATE: return "missing prerequisite call";
+        case OTMB_ERR_COMM: return "communicator (NCCL) error";
         case OTMB_ERR_CUDA: return "CUDA error";
         case OTMB_ERR_NO_GPU: return "no usable sm_100 GPU (there is no CPU fallback)";
         case OTMB_ERR_TOO_LARGE: return "grid too large";
@@ -186,6 +196,8 @@ int otmb_destroy(otmb_ctx* c) {
     if (!c) return OTMB_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    otmb_comm_release(c);
+    c->comm_buf.release();
     DevBuf* bufs[] = {&c->v3D, &c->mask, &c->wcount, &c->wpre, &c->lwet, &c->rank3d, &c->area2D, &c->thk, &c->Z3D, &c->zt, &c->edge, &c->dnbr,
                       &c->dedge, &c->lon, &c->lat, &c->lonv, &c->latv, &c->mlotst, &c->rho3d, &c->stage_a, &c->stage_b,
                       &c->flags, &c->tile_state, &c->scan_tmp, &c->sp_colptr, &c->sp_rowval, &c->sp_nzval, &c->l2};
@@ -252,10 +264,27 @@ int otmb_set_grid(otmb_ctx* c, int64_t nx, int64_t ny, int64_t nz, int topology)
     c->have_indices = c->have_metrics = c->have_phi = c->have_mlotst = c->have_rho3d = c->have_z3d = c->have_lonlat = false;
     for (int q = 0; q < 5; ++q) c->have_mat[q] = c->preset[q] = false;
     c->N = 0;
-    c->sharded = c->have_rank_offset = false;
-    c->k_own0 = c->k_win0 = 0;
-    c->k_own1 = c->k_win1 = nz;
+    c->sharded = c->have_rank_offset = c->have_uv = false;
+    c->L_own0 = c->L_win0 = 0;
+    c->L_own1 = c->L_win1 = c->M;
     c->ncols = c->h_up = c->w0 = 0;
+    return OTMB_OK;
+}
+
+int otmb_set_slab_rows(otmb_ctx* c, int64_t row_begin, int64_t row_end) {
+    if (!c) return OTMB_ERR_BADARG;
+    OT_TRY(otmb_need(c, c->have_grid, "otmb_set_grid"));
+    if (row_begin < 0 || row_end > c->ny * c->nz || row_begin >= row_end)
+        return otmb_fail(c, OTMB_ERR_BADARG, "slab must be a non-empty range of grid rows (row = j + ny*k)");
+    c->L_own0 = row_begin * c->nx;
+    c->L_own1 = row_end * c->nx;
+    c->L_win0 = std::max<i64>(0, c->L_own0 - c->P);
+    c->L_win1 = std::min<i64>(c->M, c->L_own1 + c->P);
+    c->sharded = !(c->L_own0 == 0 && c->L_own1 == c->M);
+    c->have_indices = c->have_metrics = c->have_phi = c->have_mlotst = c->have_rho3d = c->have_z3d = c->have_lonlat = false;
+    c->have_rank_offset = c->have_uv = false;
+    for (int q = 0; q < 5; ++q) c->have_mat[q] = c->preset[q] = false;
+    c->N = c->ncols = c->h_up = c->w0 = 0;
     return OTMB_OK;
 }
 
@@ -263,16 +292,7 @@ int otmb_set_slab(otmb_ctx* c, int64_t k_begin, int64_t k_end) {
     if (!c) return OTMB_ERR_BADARG;
     OT_TRY(otmb_need(c, c->have_grid, "otmb_set_grid"));
     if (k_begin < 0 || k_end > c->nz || k_begin >= k_end) return otmb_fail(c, OTMB_ERR_BADARG, "slab must be a non-empty level range");
-    c->k_own0 = k_begin;
-    c->k_own1 = k_end;
-    c->k_win0 = k_begin > 0 ? k_begin - 1 : 0;
-    c->k_win1 = k_end < c->nz ? k_end + 1 : c->nz;
-    c->sharded = !(k_begin == 0 && k_end == c->nz);
-    c->have_indices = c->have_metrics = c->have_phi = c->have_mlotst = c->have_rho3d = c->have_z3d = c->have_lonlat = false;
-    c->have_rank_offset = false;
-    for (int q = 0; q < 5; ++q) c->have_mat[q] = c->preset[q] = false;
-    c->N = c->ncols = c->h_up = c->w0 = 0;
-    return OTMB_OK;
+    return otmb_set_slab_rows(c, k_begin * c->ny, k_end * c->ny);
 }
 
 int otmb_slab_counts(otmb_ctx* c, int64_t* n_owned, int64_t* n_halo_above) {
@@ -298,18 +318,16 @@ int otmb_makeindices(otmb_ctx* c, const double* v3D, int64_t* N) {
     if (!c || !v3D) return OTMB_ERR_BADARG;
     OT_TRY(otmb_need(c, c->have_grid, "otmb_set_grid"));
     CU_TRY(c, cudaSetDevice(c->device));
-    if (c->sharded) {
-        // cells outside the window read as dry (all-ones bytes are a NaN): their data never reaches this GPU
-        CU_TRY(c, c->v3D.ensure((size_t)c->M * 8));
-        CU_TRY(c, cudaMemsetAsync(c->v3D.p, 0xff, (size_t)c->M * 8, c->stream));
-    }
+    // Only the window's cells reach this GPU (and only they are scanned); cells outside it read as dry.
     OT_TRY(otmb_upload3d(c, c->v3D, v3D));
+    const i64 word0 = c->L_win0 >> 6, word1 = (c->L_win1 + 63) >> 6;
+    c->nwords = word1 - word0;
     CU_TRY(c, c->mask.ensure((size_t)(c->nwords + 1) * 8));
     CU_TRY(c, c->wcount.ensure((size_t)(c->nwords + 1) * 4));
     CU_TRY(c, c->wpre.ensure((size_t)(c->nwords + 1) * 4));
     const int blocks = (int)std::min<i64>((c->nwords + 7) / 8, (i64)c->sm_count * 16);
-    k_wetmask<<<blocks > 0 ? blocks : 1, 256, 0, c->stream>>>(c->v3D.as<double>(), c->M, c->mask.as<u64>(),
-                                                              c->wcount.as<uint32_t>(), c->nwords);
+    k_wetmask<<<blocks > 0 ? blocks : 1, 256, 0, c->stream>>>(c->win<double>(c->v3D), c->L_win0, c->L_win1, c->mask_win(),
+                                                              c->wcount.as<uint32_t>() - word0, word0, word1);
     LAUNCHED(c);
     CU_TRY(c, cudaGetLastError());
     OT_TRY(otmb_reset_flags(c));
@@ -322,8 +340,8 @@ int otmb_makeindices(otmb_ctx* c, const double* v3D, int64_t* N) {
     c->w0 = 0;
     if (c->sharded) {
         i64 below_own = 0, below_end = 0;
-        OT_TRY(wet_below(c, c->k_own0 * c->P, &below_own));
-        OT_TRY(wet_below(c, c->k_own1 * c->P, &below_end));
+        OT_TRY(wet_below(c, c->L_own0, &below_own));
+        OT_TRY(wet_below(c, c->L_own1, &below_end));
         c->h_up = below_own;
         c->ncols = below_end - below_own;
         c->have_rank_offset = false;   // global ranks need otmb_set_rank_offset (sum of the lower ranks' counts)

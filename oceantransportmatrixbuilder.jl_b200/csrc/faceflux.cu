@@ -20,12 +20,16 @@ __global__ void __launch_bounds__(128) k_faceflux(const double* __restrict__ umo
                                                   double* __restrict__ east, double* __restrict__ west,
                                                   double* __restrict__ north, double* __restrict__ south,
                                                   double* __restrict__ top, double* __restrict__ bottom,
-                                                  DevFlags* __restrict__ flags, int k_begin, int k_end,
+                                                  DevFlags* __restrict__ flags, int row0, int row1, int p_begin, int p_end,
                                                   const double* __restrict__ carry_in, double* __restrict__ carry_out) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    // (all 3-D pointers are window-biased and indexed by the global linear cell index; the kernel covers the columns
+    // [p_begin, p_end) of the plane — one chunk of the pipelined carry chain — and, per column, the owned levels)
+    const int p = p_begin + blockIdx.x * blockDim.x + threadIdx.x;
     bool valid_u = false, valid_v = false;
-    if (p < g.P) {
+    if (p < p_end) {
         const int i = p % g.nx, j = p / g.nx;
+        // owned levels of this column: the grid rows R = j + ny*k inside [row0, row1)
+        const int k_begin = (row0 - j + g.ny - 1) / g.ny, k_end = (row1 - j + g.ny - 1) / g.ny;
         const int pE = i < g.nx - 1 ? p + 1 : p - (g.nx - 1);
         const int pW = i > 0 ? p - 1 : p + (g.nx - 1);
         const int pS = j > 0 ? p - g.nx : -1;
@@ -33,7 +37,8 @@ __global__ void __launch_bounds__(128) k_faceflux(const double* __restrict__ umo
         const int pN = j < g.ny - 1 ? p + g.nx : (g.topo == OTMB_TOPO_TRIPOLAR ? (g.nx - 1 - i) + g.nx * (g.ny - 1) : -1);
         // phi_top of the level below: 0 under the sea floor, or the plane handed up by the slab below
         double carry = carry_in ? carry_in[p] : 0.0;
-        if (carry_in && k_end < g.nz) top[(size_t)k_end * g.P + p] = carry;   // halo level: the top flux of the cell below
+        const bool owns = k_begin < k_end;
+        if (owns && carry_in && k_end < g.nz) top[(size_t)k_end * g.P + p] = carry;   // halo cell below: its top flux
         for (int k0 = k_end - 1; k0 >= k_begin; k0 -= UNROLL) {
             double e[UNROLL], w[UNROLL], n[UNROLL], s[UNROLL];
 #pragma unroll
@@ -76,8 +81,8 @@ __global__ void __launch_bounds__(128) k_faceflux(const double* __restrict__ umo
                 carry = t;
             }
         }
-        if (carry_out) carry_out[p] = carry;                                  // phi_top of the slab's first level
-        if (k_begin > 0) bottom[(size_t)(k_begin - 1) * g.P + p] = carry;     // halo level: the bottom flux of the cell above
+        if (carry_out) carry_out[p] = carry;   // phi_top of the column's first owned level (a column that owns nothing passes it on)
+        if (owns && k_begin > 0) bottom[(size_t)(k_begin - 1) * g.P + p] = carry;   // halo cell above: its bottom flux
     }
     const unsigned bu = __ballot_sync(0xffffffffu, valid_u), bv = __ballot_sync(0xffffffffu, valid_v);
     if ((threadIdx.x & 31) == 0) {
@@ -86,7 +91,75 @@ __global__ void __launch_bounds__(128) k_faceflux(const double* __restrict__ umo
     }
 }
 
+// A slab cut inside a level: the assembly of the first / last owned grid row reads the north-face flux of the row
+// before it and the south-face flux of the row after it (its south / north neighbours, same level, owned by the
+// adjacent rank).  Both are pure functions of the inputs (vmo + mask, src/velocities.jl:169-174, :213-221), which the
+// window holds, so they are recomputed here instead of exchanged.
+__global__ void __launch_bounds__(128) k_faceflux_halo_rows(const double* __restrict__ vmo, const u64* __restrict__ mask,
+                                                            GridDims g, double fill, double* __restrict__ north,
+                                                            double* __restrict__ south, int row_before, int row_after) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.nx) return;
+    if (row_before >= 0) {   // north[L] of the cells of that row; its north neighbour (j+1 < ny) is owned
+        const size_t L = (size_t)row_before * g.nx + i;
+        const double vn = (wet_at(mask, (int)L) && wet_at(mask, (int)L + g.nx)) ? __ldg(vmo + L) : 0.0;
+        north[L] = clean(vn, fill);
+    }
+    if (row_after >= 0) {    // south[L] = north flux of the cell to the south (owned), masked by both cells
+        const size_t L = (size_t)row_after * g.nx + i;
+        const double vs = (wet_at(mask, (int)L - g.nx) && wet_at(mask, (int)L)) ? __ldg(vmo + L - g.nx) : 0.0;
+        south[L] = clean(vs, fill);
+    }
+}
+
 }  // namespace
+
+// ---- internal pieces shared with the NCCL-chained driver (comm.cu) ---------------------------------------------
+// window-sized ϕ buffers, flags reset, halo rows of a mid-level cut
+int otmb_faceflux_begin(otmb_ctx* c, double fill) {
+    for (int q = 0; q < 6; ++q) CU_TRY(c, c->phi[q].ensure(c->win_cells() * 8));
+    OT_TRY(otmb_reset_flags(c));
+    const i64 rows = c->ny * c->nz, row0 = c->L_own0 / c->nx, row1 = c->L_own1 / c->nx;
+    const int before = (row0 > 0 && row0 % c->ny != 0) ? (int)(row0 - 1) : -1;
+    const int after = (row1 < rows && row1 % c->ny != 0) ? (int)row1 : -1;
+    if (before >= 0 || after >= 0) {
+        GridDims g{(int)c->nx, (int)c->ny, (int)c->nz, c->topo, (int)c->P, (int)c->M};
+        k_faceflux_halo_rows<<<grid_for(c->nx, 128), 128, 0, c->stream>>>(c->win<double>(c->stage_b), c->mask_win(), g, fill,
+                                                                          c->win<double>(c->phi[OTMB_FACE_NORTH]),
+                                                                          c->win<double>(c->phi[OTMB_FACE_SOUTH]), before, after);
+        LAUNCHED(c);
+        CU_TRY(c, cudaGetLastError());
+    }
+    return OTMB_OK;
+}
+// the columns [p_begin, p_end) of the plane; d_in / d_out are device planes of nx*ny doubles (or null)
+int otmb_faceflux_columns(otmb_ctx* c, double fill, i64 p_begin, i64 p_end, const double* d_in, double* d_out) {
+    if (p_end <= p_begin) return OTMB_OK;
+    GridDims g{(int)c->nx, (int)c->ny, (int)c->nz, c->topo, (int)c->P, (int)c->M};
+    k_faceflux<5><<<grid_for(p_end - p_begin, 128), 128, 0, c->stream>>>(
+        c->win<double>(c->stage_a), c->win<double>(c->stage_b), c->mask_win(), g, fill,
+        c->win<double>(c->phi[OTMB_FACE_EAST]), c->win<double>(c->phi[OTMB_FACE_WEST]), c->win<double>(c->phi[OTMB_FACE_NORTH]),
+        c->win<double>(c->phi[OTMB_FACE_SOUTH]), c->win<double>(c->phi[OTMB_FACE_TOP]), c->win<double>(c->phi[OTMB_FACE_BOTTOM]),
+        c->flags.as<DevFlags>(), (int)(c->L_own0 / c->nx), (int)(c->L_own1 / c->nx), (int)p_begin, (int)p_end, d_in, d_out);
+    LAUNCHED(c);
+    CU_TRY(c, cudaGetLastError());
+    return OTMB_OK;
+}
+// copy the owned part of the six results into the caller's full-size arrays (any may be null)
+int otmb_faceflux_copy_out(otmb_ctx* c, double* const outs[6]) {
+    const size_t n = (size_t)(c->L_own1 - c->L_own0);
+    for (int q = 0; q < 6; ++q)
+        if (outs[q])
+            CU_TRY(c, cudaMemcpyAsync(outs[q] + c->L_own0, c->win<double>(c->phi[q]) + c->L_own0, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    return OTMB_OK;
+}
+int otmb_upload_uv(otmb_ctx* c, const double* umo, const double* vmo, double fill) {
+    OT_TRY(otmb_upload3d(c, c->stage_a, umo));
+    OT_TRY(otmb_upload3d(c, c->stage_b, vmo));
+    c->have_uv = true;
+    c->uv_fill = fill;
+    return OTMB_OK;
+}
 
 static int facefluxes_impl(otmb_ctx* c, const double* umo, const double* vmo, double fill, const double* carry_in,
                            double* carry_out, int carry_on_device, int32_t* valid_uv, double* const outs[6]) {
@@ -94,10 +167,8 @@ static int facefluxes_impl(otmb_ctx* c, const double* umo, const double* vmo, do
     OT_TRY(otmb_need(c, c->have_indices, "otmb_makeindices"));
     if (c->topo == OTMB_TOPO_UNKNOWN) return otmb_fail(c, OTMB_ERR_UNKNOWN_GRID, otmb_status_string(OTMB_ERR_UNKNOWN_GRID));
     CU_TRY(c, cudaSetDevice(c->device));
-    const size_t M8 = (size_t)c->M * 8, P8 = (size_t)c->P * 8;
-    OT_TRY(otmb_upload3d(c, c->stage_a, umo));
-    OT_TRY(otmb_upload3d(c, c->stage_b, vmo));
-    for (int q = 0; q < 6; ++q) CU_TRY(c, c->phi[q].ensure(M8));
+    const size_t P8 = (size_t)c->P * 8;
+    OT_TRY(otmb_upload_uv(c, umo, vmo, fill));
     // carry planes: device pointers are used in place (e.g. buffers an NCCL send/recv works on)
     const double* d_in = nullptr;
     double* d_out = nullptr;
@@ -118,15 +189,8 @@ static int facefluxes_impl(otmb_ctx* c, const double* umo, const double* vmo, do
             d_out = c->carry[1].as<double>();
         }
     }
-    OT_TRY(otmb_reset_flags(c));
-    GridDims g{(int)c->nx, (int)c->ny, (int)c->nz, c->topo, (int)c->P, (int)c->M};
-    k_faceflux<5><<<grid_for(c->P, 128), 128, 0, c->stream>>>(
-        c->stage_a.as<double>(), c->stage_b.as<double>(), c->mask.as<u64>(), g, fill,
-        c->phi[OTMB_FACE_EAST].as<double>(), c->phi[OTMB_FACE_WEST].as<double>(), c->phi[OTMB_FACE_NORTH].as<double>(),
-        c->phi[OTMB_FACE_SOUTH].as<double>(), c->phi[OTMB_FACE_TOP].as<double>(), c->phi[OTMB_FACE_BOTTOM].as<double>(),
-        c->flags.as<DevFlags>(), (int)c->k_own0, (int)c->k_own1, d_in, d_out);
-    LAUNCHED(c);
-    CU_TRY(c, cudaGetLastError());
+    OT_TRY(otmb_faceflux_begin(c, fill));
+    OT_TRY(otmb_faceflux_columns(c, fill, 0, c->P, d_in, d_out));
     OT_TRY(otmb_fetch_flags(c));
     if (valid_uv) {
         // a slab only sees its own levels: the caller combines the flags of all ranks (src/velocities.jl:199-200)
@@ -137,11 +201,7 @@ static int facefluxes_impl(otmb_ctx* c, const double* umo, const double* vmo, do
         return otmb_fail(c, OTMB_ERR_ALL_FILL, otmb_status_string(OTMB_ERR_ALL_FILL));
     }
     if (carry_out && !carry_on_device) CU_TRY(c, cudaMemcpyAsync(carry_out, d_out, P8, cudaMemcpyDeviceToHost, c->stream));
-    // results: the owned levels, written into the caller's full-size arrays
-    const size_t a = (size_t)c->k_own0 * c->P, b = (size_t)c->k_own1 * c->P;
-    for (int q = 0; q < 6; ++q)
-        if (outs[q])
-            CU_TRY(c, cudaMemcpyAsync(outs[q] + a, c->phi[q].as<double>() + a, (b - a) * 8, cudaMemcpyDeviceToHost, c->stream));
+    OT_TRY(otmb_faceflux_copy_out(c, outs));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     c->have_phi = true;
     return OTMB_OK;

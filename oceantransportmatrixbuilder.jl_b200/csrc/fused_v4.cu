@@ -897,20 +897,21 @@ int otmb_fused_v4_build(otmb_ctx* c, const otmb_tm_params* prm, int build) {
     P.g = GridDims{(int)c->nx, (int)c->ny, (int)c->nz, c->topo, (int)c->P, (int)c->M};
     P.divP = make_fastdiv((unsigned)c->P);
     P.divNx = make_fastdiv((unsigned)c->nx);
-    P.v3D = c->v3D.as<double>();
-    P.thk = c->thk.as<double>();
+    // 3-D arrays: window-biased pointers, indexed by the global linear cell index (common.cuh)
+    P.v3D = c->win<double>(c->v3D);
+    P.thk = c->win<double>(c->thk);
     P.area2D = c->area2D.as<double>();
     P.zt = c->zt.as<double>();
     P.edge = c->edge.as<double>();
     P.dnbr = c->dnbr.as<double>();
     P.mlotst = c->mlotst.as<double>();
-    P.rho3d = c->have_rho3d ? c->rho3d.as<double>() : nullptr;
-    P.pe = c->phi[OTMB_FACE_EAST].as<double>();
-    P.pw = c->phi[OTMB_FACE_WEST].as<double>();
-    P.pn = c->phi[OTMB_FACE_NORTH].as<double>();
-    P.ps = c->phi[OTMB_FACE_SOUTH].as<double>();
-    P.pt = c->phi[OTMB_FACE_TOP].as<double>();
-    P.pb = c->phi[OTMB_FACE_BOTTOM].as<double>();
+    P.rho3d = c->have_rho3d ? c->win<double>(c->rho3d) : nullptr;
+    P.pe = c->win<double>(c->phi[OTMB_FACE_EAST]);
+    P.pw = c->win<double>(c->phi[OTMB_FACE_WEST]);
+    P.pn = c->win<double>(c->phi[OTMB_FACE_NORTH]);
+    P.ps = c->win<double>(c->phi[OTMB_FACE_SOUTH]);
+    P.pt = c->win<double>(c->phi[OTMB_FACE_TOP]);
+    P.pb = c->win<double>(c->phi[OTMB_FACE_BOTTOM]);
     P.phi_nb[cT] = P.pb;
     P.phi_nb[cS] = P.pn;
     P.phi_nb[cW] = P.pe;
@@ -919,7 +920,7 @@ int otmb_fused_v4_build(otmb_ctx* c, const otmb_tm_params* prm, int build) {
     P.phi_nb[cN] = P.ps;
     P.phi_nb[cB] = P.pt;
     P.phi_nb[7] = P.pn;
-    P.rank3d = c->rank3d.as<int>();
+    P.rank3d = c->win<int>(c->rank3d);
     P.lwet = c->lwet.as<int>() + c->h_up;   // the owned cells (all wet cells when unsharded)
     P.kH = prm->kH;
     P.kVML = prm->kVML;

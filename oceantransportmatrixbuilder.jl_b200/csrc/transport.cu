@@ -81,7 +81,7 @@ int otmb_transportmatrix_build(otmb_ctx* c, const otmb_tm_params* prm, int64_t n
     // the fused kernel dereferences every input; give unused ones a valid dummy
     if (!c->have_mlotst) CU_TRY(c, c->mlotst.ensure((size_t)c->P * 8));
     if (!c->have_phi)
-        for (int q = 0; q < 6; ++q) CU_TRY(c, c->phi[q].ensure((size_t)c->M * 8));
+        for (int q = 0; q < 6; ++q) CU_TRY(c, c->phi[q].ensure(c->win_cells() * 8));
     for (int m = 1; m <= 4; ++m)
         if ((ops >> m & 1)) c->preset[m] = false;
     if (c->preset[1] || c->preset[2] || c->preset[3] || c->preset[4]) {

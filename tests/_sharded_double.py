@@ -10,43 +10,53 @@ NAMES = {"T": "T", "Tadv": "Tadv", "TκH": "TkH", "TκVML": "TkVML", "TκVdeep":
 
 
 class OracleSlab:
-    def __init__(self, shape, topology, k0, k1, device=0):
-        self.shape, self.topology, self.k0, self.k1 = shape, topology, k0, k1
+    def __init__(self, shape, topology, row0, row1, device=0):
+        self.shape, self.topology, self.rows = shape, topology, (row0, row1)
+        nx, ny, nz = shape
+        self.L0, self.L1 = row0 * nx, row1 * nx          # owned linear cells
         self.phi = None
         self.log = []
 
     def makeindices(self, v3D):
         self.v3D = np.asfortranarray(v3D)
-        wet = ~np.isnan(self.v3D)
-        self.n_owned = int(wet[:, :, self.k0:self.k1].sum())
-        self.h_up = int(wet[:, :, self.k0 - 1].sum()) if self.k0 > 0 else 0
-        self.below = int(wet[:, :, :self.k0].sum())
+        wet = ~np.isnan(self.v3D.ravel(order="F"))
+        P = self.shape[0] * self.shape[1]
+        self.n_owned = int(wet[self.L0:self.L1].sum())
+        self.h_up = int(wet[max(0, self.L0 - P):self.L0].sum())
+        self.below = int(wet[:self.L0].sum())
         return self.n_owned, self.h_up
 
     def set_rank_offset(self, w0):
-        assert w0 == self.below, "global wet-rank offset must equal the wet cells of the lower levels"
+        assert w0 == self.below, "global wet-rank offset must equal the wet cells before the slab"
         self.w0 = w0
 
     def set_metrics(self, gm):
         self.gm = gm
 
     def facefluxes(self, umo, vmo, fill, carry_in, carry_out, outputs=None):
-        nz = self.shape[2]
+        from otmb_b200.sharded import column_levels
+        nx, ny, nz = self.shape
         full = O.facefluxes(umo, vmo, self.v3D, self.topology, fill)
-        if self.k1 < nz:
+        kb, ke = column_levels(self.rows, ny)                    # owned levels per j
+        top = np.concatenate([full["top"], np.zeros((nx, ny, 1))], axis=2)      # level nz: 0 under the sea floor
+        jj = np.arange(ny)
+        if self.L1 < nx * ny * nz:
             assert carry_in is not None
-            got = np.asarray(carry_in[3]).reshape(self.shape[:2], order="F")
-            assert np.array_equal(got.view(np.int64), full["top"][:, :, self.k1].view(np.int64)), "carry from the slab below"
+            got = np.asarray(carry_in[3]).reshape(nx, ny, order="F")
+            want = top[:, jj, ke]                                 # ϕtop of the cell below the last owned one
+            assert np.array_equal(got.view(np.int64), want.view(np.int64)), "carry from the slab below"
         else:
             assert carry_in is None
-        if self.k0 > 0:
-            carry_out[3][...] = full["top"][:, :, self.k0].ravel(order="F")
+        if self.L0 > 0:
+            carry_out[3][...] = top[:, jj, kb].ravel(order="F")   # ϕtop of the first owned level (passed on if none)
         else:
             assert carry_out is None
         self.phi = full
-        sl = (slice(None), slice(None), slice(self.k0, self.k1))
-        vu = bool((~(np.isnan(umo[sl]) | (umo[sl] == fill))).any())
-        vv = bool((~(np.isnan(vmo[sl]) | (vmo[sl] == fill))).any())
+        own = np.zeros(nx * ny * nz, bool)
+        own[self.L0:self.L1] = True
+        own = own.reshape(self.shape, order="F")
+        vu = bool((~(np.isnan(umo) | (umo == fill)) & own).any())
+        vv = bool((~(np.isnan(vmo) | (vmo == fill)) & own).any())
         return vu, vv
 
     def set_facefluxes(self, phi):

@@ -11,6 +11,8 @@ import numpy as np
 import pytest
 
 import otmb_b200  # noqa: F401
+import otmb_b200.api as A
+from otmb_b200 import _lib as _L
 from otmb_b200 import sharded, synthetic
 from oracle import oracle as O
 
@@ -22,19 +24,42 @@ ROOT = Path(__file__).resolve().parent.parent
 
 def test_plan_slabs_properties():
     rng = np.random.default_rng(0)
-    for nz in (1, 2, 5, 20, 50):
-        wet = rng.integers(0, 1000, nz)
-        for R in range(1, min(nz, 9) + 1):
-            slabs = sharded.plan_slabs(wet, R)
-            assert len(slabs) == R and slabs[0][0] == 0 and slabs[-1][1] == nz
-            assert all(a < b for a, b in slabs) and all(slabs[r][1] == slabs[r + 1][0] for r in range(R - 1))
-    # balanced on a surface-heavy profile (upper levels are wetter, like a real ocean)
-    wet = np.linspace(1000, 100, 50).astype(int)
-    slabs = sharded.plan_slabs(wet, 8)
-    per = [wet[a:b].sum() for a, b in slabs]
-    assert max(per) / (sum(per) / 8) < 1.25
-    with pytest.raises(ValueError):
-        sharded.plan_slabs([1, 2], 3)
+    for nx, ny, nz in ((5, 4, 1), (7, 3, 2), (6, 5, 5), (9, 4, 20)):
+        v = np.asfortranarray(np.where(rng.random((nx, ny, nz)) < 0.6, 1.0, np.nan))
+        wet_rows = (~np.isnan(v)).sum(axis=0).ravel(order="F")            # wet cells per grid row R = j + ny*k
+        for levels in (False, True):
+            units = nz if levels else ny * nz
+            for R in range(1, min(units, 9) + 1):
+                slabs, wet = sharded.plan_slabs(v, R, level_cuts_only=levels)
+                assert len(slabs) == R and slabs[0][0] == 0 and slabs[-1][1] == ny * nz
+                assert all(a < b for a, b in slabs) and all(slabs[r][1] == slabs[r + 1][0] for r in range(R - 1))
+                assert wet == [int(wet_rows[a:b].sum()) for a, b in slabs] and sum(wet) == int(wet_rows.sum())
+                if levels:
+                    assert all(a % ny == 0 and b % ny == 0 for a, b in slabs)
+            with pytest.raises(ValueError):
+                sharded.plan_slabs(v, units + 1, level_cuts_only=levels)
+    # a realistic mask: row cuts balance to within one grid row, level cuts are much coarser
+    oc = synthetic.make_ocean(90, 45, 20, "tripolar", seed=1)
+    v = O.clean_missing(oc.volcello)
+    nx = v.shape[0]
+    for R in (2, 4, 8):
+        _, wet = sharded.plan_slabs(v, R)
+        assert max(abs(w - sum(wet) / R) for w in wet) <= nx
+        _, wet_lv = sharded.plan_slabs(v, R, level_cuts_only=True)
+        assert max(wet_lv) >= max(wet)
+
+
+def test_column_levels_tile_the_grid():
+    ny, nz = 7, 5
+    cuts = [0, 3, 9, 10, 24, 35]
+    seen = np.zeros((ny, nz), int)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        kb, ke = sharded.column_levels((a, b), ny)
+        for j in range(ny):
+            for k in range(kb[j], ke[j]):
+                assert a <= j + ny * k < b
+                seen[j, k] += 1
+    assert (seen == 1).all()
 
 
 def _run_double(oc, R, **kw):
@@ -44,15 +69,18 @@ def _run_double(oc, R, **kw):
     return sharded.run_threaded(R, fn)
 
 
+@pytest.mark.parametrize("levels", [False, True])
 @pytest.mark.parametrize("R", [1, 2, 3, 5])
-def test_sharded_host_logic_threads(R):
+def test_sharded_host_logic_threads(R, levels):
     oc = synthetic.make_ocean(12, 10, 6, "tripolar", seed=0, land_frac=0.25)
     o = oracle_pipeline(oc)
-    res = _run_double(oc, R)
+    res = _run_double(oc, R, level_cuts_only=levels)
     full, segs, info = res[0]
     assert all(r[0] is None for r in res[1:])
     for oname, gname in {v: k for k, v in NAMES.items()}.items():
         assert_csc_equal(getattr(full, gname), o["tm"][oname], f"R={R} {oname}", exact=True)
+    if not levels and R > 1:
+        assert any(a % 10 for a, _ in info["slabs"]), "row cuts should fall inside a level on this mask"
     # segments tile the column range and carry global entry offsets
     col = 0
     for r in range(R):
@@ -80,10 +108,13 @@ def test_sharded_gloo_world_size_2():
 
 # ------------------------------------------------------------------------------------------ CUDA slab path
 @pytest.mark.gpu
-@pytest.mark.parametrize("R", [2, 3])
+@pytest.mark.parametrize("levels", [False, True])
+@pytest.mark.parametrize("R", [2, 3, 7])
 @pytest.mark.parametrize("case", [(12, 10, 6, "tripolar", 0), (10, 8, 4, "bipolar", 3), (90, 45, 20, "tripolar", 5)])
-def test_sharded_cuda_slabs_match_oracle(case, R):
+def test_sharded_cuda_slabs_match_oracle(case, R, levels):
     nx, ny, nz, topo, seed = case
+    if levels and R > nz:
+        pytest.skip("more ranks than levels")
     oc = synthetic.make_ocean(nx, ny, nz, topo, seed=seed, land_frac=0.25)
     o = oracle_pipeline(oc)
     gm = oracle_gridmetrics(oc)
@@ -91,7 +122,7 @@ def test_sharded_cuda_slabs_match_oracle(case, R):
         want = O.transportmatrix(o["phi"], oc.mlotst, o["v3D"], o["gm"]["thkcello"], o["area"], oc.lev, o["gm"]["edge"],
                                  o["gm"]["dnbr"], o["topo"], rho, upwind=upwind)
         fn = lambda ex: sharded.transportmatrix_sharded(exchange=ex, gridmetrics=gm, mlotst=oc.mlotst, ρ=rho, umo=oc.umo,
-                                                        vmo=oc.vmo, FillValue=oc.fill, upwind=upwind)
+                                                        vmo=oc.vmo, FillValue=oc.fill, upwind=upwind, level_cuts_only=levels)
         full, segs, info = sharded.run_threaded(R, fn)[0]
         assert info["N"] == o["ix"]["N"]
         for gname, oname in NAMES.items():
@@ -159,3 +190,75 @@ def test_large_grid_sharded_equals_unsharded_and_invariants():
         a, b = getattr(tm, name), getattr(full, name)
         assert np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices), name
         assert np.array_equal(a.data.view(np.int64), b.data.view(np.int64)), name
+
+
+# ------------------------------------------------------------------------------------------ errors are collective
+class _FailingSlab(OracleSlab):
+    """Test double whose rank-local step raises on ONE rank (the slab that owns grid row `bad_row`)."""
+    bad_row, where = 0, "build"
+
+    def _mine(self):
+        return self.rows[0] <= self.bad_row < self.rows[1]
+
+    def facefluxes(self, *a, **kw):
+        if self.where == "fluxes" and self._mine():
+            raise A.OTMBError(_L.ERR_CUDA, "injected failure in facefluxes")
+        if self.where == "fluxes":           # the plane from the failed rank below is a dummy: do not check it
+            return True, True
+        return super().facefluxes(*a, **kw)
+
+    def transportmatrix(self, *a, **kw):
+        if self.where == "build" and self._mine():
+            raise A.OTMBError(_L.ERR_TADV_NAN, "Tadv contains NaNs.")
+        return super().transportmatrix(*a, **kw)
+
+
+@pytest.mark.parametrize("where,bad_row,code", [("build", 0, 1), ("build", 59, 1), ("fluxes", 59, 100), ("fluxes", 30, 100)])
+def test_rank_local_errors_are_raised_on_every_rank(where, bad_row, code):
+    """One slab fails (NaN check, CUDA error): no rank may be left blocking in the next collective or in the
+    carry chain's recv — every rank raises, the failing one its own error, the others one that names it."""
+    oc = synthetic.make_ocean(12, 10, 6, "tripolar", seed=0, land_frac=0.25)
+    gm = oracle_gridmetrics(oc)
+    factory = type("F", (_FailingSlab,), dict(bad_row=bad_row, where=where))
+    raised = []
+
+    def fn(ex):
+        try:
+            sharded.transportmatrix_sharded(exchange=ex, gridmetrics=gm, mlotst=oc.mlotst, ρ=1035.0, umo=oc.umo, vmo=oc.vmo,
+                                            FillValue=oc.fill, slab_factory=factory)
+        except A.OTMBError as e:
+            raised.append((ex.rank, e.code, str(e)))
+            return "raised"
+        return "completed"
+
+    assert sharded.run_threaded(3, fn) == ["raised"] * 3
+    assert sorted(r for r, _, _ in raised) == [0, 1, 2] and {c for _, c, _ in raised} == {code}
+    assert sum("rank " in m for _, _, m in raised) == 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nchunks", [1, 3, 8])
+def test_native_driver_single_rank_and_chunked_columns(nchunks):
+    """The in-library sharded driver (csrc/comm.cu) with one rank (no NCCL is loaded): makeindices, the face-flux
+    kernel launched over column chunks of the plane — the unit the carry chain pipelines — and the assembly must
+    reproduce the oracle bit for bit, whatever the number of chunks."""
+    oc = synthetic.make_ocean(37, 11, 7, "tripolar", seed=6, land_frac=0.25, dirty=True)
+    o = oracle_pipeline(oc)
+    gm = oracle_gridmetrics(oc)
+    ns = sharded.NativeSharded(gridmetrics=gm, rank=0, nranks=1, id_bytes=None)
+    assert (ns.N, ns.w0) == (o["ix"]["N"], 0)
+    ns.set_masstransport(oc.umo, oc.vmo, oc.fill)
+    outs = [np.full(gm.v3D.shape, np.nan, order="F") for _ in range(6)]
+    ns.facefluxes(nchunks, outs)
+    for k, a in zip(A.FACES, outs):
+        assert np.array_equal(a.view(np.int64), o["phi"][k].view(np.int64)), k
+    ns.build(oc.mlotst, 1035.0)
+    assert ns.nnz_before == [0] * 5 and ns.nnz_total == ns.slab.nnz
+    segs = ns.segments()
+    for gname, oname in NAMES.items():
+        sgm = segs[gname]
+        assert_csc_equal(A._csc(ns.N, sgm.colptr, sgm.rowval, sgm.nzval), o["tm"][oname], oname, exact=True)
+    # the device-resident form of the chain (what a per-month pipeline enqueues) gives the same matrix
+    ns.facefluxes_enqueue(nchunks)
+    assert ns.build(oc.mlotst, 1035.0, upload=False) == ns.nnz_total
+    ns.close()
