@@ -240,6 +240,19 @@ int otmb_triad_derivative(otmb_ctx* ctx, const double* chi, int dir, double* out
 int otmb_dyad_derivative(otmb_ctx* ctx, const double* chi, double* out);
 int otmb_bolus_gm_velocity(otmb_ctx* ctx, const double* rho, double kGM, double maxslope, double* u, double* v);
 
+/* BASELINE configs[2] ("C3"): the Gent-McWilliams bolus transport folded into the advective mass fluxes — an
+ * EXTENSION (parity unpinned: the reference has bolus_GM_velocity, src/RediGM.jl:46-79, and velocity2fluxes,
+ * src/velocities.jl:10-39, but no wiring between them and no Redi/GM option of transportmatrix).  On the device:
+ *   (u*, v*) = bolus_GM_velocity(rho3d; kGM, maxslope);  (ϕᵢ*, ϕⱼ*) = velocity2fluxes(u*, v*, gridmetrics, ρ)
+ *   ϕ = facefluxes(umo + ϕᵢ*, vmo + ϕⱼ*)   (a NaN bolus flux adds nothing; fill / NaN transports stay as they are)
+ * and ϕ stays resident for otmb_transportmatrix_build, whose 7-point pattern is unchanged.  ρ of velocity2fluxes:
+ * rho3d itself (flux_rho_is_3d != 0) or rho_scalar.  kGM = 0 reproduces otmb_facefluxes bit for bit.  Needs the
+ * resident Z3D, lon, lat, thkcello, edge lengths (otmb_gridmetrics); tripolar grids only.  The six outputs and the
+ * bolus fluxes gm_phi_i / gm_phi_j (nx,ny,nz) may be NULL. */
+int otmb_facefluxes_gm(otmb_ctx* ctx, const double* umo, const double* vmo, double fill_value, const double* rho3d,
+                       double kGM, double maxslope, double rho_scalar, int32_t flux_rho_is_3d, double* east, double* west,
+                       double* north, double* south, double* top, double* bottom, double* gm_phi_i, double* gm_phi_j);
+
 /* velocity <-> mass flux on the C-grid, needs the resident thkcello / edge lengths:
  * velocity2fluxes src/velocities.jl:10-39 (ϕᵢ = u·ρ̄·min(thk)·edge_east, ϕⱼ = v·ρ̄·min(thk)·edge_north, NaN-aware
  * two-cell mean / min :81-108), fluxes2velocity :50-74 (the inverse).  All arrays (nx,ny,nz); rho3d may be

@@ -590,6 +590,32 @@ def bolus_GM_velocity(ρ, gridmetrics, indices, *, κGM=600, maxslope=0.01, ctx=
     return u, v
 
 
+def facefluxes_GM(*, umo, vmo, gridmetrics, indices, ρ, κGM=600, maxslope=0.01, ρ_flux=None, return_bolus_fluxes=False, ctx=None):
+    """BASELINE configs[2] ("C3") — an EXTENSION, the reference has no such function (parity unpinned): face fluxes of
+    the mass transport plus the Gent-McWilliams bolus transport,
+        ϕ = facefluxes(umo + ϕᵢ*, vmo + ϕⱼ*),  (ϕᵢ*, ϕⱼ*) = velocity2fluxes(bolus_GM_velocity(ρ; κGM, maxslope)..., ρ_flux)
+    (src/RediGM.jl:46-79, src/velocities.jl:10-39, :190-255), chained on the device.  `ρ` is the 3-D density the
+    slopes are taken of; `ρ_flux` the density of velocity2fluxes (None: the same 3-D field; or a scalar).  The result
+    goes into transportmatrix like any ϕ; T keeps its 7-point pattern.  κGM = 0 gives facefluxesfrommasstransport."""
+    fill = umo.properties["_FillValue"]
+    fv = vmo.properties["_FillValue"]
+    assert (fill == fv) or (fill != fill and fv != fv), "AssertionError: isequal(FillValue, vmo.properties[\"_FillValue\"])"
+    ctx = _ctx_of(gridmetrics.v3D, ctx=ctx)
+    _ensure_z(ctx, gridmetrics)
+    u, v, rho = _f64(_data(umo)), _f64(_data(vmo)), _f64(_data(ρ))
+    shape = gridmetrics.v3D.shape
+    out = [ctx.pinned_empty(gridmetrics.v3D.size, np.float64, shape, "F") for _ in range(6)]
+    gi = np.empty(shape, order="F") if return_bolus_fluxes else None
+    gj = np.empty(shape, order="F") if return_bolus_fluxes else None
+    ctx.check(ctx.lib.otmb_facefluxes_gm(ctx.h, _ptr(u), _ptr(v), float(fill), _ptr(rho), float(κGM), float(maxslope),
+                                         0.0 if ρ_flux is None else float(ρ_flux), int(ρ_flux is None),
+                                         *[_ptr(o) for o in out], _ptr(gi), _ptr(gj)))
+    _freeze(*out)
+    phi = FaceFluxes(*out)
+    ctx.resident["phi_arrays"] = tuple(out)
+    return (phi, gi, gj) if return_bolus_fluxes else phi
+
+
 # ---- bare sparse helpers (SparseArrays.sparse / +), exposed for parity tests ------------------
 def sparse(I, J, V, n, ctx=None):
     ctx = ctx or default_context()

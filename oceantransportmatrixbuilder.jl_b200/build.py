@@ -11,7 +11,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 INCLUDE = HERE.parent / "include"
 LIB = HERE / "libotmb.so"
-SOURCES = ["ctx.cu", "scan.cu", "geometry.cu", "faceflux.cu", "fused.cu", "fused_v4.cu", "coo.cu", "transport.cu", "redigm.cu", "velocity.cu", "lump.cu", "spmv.cu", "fetch.cu", "comm.cu"]
+SOURCES = ["ctx.cu", "scan.cu", "geometry.cu", "faceflux.cu", "fused.cu", "fused_v4.cu", "coo.cu", "transport.cu", "redigm.cu", "velocity.cu", "lump.cu", "spmv.cu", "fetch.cu", "comm.cu", "gm.cu"]
 HEADERS = ["common.cuh", "sphere.cuh", "fused_generic.cuh"]
 
 NVCC_FLAGS = [

@@ -115,6 +115,22 @@ int dyad_dev(otmb_ctx* c, const double* dchi, double* dout) {
 
 }  // namespace
 
+// bolus_GM_velocity on DEVICE buffers (all of M doubles): d_si / d_sj are scratch for the two slope fields, d_u / d_v
+// the results.  The caller resets / reads the flag block (err_dry_neighbour: a triad group needs a neighbour that
+// does not exist, where the reference throws).
+int otmb_bolus_gm_dev(otmb_ctx* c, const double* d_rho, double kGM, double maxslope, double* d_si, double* d_sj, double* d_u,
+                      double* d_v) {
+    OT_TRY(triad_dev(c, d_rho, 0, d_si));
+    OT_TRY(triad_dev(c, d_rho, 1, d_sj));
+    k_gm_taper<<<grid_for(c->M, 256), 256, 0, c->stream>>>(d_si, d_sj, (int)c->M, kGM, maxslope);
+    LAUNCHED(c);
+    CU_TRY(c, cudaGetLastError());
+    OT_TRY(dyad_dev(c, d_si, d_u));
+    OT_TRY(dyad_dev(c, d_sj, d_v));
+    return OTMB_OK;
+}
+int otmb_redigm_prereq(otmb_ctx* c) { return prereq(c); }
+
 extern "C" {
 
 int otmb_triad_derivative(otmb_ctx* c, const double* chi, int dir, double* out) {

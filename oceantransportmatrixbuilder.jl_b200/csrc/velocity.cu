@@ -96,6 +96,17 @@ int run_velflux(otmb_ctx* c, int mode, const double* a_i, const double* a_j, con
 
 }  // namespace
 
+// velocity2fluxes on DEVICE buffers (src/velocities.jl:10-39); d_rho3d may be null (scalar rho)
+int otmb_velocity2fluxes_dev(otmb_ctx* c, const double* d_u, const double* d_v, const double* d_rho3d, double rho, double* d_phi_i,
+                             double* d_phi_j) {
+    GridDims g{(int)c->nx, (int)c->ny, (int)c->nz, c->topo, (int)c->P, (int)c->M};
+    k_velflux<0><<<grid_for(c->M, 256), 256, 0, c->stream>>>(d_u, d_v, d_rho3d, rho, c->thk.as<double>(), c->edge.as<double>(), g,
+                                                              d_phi_i, d_phi_j);
+    LAUNCHED(c);
+    CU_TRY(c, cudaGetLastError());
+    return OTMB_OK;
+}
+
 extern "C" {
 
 int otmb_velocity2fluxes(otmb_ctx* c, const double* u, const double* v, const double* rho3d, double rho, double* phi_i,

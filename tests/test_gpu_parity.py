@@ -473,3 +473,57 @@ def test_failed_build_invalidates_earlier_results(ctx):
     with pytest.raises(A.OTMBError) as e:
         A.resident_matvec("T", np.ones(g["ix"].N), ctx=c)
     assert e.value.code == otmb_b200._lib.ERR_STATE
+
+
+# ------------------------------------------------------------------------------------------ C3: GM bolus -> T (extension)
+@pytest.mark.parametrize("cfg", ["C1t", "C2"])
+def test_c3_gm_bolus_transport_matrix(cfg):
+    """BASELINE configs[2]: bolus_GM_velocity -> velocity2fluxes -> + umo/vmo -> facefluxes -> transportmatrix, on the
+    device (csrc/gm.cu).  The reference has the pieces, not the chain (parity unpinned), so the checks are: κGM = 0
+    reproduces the plain path bit for bit; the chain agrees with the oracle's composition of the same pieces; T given
+    the GPU's ϕ is the oracle's T bit for bit; pattern stays 7-point; mass is conserved (vᵀT = 0) and T·1 vanishes
+    below the surface level (the continuity scan closes every cell but the skipped surface face)."""
+    from oracle import gm_np
+    oc = synthetic.make_config(cfg, seed=3)
+    f = fields(oc)
+    gm = otmb_b200.makegridmetrics(areacello=f["areacello"], volcello=f["volcello"], lon=f["lon"], lat=f["lat"], lev=f["lev"],
+                                   lon_vertices=f["lon_vertices"], lat_vertices=f["lat_vertices"])
+    ix = otmb_b200.makeindices(gm.v3D)
+    plain = otmb_b200.facefluxesfrommasstransport(umo=f["umo"], vmo=f["vmo"], gridmetrics=gm, indices=ix)
+    plain = {k: np.array(getattr(plain, k)) for k in A.FACES}
+    # (1) κGM = 0: the bolus fluxes are exact zeros
+    phi0 = otmb_b200.facefluxes_GM(umo=f["umo"], vmo=f["vmo"], gridmetrics=gm, indices=ix, ρ=oc.rho3d, κGM=0.0)
+    for k in A.FACES:
+        assert np.array_equal(getattr(phi0, k) + 0.0, plain[k] + 0.0), k          # (+0.0: -0.0 and 0.0 are the same flux)
+    # (2) against the oracle's composition, with the GPU's own geometry as input on both sides
+    phi, gi, gj = otmb_b200.facefluxes_GM(umo=f["umo"], vmo=f["vmo"], gridmetrics=gm, indices=ix, ρ=oc.rho3d, κGM=600.0,
+                                          return_bolus_fluxes=True)
+    edge = np.asfortranarray(np.stack([gm.edge_length_2D[d] for d in A.DIRS], axis=-1))
+    dnbr = np.asfortranarray(np.stack([gm.distance_to_neighbour_2D[d] for d in A.DIRS], axis=-1))
+    um, vm, gi_o, gj_o = gm_np.total_transport(oc.umo, oc.vmo, oc.fill, oc.rho3d, gm.lon, gm.lat, gm.Z3D, gm.v3D, gm.thkcello,
+                                               edge, oc.topology)
+    scale = max(np.nanmax(np.abs(gi_o)), np.nanmax(np.abs(gj_o)))
+    assert scale > 0 and np.array_equal(np.isnan(gi), np.isnan(gi_o)) and np.array_equal(np.isnan(gj), np.isnan(gj_o))
+    # 1e-12 relative, plus 1e-12 of the field's scale: where the taper 1 + tanh(..) cancels to ~0 the VALUE is
+    # negligible but its last bits depend on the tanh implementation (CUDA vs glibc; Julia's is a third one)
+    np.testing.assert_allclose(gi, gi_o, rtol=1e-12, atol=1e-12 * scale, equal_nan=True)
+    np.testing.assert_allclose(gj, gj_o, rtol=1e-12, atol=1e-12 * scale, equal_nan=True)
+    want = O.facefluxes(um, vm, gm.v3D, oc.topology, oc.fill)
+    fscale = max(np.abs(want[k]).max() for k in A.FACES)
+    for k in A.FACES:
+        np.testing.assert_allclose(getattr(phi, k), want[k], rtol=0, atol=1e-12 * fscale, err_msg=k)
+    assert any(not np.array_equal(getattr(phi, k), plain[k]) for k in ("east", "north", "top"))
+    # (3) T from the GPU's ϕ: the oracle's matrix, bit for bit; 7-point pattern; invariants
+    tm = otmb_b200.transportmatrix(ϕ=phi, mlotst=oc.mlotst, gridmetrics=gm, indices=ix, ρ=1035.0)
+    ot = O.transportmatrix({k: np.asarray(getattr(phi, k)) for k in A.FACES}, oc.mlotst, gm.v3D, gm.thkcello, gm.area2D, oc.lev,
+                           edge, dnbr, oc.topology, 1035.0)
+    for oname, gname in NAMES.items():
+        assert_csc_equal(getattr(tm, gname), ot[oname], f"C3 {oname}", exact=True)
+    T = tm.T
+    assert np.diff(T.indptr).max() <= 7
+    v = gm.v3D.ravel(order="F")
+    v = v[~np.isnan(v)]
+    assert np.abs(T.T @ v).max() <= 1e-9 * np.abs(T.diagonal() * v).max()
+    surface = (ix.Lwet - 1) < gm.v3D.shape[0] * gm.v3D.shape[1]
+    r = np.abs(tm.Tadv @ np.ones(ix.N))
+    assert r[~surface].max() <= 1e-9 * np.abs(tm.Tadv.diagonal()).max()
