@@ -213,6 +213,18 @@ int otmb_transportmatrix_fetch(otmb_ctx* ctx, int which, int64_t* colptr, int64_
  * spare, copy the 8-byte arrays as they are.  Both calls return identical arrays. */
 int otmb_transportmatrix_fetch_all(otmb_ctx* ctx, int mask, int64_t* const colptr[5], int64_t* const rowval[5],
                                    double* const nzval[5]);
+/* transportmatrix end to end in ONE call — host ϕ (six arrays, order OTMB_FACE_*), mlotst and optionally a 3-D ρ in,
+ * the five host CSC matrices out — pipelined by level slabs: the upload of slab s+1, the assembly of slab s and the
+ * copy-out of slab s-1 overlap, so the two directions of the PCIe link are busy at once (a set_facefluxes -> build ->
+ * fetch_all sequence runs them back to back).  nslabs: 0 = default.  The nnz are data dependent: the caller passes
+ * rowval / nzval arrays holding capacity[m] entries (N x {7,7,5,3,3} always suffices) and colptr arrays of N+1, and
+ * receives nnz_out; the matrices are the first nnz entries (Julia: resize!).  Results are bit-identical to
+ * otmb_transportmatrix_build + fetch, and stay resident like theirs.  Page-locked arrays (otmb_host_alloc) move at
+ * link rate; pageable result arrays are filled through pinned staging by the host threads. */
+int otmb_transportmatrix_stream(otmb_ctx* ctx, const otmb_tm_params* params, const double* const phi[6],
+                                const double* mlotst, const double* rho3d, int32_t nslabs, const int64_t capacity[5],
+                                int64_t* const colptr[5], int64_t* const rowval[5], double* const nzval[5],
+                                int64_t nnz_out[5]);
 /* host half of that pipeline alone (no GPU needed): sign-extend n Int32 indices into Int64 on `threads` pool
  * threads (0 = the calling thread). */
 int otmb_host_widen(const int32_t* src, int64_t* dst, int64_t n, int32_t threads);

@@ -328,6 +328,27 @@ def facefluxes(umo, vmo, gridmetrics, indices, *, FillValue, ctx=None) -> FaceFl
     return phi
 
 
+def _transportmatrix_stream(ctx, N, phi, mlotst, ρ, κH, κVML, κVdeep, upwind, nslabs=0, pageable=False, caps=None):
+    """otmb_transportmatrix_stream: result arrays sized by the upper bound N x {7,7,5,3,3} (page-locked, pooled), the
+    matrices are views of their first nnz entries."""
+    lib = ctx.lib
+    ml = _data(mlotst)
+    ml = _f64(np.ma.filled(ml.astype(np.float64), np.nan) if np.ma.isMaskedArray(ml) else ml)
+    rho3 = None if np.isscalar(ρ) else _f64(_data(ρ))
+    prm = _L.TMParams(float(κH), float(κVML), float(κVdeep), float(ρ) if np.isscalar(ρ) else 0.0, int(bool(upwind)), 0,
+                      _L.PATH["fused"], 0)
+    caps = caps or [N * w for w in (7, 7, 5, 3, 3)]
+    new = (lambda n, dt: np.empty(max(int(n), 1), dt)) if pageable else ctx.pinned_empty
+    arrays = [(new(N + 1, np.int64), new(caps[m], np.int64), new(caps[m], np.float64)) for m in range(5)]
+    ptrs = [(C.c_void_p * 5)(*[_ptr(arrays[m][q]).value for m in range(5)]) for q in range(3)]
+    phi_ptrs = (C.c_void_p * 6)(*[a.ctypes.data for a in phi])
+    nnz = (C.c_int64 * 5)()
+    ctx.check(lib.otmb_transportmatrix_stream(ctx.h, C.byref(prm), phi_ptrs, _ptr(ml), _ptr(rho3), int(nslabs),
+                                              (C.c_int64 * 5)(*caps), *ptrs, nnz))
+    ctx.resident["phi_arrays"] = None
+    return TransportMatrices(*[_csc(N, arrays[m][0], arrays[m][1][:nnz[m]], arrays[m][2][:nnz[m]]) for m in range(5)])
+
+
 def _metric_dicts_same(a, b):
     return a is b and all(isinstance(v, np.ndarray) and not v.flags.writeable for v in b.values())
 
@@ -362,11 +383,15 @@ def transportmatrix(*, ϕ, mlotst, gridmetrics, indices, ρ, κH=500.0, κVML=0.
         ctx.resident["metrics_src"] = None          # caller-owned arrays: never assumed unchanged
     preset = {1: Tadv, 2: TκH, 3: TκVML, 4: TκVdeep}
     mask = 32 | sum(1 << m for m, v in preset.items() if v is None)   # bit 5: the mask is explicit
+    get = (lambda k: ϕ[k]) if isinstance(ϕ, dict) else (lambda k: getattr(ϕ, k))
+    res = ctx.resident.get("phi_arrays")
+    phi_resident = res is not None and all(_same_frozen(get(k), b) for k, b in zip(FACES, res))
+    if path == "fused" and all(v is None for v in preset.values()) and not phi_resident and N > 0:
+        # caller-owned ϕ and all four operators to build: upload, assembly and copy-out overlap inside ONE call
+        return _transportmatrix_stream(ctx, N, [_f64(get(k)) for k in FACES], mlotst, ρ, κH, κVML, κVdeep, upwind)
     if mask & 2:
-        get = (lambda k: ϕ[k]) if isinstance(ϕ, dict) else (lambda k: getattr(ϕ, k))
         arrs = tuple(get(k) for k in FACES)
-        res = ctx.resident.get("phi_arrays")
-        if not (res is not None and all(_same_frozen(a, b) for a, b in zip(arrs, res))):
+        if not phi_resident:
             arrs = tuple(_f64(a) for a in arrs)
             ptrs = (C.c_void_p * 6)(*[a.ctypes.data for a in arrs])
             ctx.check(lib.otmb_set_facefluxes(ctx.h, ptrs))

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "otmb.h"
 
@@ -46,7 +47,7 @@ struct DevFlags {
     int any_valid_u, any_valid_v;
     int generic_columns;   // columns that took the coincidence (generic) branch
     int zero_dropped;      // an exactly-zero T entry was stored and must be compacted away
-    unsigned tiles_done;   // k_fused_v4: tiles that have finished (the last one publishes the host record)
+    unsigned spare;
     int lookback_timeout;  // k_fused_v4: a look-back spun past its bound (diagnostic instead of a hang)
     int pad[4];
     u64 nnz[5];
@@ -109,8 +110,11 @@ struct otmb_ctx {
         u64 pad[7];
         DevFlags snap;
     };
-    HostDone* h_done = nullptr;
+    static constexpr int DONE_RING = 64;   // launches whose records may be unread at once (slab-pipelined builds)
+    HostDone* h_done = nullptr;   // DONE_RING records; launch `serial` uses record serial % DONE_RING
     HostDone* d_done = nullptr;   // device alias of h_done
+    DevBuf run_nnz;               // 5 running entry totals on the device: chained slab launches of one build
+    std::vector<long long> level_cum;   // wet cells above level k (nz+1 entries), cached per makeindices (slab plans)
     bool flags_clean = false;     // the device flag block is known to be all zero (k_fused_v4 re-zeroes it itself)
     u64 v4_serial = 0;            // launches of k_fused_v4 on this context (epoch of the look-back descriptors)
     size_t ts_zeroed = 0;         // bytes of tile_state known to hold no descriptor of a conflicting epoch
@@ -204,7 +208,13 @@ int otmb_scan_u32_to_i64(otmb_ctx* ctx, const uint32_t* in, i64* out, i64 n, u64
 int otmb_need(otmb_ctx* ctx, bool cond, const char* what);
 int otmb_upload3d(otmb_ctx* ctx, DevBuf& buf, const double* host);   // whole (nx,ny,nz) array, or only the slab window
 int otmb_fused_build(otmb_ctx* ctx, const otmb_tm_params* prm, int mask, bool two_pass);
-int otmb_fused_v4_build(otmb_ctx* ctx, const otmb_tm_params* prm, int mask);
+// columns [col0, col0 + ncols) of the context's owned columns (ncols < 0: all of them).  chain: 0 = a build of its
+// own; 1 = first launch of a chained build (running entry totals start at zero), 2 = continues the chain: the
+// launch's entries follow those of the launches before it (slab-pipelined builds, stream.cu)
+int otmb_fused_v4_build(otmb_ctx* ctx, const otmb_tm_params* prm, int mask, i64 col0 = 0, i64 ncols = -1, int chain = 0);
+int otmb_v4_publish(otmb_ctx* ctx);   // enqueue the completion record of the last k_fused_v4 launch
+int otmb_wait_v4(otmb_ctx* ctx, u64 serial, bool block);   // 0 = done (flags in h_flags), -1 = not yet (block == false)
+int otmb_check_build_flags(otmb_ctx* ctx, int ops);
 int otmb_drop_zeros(otmb_ctx* ctx, int m, int base);
 int otmb_coo_build(otmb_ctx* ctx, const otmb_tm_params* prm, int mask);
 int otmb_sum_operators(otmb_ctx* ctx, int base);

@@ -179,14 +179,15 @@ int otmb_create(otmb_ctx** out, int device) {
         cudaEventCreate(&c->ev_b0) != cudaSuccess || cudaEventCreate(&c->ev_b1) != cudaSuccess ||
         c->flags.ensure(sizeof(DevFlags)) != cudaSuccess ||
         cudaMallocHost((void**)&c->h_flags, sizeof(DevFlags)) != cudaSuccess ||
-        cudaHostAlloc((void**)&c->h_done, sizeof(otmb_ctx::HostDone), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostAlloc((void**)&c->h_done, sizeof(otmb_ctx::HostDone) * otmb_ctx::DONE_RING, cudaHostAllocMapped) != cudaSuccess ||
+        c->run_nnz.ensure(64) != cudaSuccess ||
         cudaHostGetDevicePointer((void**)&c->d_done, c->h_done, 0) != cudaSuccess) {
         cudaGetLastError();
         delete c;
         return OTMB_ERR_CUDA;
     }
     cudaMemset(c->flags.p, 0, sizeof(DevFlags));
-    memset(c->h_done, 0, sizeof(otmb_ctx::HostDone));
+    memset(c->h_done, 0, sizeof(otmb_ctx::HostDone) * otmb_ctx::DONE_RING);
     c->flags_clean = true;
     *out = c;
     return OTMB_OK;
@@ -198,6 +199,7 @@ int otmb_destroy(otmb_ctx* c) {
     cudaStreamSynchronize(c->stream);
     otmb_comm_release(c);
     c->comm_buf.release();
+    c->run_nnz.release();
     DevBuf* bufs[] = {&c->v3D, &c->mask, &c->wcount, &c->wpre, &c->lwet, &c->rank3d, &c->area2D, &c->thk, &c->Z3D, &c->zt, &c->edge, &c->dnbr,
                       &c->dedge, &c->lon, &c->lat, &c->lonv, &c->latv, &c->mlotst, &c->rho3d, &c->stage_a, &c->stage_b,
                       &c->flags, &c->tile_state, &c->scan_tmp, &c->sp_colptr, &c->sp_rowval, &c->sp_nzval, &c->l2};
@@ -350,6 +352,7 @@ int otmb_makeindices(otmb_ctx* c, const double* v3D, int64_t* N) {
         OT_TRY(fill_ranks(c));
     }
     c->have_indices = true;
+    c->level_cum.clear();
     for (int q = 0; q < 5; ++q) c->have_mat[q] = c->preset[q] = false;
     if (N) *N = c->N;
     return OTMB_OK;

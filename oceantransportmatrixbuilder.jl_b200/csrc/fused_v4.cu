@@ -88,9 +88,9 @@ struct V4Params {
     double* nzval[5];
     DevFlags* flags;
     u64* tile_state;
+    const u64* start;                // 5 entry totals of the launches before this one (chained slab launches), or null
+    u64* run_out;                    // where the last tile leaves the totals including this launch, or null
     unsigned epoch;                  // look-back epoch of this launch (serial mod 2^20)
-    u64 serial;                      // stored to host_done->seq by the last tile
-    otmb_ctx::HostDone* host_done;   // mapped pinned memory
     long long* timeline;   // TLINE instantiation only (OTMB_V4_TIMELINE): 64 stamps per tile, see profiles/timeline.py
 };
 
@@ -130,7 +130,6 @@ struct Smem {
     u64 lexcl[TILE];               // in-warp exclusive offsets of the column, five 12-bit fields
     u64 warp[TILE / 32];           // entries of each warp, five 12-bit fields
     u64 excl[5];
-    int done;                      // warps of this block that have finished
 };
 
 // ---------------------------------------------------------------------------------------
@@ -146,29 +145,6 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int tile = blockIdx.x;
-    if (tid == 0) S.done = 0;   // ordered before every use by barrier 1 (this warp arrives after it)
-    // ---- completion.  Every warp ends here; the last warp of the last tile to finish copies the flag block and the
-    // five nnz into the host-mapped record, re-zeroes the device block for the next launch and stores the launch's
-    // serial number: the host polls that word instead of issuing a copy and a stream synchronise per build.
-    auto finish = [&]() {
-        __syncwarp();
-        if (lane != 0) return;
-        __threadfence();
-        if (atomicAdd(&S.done, 1) != NW) return;
-        __threadfence();
-        if (atomicAdd(&P.flags->tiles_done, 1u) != (unsigned)(P.ntiles - 1)) return;
-        __threadfence();
-        volatile int* src = reinterpret_cast<volatile int*>(P.flags);
-        volatile int* dst = reinterpret_cast<volatile int*>(&P.host_done->snap);
-        constexpr int NI = (int)(sizeof(DevFlags) / sizeof(int));
-#pragma unroll 1
-        for (int q = 0; q < NI; ++q) {
-            dst[q] = src[q];
-            src[q] = 0;
-        }
-        __threadfence_system();
-        *reinterpret_cast<volatile u64*>(&P.host_done->seq) = P.serial;
-    };
     // timeline instrumentation (debug instantiation): SM clock stamps of one tile's phases
     long long* const tl = TLINE ? P.timeline + (size_t)tile * 64 : nullptr;
     // (a clock read right behind BAR.SYNC.DEFER_BLOCKING issues before the barrier resolves: stamps behind a barrier
@@ -209,7 +185,9 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
             if (lane == m) agg_m = tot;
         }
         const unsigned tagA = (1u << 20) | P.epoch, tagP = (2u << 20) | P.epoch;   // the descriptor's top 22 bits
-        if (lane < 5) st_vol(P.tile_state + (size_t)tile * 8 + lane, ((u64)(tile == 0 ? tagP : tagA) << ST_SHIFT) | (u64)agg_m);
+        // entries of earlier launches of the same build (slab-pipelined builds): the first tile's exclusive prefix
+        const u64 first = (tile == 0 && P.start != nullptr && lane < 5) ? P.start[lane] : 0ull;
+        if (lane < 5) st_vol(P.tile_state + (size_t)tile * 8 + lane, ((u64)(tile == 0 ? tagP : tagA) << ST_SHIFT) | (first + (u64)agg_m));
         stamp(3);
         int rounds = 0;
         u64 excl[5] = {0, 0, 0, 0, 0};
@@ -277,13 +255,14 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
         }
         stamp(4);
         if (TLINE && lane == 0) tl[5] = rounds;
-        const u64 mine = lane == 0 ? excl[0] : lane == 1 ? excl[1] : lane == 2 ? excl[2] : lane == 3 ? excl[3] : excl[4];
+        const u64 mine = first + (lane == 0 ? excl[0] : lane == 1 ? excl[1] : lane == 2 ? excl[2] : lane == 3 ? excl[3] : excl[4]);
         if (lane < 5) {
             const u64 agg = agg_m;
             if (tile > 0) st_vol(P.tile_state + (size_t)tile * 8 + lane, ((u64)tagP << ST_SHIFT) | (mine + agg));
             S.excl[lane] = mine;
             if (tile == P.ntiles - 1) {
                 P.flags->nnz[lane] = mine + agg;
+                if (P.run_out) P.run_out[lane] = mine + agg;
                 if (P.build >> lane & 1) P.colptr[lane][P.ncols] = (i64)(mine + agg) + P.base;
             }
         }
@@ -296,7 +275,6 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
             const int members = (gq + 1) * BG <= NW ? BG : NW - gq * BG;
             asm volatile("bar.arrive %0, %1;" ::"r"(2 + gq), "r"(32 * members + 32) : "memory");
         }
-        finish();
         return;
     }
     const GridDims g = P.g;
@@ -812,7 +790,24 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
             }
         }
     }
-    finish();
+}
+
+// Completion record.  Launched behind k_fused_v4 on the same stream, so every tile has finished and every flag is in
+// place: copy the flag block and the five nnz into the host-mapped record of this launch, re-zero the device block
+// for the next launch, then store the launch's serial number — the word the host polls (transport.cu, otmb_wait_v4)
+// instead of issuing a copy and a stream synchronise per build.
+__global__ void __launch_bounds__(32) k_publish(DevFlags* __restrict__ flags, otmb_ctx::HostDone* __restrict__ rec, u64 serial) {
+    constexpr int NI = (int)(sizeof(DevFlags) / sizeof(int));
+    static_assert(NI <= 32, "one warp copies the flag block");
+    int* src = reinterpret_cast<int*>(flags);
+    volatile int* dst = reinterpret_cast<volatile int*>(&rec->snap);
+    if (threadIdx.x < NI) {
+        dst[threadIdx.x] = src[threadIdx.x];
+        src[threadIdx.x] = 0;
+    }
+    __threadfence_system();
+    __syncwarp();
+    if (threadIdx.x == 0) *reinterpret_cast<volatile u64*>(&rec->seq) = serial;
 }
 
 FastDiv make_fastdiv(unsigned d) {
@@ -833,7 +828,6 @@ int launch_v4(otmb_ctx* c, V4Params& P) {
     const size_t ts_bytes = (size_t)ntiles * 8 * sizeof(u64);
     c->v4_serial++;
     P.epoch = (unsigned)(c->v4_serial % ST_EPOCHS);
-    P.serial = c->v4_serial;
     if (ts_bytes > c->tile_state.cap || !c->tile_state.p) c->ts_zeroed = 0;
     CU_TRY(c, c->tile_state.ensure(ts_bytes));
     if (P.epoch == 0) c->ts_zeroed = 0;
@@ -842,7 +836,6 @@ int launch_v4(otmb_ctx* c, V4Params& P) {
         c->ts_zeroed = c->tile_state.cap;
     }
     P.tile_state = c->tile_state.as<u64>();
-    P.host_done = c->d_done;
     DevBuf tline;
     if (TLINE) {
         CU_TRY(c, tline.ensure((size_t)ntiles * 64 * 8));
@@ -892,8 +885,18 @@ int launch_v4(otmb_ctx* c, V4Params& P) {
 
 }  // namespace
 
-int otmb_fused_v4_build(otmb_ctx* c, const otmb_tm_params* prm, int build) {
+int otmb_v4_publish(otmb_ctx* c) {
+    k_publish<<<1, 32, 0, c->stream>>>(c->flags.as<DevFlags>(), c->d_done + (c->v4_serial % otmb_ctx::DONE_RING), c->v4_serial);
+    LAUNCHED(c);
+    CU_TRY(c, cudaGetLastError());
+    return OTMB_OK;
+}
+
+int otmb_fused_v4_build(otmb_ctx* c, const otmb_tm_params* prm, int build, i64 col0, i64 ncols, int chain) {
+    if (ncols < 0) ncols = c->ncols - col0;
     V4Params P;
+    P.start = chain == 2 ? c->run_nnz.as<u64>() : nullptr;
+    P.run_out = chain ? c->run_nnz.as<u64>() : nullptr;
     P.g = GridDims{(int)c->nx, (int)c->ny, (int)c->nz, c->topo, (int)c->P, (int)c->M};
     P.divP = make_fastdiv((unsigned)c->P);
     P.divNx = make_fastdiv((unsigned)c->nx);
@@ -921,7 +924,7 @@ int otmb_fused_v4_build(otmb_ctx* c, const otmb_tm_params* prm, int build) {
     P.phi_nb[cB] = P.pt;
     P.phi_nb[7] = P.pn;
     P.rank3d = c->win<int>(c->rank3d);
-    P.lwet = c->lwet.as<int>() + c->h_up;   // the owned cells (all wet cells when unsharded)
+    P.lwet = c->lwet.as<int>() + c->h_up + col0;   // the owned cells (all wet cells when unsharded), from column col0
     P.kH = prm->kH;
     P.kVML = prm->kVML;
     P.kVdeep = prm->kVdeep;
@@ -933,8 +936,8 @@ int otmb_fused_v4_build(otmb_ctx* c, const otmb_tm_params* prm, int build) {
 #ifdef OTMB_AB
     if (getenv("OTMB_V4_NOPREFETCH")) P.prefetch = 0;
 #endif
-    P.w0 = (int)c->w0;
-    P.ncols = (int)c->ncols;
+    P.w0 = (int)(c->w0 + col0);
+    P.ncols = (int)ncols;
     P.flags = c->flags.as<DevFlags>();
     const int cap_per_col[5] = {7, 7, 5, 3, 3};
     for (int m = 0; m < 5; ++m) {
@@ -946,7 +949,7 @@ int otmb_fused_v4_build(otmb_ctx* c, const otmb_tm_params* prm, int build) {
         CU_TRY(c, c->colptr[m].ensure((size_t)(c->ncols + 1) * 8));
         CU_TRY(c, c->rowval[m].ensure(cap * 8));
         CU_TRY(c, c->nzval[m].ensure(cap * 8));
-        P.colptr[m] = c->colptr[m].as<i64>();
+        P.colptr[m] = c->colptr[m].as<i64>() + col0;
         P.rowval[m] = c->rowval[m].as<i64>();
         P.nzval[m] = c->nzval[m].as<double>();
     }

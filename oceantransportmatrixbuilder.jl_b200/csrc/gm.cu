@@ -12,7 +12,8 @@
 // exact zeros and the result is bit-identical to the plain path.  The sum is defined here (no reference arithmetic
 // exists for it): a valid umo / vmo value gets the bolus flux added when that is not NaN (u* is NaN where a triad or
 // dyad has no valid neighbour); fill / NaN values of umo / vmo stay as they are, so nofluxboundaries! and the
-// all-fill assertion see the same cells as without GM.
+// all-fill assertion see the same cells as without GM; on the tripolar fold row the two cells that share a north
+// face average their estimates of its flux antisymmetrically (k_add_gm), which keeps the transport non-divergent.
 #include "common.cuh"
 
 int otmb_bolus_gm_dev(otmb_ctx* c, const double* d_rho, double kGM, double maxslope, double* d_si, double* d_sj, double* d_u,
@@ -24,10 +25,22 @@ int otmb_velocity2fluxes_dev(otmb_ctx* c, const double* d_u, const double* d_v, 
 namespace {
 
 __global__ void __launch_bounds__(256) k_add_gm(double* __restrict__ umo, double* __restrict__ vmo, const double* __restrict__ gi,
-                                                const double* __restrict__ gj, double fill, i64 M) {
-    const i64 L = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (L >= M) return;
-    const double u = umo[L], v = vmo[L], a = gi[L], b = gj[L];
+                                                const double* __restrict__ gj, double fill, GridDims g) {
+    const int L = blockIdx.x * blockDim.x + threadIdx.x;
+    if (L >= g.M) return;
+    const double u = umo[L], v = vmo[L], a = gi[L];
+    double b = gj[L];
+    // The north face of (i, ny) IS the north face of its fold partner (nx-i+1, ny) (src/gridtopology.jl:94-95), seen with
+    // the opposite sign, and facefluxes carries no fold term (src/velocities.jl:219-221): the two cells' estimates of
+    // that one flux are averaged antisymmetrically, (b - b')/2 (the one that is not NaN when the other is), so that
+    // what leaves one cell enters the other.
+    const int p = L % g.P, j = p / g.nx;
+    if (j == g.ny - 1) {
+        const int i = p - j * g.nx;
+        const double bm = gj[L + (g.nx - 1 - 2 * i)];
+        const bool wa = !isnan(b), wb = !isnan(bm);
+        b = ((wa ? b : 0.0) - (wb ? bm : 0.0)) / (double)((int)wa + (int)wb);
+    }
     if (!(isnan(u) || u == fill) && !isnan(a)) umo[L] = u + a;
     if (!(isnan(v) || v == fill) && !isnan(b)) vmo[L] = v + b;
 }
@@ -55,8 +68,9 @@ extern "C" int otmb_facefluxes_gm(otmb_ctx* c, const double* umo, const double* 
                              b[4].as<double>()));
     OT_TRY(otmb_velocity2fluxes_dev(c, b[3].as<double>(), b[4].as<double>(), flux_rho_is_3d ? b[0].as<double>() : nullptr, rho_scalar,
                                     b[5].as<double>(), b[6].as<double>()));
+    GridDims g{(int)c->nx, (int)c->ny, (int)c->nz, c->topo, (int)c->P, (int)c->M};
     k_add_gm<<<grid_for(c->M, 256), 256, 0, c->stream>>>(c->stage_a.as<double>(), c->stage_b.as<double>(), b[5].as<double>(),
-                                                         b[6].as<double>(), fill, c->M);
+                                                         b[6].as<double>(), fill, g);
     LAUNCHED(c);
     CU_TRY(c, cudaGetLastError());
     OT_TRY(otmb_fetch_flags(c));

@@ -28,23 +28,26 @@ int check_flags(otmb_ctx* c, int build) {
 // k_fused_v4 publishes its flag block and the five nnz in mapped pinned memory and then the launch's serial
 // number (fused_v4.cu, `finish`): poll that word.  After a while the stream is queried as well, which is what
 // surfaces a faulted kernel; a kernel that ended without publishing is an error, not a hang.
-int wait_v4(otmb_ctx* c) {
-    const u64 want = c->v4_serial;
+}  // namespace
+
+int otmb_wait_v4(otmb_ctx* c, u64 want, bool block) {
+    volatile otmb_ctx::HostDone* const rec = c->h_done + (want % otmb_ctx::DONE_RING);
     const auto t0 = std::chrono::steady_clock::now();
     for (unsigned it = 1;; ++it) {
-        if (c->h_done->seq == want) break;
+        if (rec->seq == want) break;
+        if (!block) return -1;
         _mm_pause();
         if ((it & 255u) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(300)) {
             const cudaError_t e = cudaStreamQuery(c->stream);
             if (e == cudaSuccess) {
-                if (c->h_done->seq == want) break;
+                if (rec->seq == want) break;
                 return otmb_fail(c, OTMB_ERR_CUDA, "assembly kernel ended without publishing its completion record");
             }
             if (e != cudaErrorNotReady) CU_TRY(c, e);
         }
     }
     std::atomic_thread_fence(std::memory_order_acquire);
-    memcpy(c->h_flags, (const void*)&c->h_done->snap, sizeof(DevFlags));
+    memcpy(c->h_flags, (const void*)&rec->snap, sizeof(DevFlags));
     c->flags_clean = true;   // the kernel re-zeroed the device block
     if (c->h_flags->lookback_timeout) {
         c->ts_zeroed = 0;
@@ -53,7 +56,7 @@ int wait_v4(otmb_ctx* c) {
     return OTMB_OK;
 }
 
-}  // namespace
+int otmb_check_build_flags(otmb_ctx* c, int ops) { return check_flags(c, ops); }
 
 extern "C" {
 
@@ -128,8 +131,10 @@ int otmb_transportmatrix_build(otmb_ctx* c, const otmb_tm_params* prm, int64_t n
         st = v4 ? otmb_fused_v4_build(c, prm, build) : otmb_fused_build(c, prm, build, true);
         if (st != OTMB_OK) return st;
         CU_TRY(c, cudaEventRecord(c->ev_b1, c->stream));
-        if (v4)
-            OT_TRY(wait_v4(c));
+        if (v4) {
+            OT_TRY(otmb_v4_publish(c));
+            OT_TRY(otmb_wait_v4(c, c->v4_serial, true));
+        }
         else
             OT_TRY(otmb_fetch_flags(c));
         OT_TRY(check_flags(c, ops));

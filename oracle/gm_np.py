@@ -17,6 +17,13 @@ def total_transport(umo, vmo, fill, rho3d, lon, lat, Z3D, v3D, thk, edge, topolo
     """(umo', vmo', ϕᵢ*, ϕⱼ*): the transports facefluxes is given, and the bolus fluxes on their own."""
     u, v = O.bolus_gm(rho3d, lon, lat, Z3D, v3D, topology, kGM=kGM, maxslope=maxslope)
     gi, gj = V.velocity2fluxes(u, v, thk, edge, rho3d if rho_flux is None else rho_flux, topology)
+    # the fold row: one face, two estimates of opposite sign -> antisymmetric NaN-aware mean (csrc/gm.cu, k_add_gm)
+    a, b = gj[:, -1, :], gj[::-1, -1, :]
+    wa, wb = ~np.isnan(a), ~np.isnan(b)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        fold = (np.where(wa, a, 0.0) - np.where(wb, b, 0.0)) / (wa.astype(np.float64) + wb.astype(np.float64))
+    gj = np.array(gj, order="F")
+    gj[:, -1, :] = fold
     ok_u = ~(np.isnan(umo) | (umo == fill)) & ~np.isnan(gi)
     ok_v = ~(np.isnan(vmo) | (vmo == fill)) & ~np.isnan(gj)
     with np.errstate(invalid="ignore"):

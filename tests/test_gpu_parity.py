@@ -503,6 +503,8 @@ def test_c3_gm_bolus_transport_matrix(cfg):
     um, vm, gi_o, gj_o = gm_np.total_transport(oc.umo, oc.vmo, oc.fill, oc.rho3d, gm.lon, gm.lat, gm.Z3D, gm.v3D, gm.thkcello,
                                                edge, oc.topology)
     scale = max(np.nanmax(np.abs(gi_o)), np.nanmax(np.abs(gj_o)))
+    # (the library returns velocity2fluxes' own output; the oracle's has the fold row averaged already: compare below it)
+    gj, gj_o = gj[:, :-1], gj_o[:, :-1]
     assert scale > 0 and np.array_equal(np.isnan(gi), np.isnan(gi_o)) and np.array_equal(np.isnan(gj), np.isnan(gj_o))
     # 1e-12 relative, plus 1e-12 of the field's scale: where the taper 1 + tanh(..) cancels to ~0 the VALUE is
     # negligible but its last bits depend on the tanh implementation (CUDA vs glibc; Julia's is a third one)
@@ -527,3 +529,52 @@ def test_c3_gm_bolus_transport_matrix(cfg):
     surface = (ix.Lwet - 1) < gm.v3D.shape[0] * gm.v3D.shape[1]
     r = np.abs(tm.Tadv @ np.ones(ix.N))
     assert r[~surface].max() <= 1e-9 * np.abs(tm.Tadv.diagonal()).max()
+
+
+# ------------------------------------------------------------------------------------------ slab-pipelined end-to-end call
+@pytest.mark.parametrize("pageable", [False, True])
+@pytest.mark.parametrize("nslabs", [0, 1, 2, 7, 20])
+def test_stream_call_equals_build_and_fetch(nslabs, pageable):
+    """otmb_transportmatrix_stream (upload, chained slab launches and copy-out overlapped in one call) returns the very
+    arrays of set_facefluxes -> build -> fetch_all, for any number of slabs, into page-locked and pageable arrays."""
+    oc = synthetic.make_config("C1t", seed=6)
+    o = oracle_pipeline(oc)
+    g = gpu_pipeline(oc)                              # ϕ resident: the build + fetch path
+    c = A._ctx_of(g["gm"].v3D)
+    for rho, upwind in ((1035.0, True), (np.array(oc.rho3d, order="F"), False)):
+        want = otmb_b200.transportmatrix(ϕ=g["phi"], mlotst=oc.mlotst, gridmetrics=g["gm"], indices=g["ix"], ρ=rho, upwind=upwind)
+        phi = [np.array(getattr(g["phi"], k), order="F") for k in A.FACES]
+        got = A._transportmatrix_stream(c, g["ix"].N, phi, oc.mlotst, rho, 500.0, 0.1, 1e-5, upwind, nslabs=nslabs, pageable=pageable)
+        for name in A.MATRICES:
+            a, b = getattr(got, name), getattr(want, name)
+            assert np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices), name
+            assert np.array_equal(bits(a.data), bits(b.data)), name
+        # ... and stay resident like theirs
+        y = A.resident_matvec("T", np.ones(g["ix"].N), ctx=c)
+        assert np.array_equal(bits(y), bits(A.resident_matvec("T", np.ones(g["ix"].N), ctx=c)))
+
+
+def test_stream_call_zero_dropping_errors_and_capacity():
+    oc = synthetic.make_config("C1t", seed=2)
+    o = oracle_pipeline(oc)
+    # κ = 0: T's exact zeros are dropped (src/matrixbuilding.jl:147) — the stream call compacts and re-sends T
+    want = O.transportmatrix(o["phi"], oc.mlotst, o["v3D"], o["gm"]["thkcello"], o["area"], oc.lev, o["gm"]["edge"], o["gm"]["dnbr"],
+                             o["topo"], 1035.0, kH=0.0, kVML=0.0, kVdeep=0.0)
+    tm, gm = transport_from_oracle_inputs(o, oc, κH=0.0, κVML=0.0, κVdeep=0.0)     # caller-owned ϕ: the stream path
+    for oname, gname in NAMES.items():
+        assert_csc_equal(getattr(tm, gname), want[oname], f"kappa=0 {oname}")
+    assert tm.T.nnz == tm.Tadv.nnz < tm.TκH.nnz + tm.Tadv.nnz
+    # NaN density: the reference's message, through the stream path too
+    c = A._ctx_of(gm.v3D)
+    phi = [np.array(o["phi"][k], order="F") for k in O.FACES]
+    rho = np.full(gm.v3D.shape, np.nan, order="F")
+    with pytest.raises(A.OTMBError) as e:
+        A._transportmatrix_stream(c, o["ix"]["N"], phi, oc.mlotst, rho, 500.0, 0.1, 1e-5, True)
+    assert e.value.code == otmb_b200._lib.ERR_RHO_NAN and "ρ contains NaNs" in str(e.value)
+    # result arrays too small
+    with pytest.raises(A.OTMBError) as e:
+        A._transportmatrix_stream(c, o["ix"]["N"], phi, oc.mlotst, 1035.0, 500.0, 0.1, 1e-5, True, caps=[10] * 5)
+    assert e.value.code == otmb_b200._lib.ERR_BADARG
+    # and the context is still usable
+    ok = A._transportmatrix_stream(c, o["ix"]["N"], phi, oc.mlotst, 1035.0, 500.0, 0.1, 1e-5, True)
+    assert_csc_equal(ok.T, o["tm"]["T"], "after the failures")
