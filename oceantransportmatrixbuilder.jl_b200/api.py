@@ -499,8 +499,9 @@ def _vel_common(gridmetrics, ctx):
 
 def velocity2fluxes(u, u_lon, u_lat, v, v_lon, v_lat, gridmetrics, ρ, ctx=None):
     """velocity2fluxes, src/velocities.jl:10-39."""
-    ctx = _vel_common(gridmetrics, ctx)
+    ctx = _ctx_of(gridmetrics.v3D, ctx=ctx)
     u, _, _, v, _, _ = interpolateontodefaultCgrid(u, u_lon, u_lat, v, v_lon, v_lat, gridmetrics, ctx=ctx)
+    ctx = _vel_common(gridmetrics, ctx)      # last: caller-owned metrics are uploaded afresh by every step that needs them
     ua, va = _f64(_data(u)), _f64(_data(v))
     pi, pj = np.empty_like(ua), np.empty_like(va)
     rho3 = None if np.isscalar(ρ) else _f64(_data(ρ))

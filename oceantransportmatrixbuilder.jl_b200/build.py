@@ -46,6 +46,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
     objdir = HERE / "build"
     objdir.mkdir(exist_ok=True)
     flags = [f for f in NVCC_FLAGS if f != "-shared"] + [f"-I{INCLUDE}", f"-I{CSRC}"]
+    flags += os.environ.get("OTMB_NVCC_EXTRA", "").split()      # e.g. -DOTMB_AB: measurement build (A/B switches, traces)
     if ptxas_info:
         flags += ["-Xptxas", "-v"]
 

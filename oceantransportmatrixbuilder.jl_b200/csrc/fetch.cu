@@ -12,6 +12,7 @@
 // same bits as a direct 8-byte copy.  Matrices whose indices do not fit 32 bits take the direct copy.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #if defined(__x86_64__)
 #include <immintrin.h>
 #endif
@@ -503,6 +504,15 @@ extern "C" int otmb_transportmatrix_stream(otmb_ctx* c, const otmb_tm_params* pr
         }
     });
 
+#ifdef OTMB_AB
+    std::vector<std::pair<const char*, double>> trace;
+    const auto tr0 = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+        trace.emplace_back(what, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tr0).count());
+    };
+#else
+    auto mark = [](const char*) {};
+#endif
     // ---- event loop: launch slabs as their inputs are enqueued, send results out as slabs complete, do the host half
     int launched = 0, issued = 0;
     u64 serial[otmb_ctx::DONE_RING];
@@ -539,6 +549,7 @@ extern "C" int otmb_transportmatrix_stream(otmb_ctx* c, const otmb_tm_params* pr
             cudaEventRecord(ev_k[s], c->stream);
             ++launched;
             progress = true;
+            mark("launched");
         }
         if (issued < launched) {
             const int s = issued;
@@ -551,6 +562,7 @@ extern "C" int otmb_transportmatrix_stream(otmb_ctx* c, const otmb_tm_params* pr
                 }
             }
             if (done == 0) {
+                mark("slab done seen");
                 if (serial[s] != 0) {
                     const DevFlags& h = *c->h_flags;
                     agg.err_dry_neighbour |= h.err_dry_neighbour, agg.nan_adv |= h.nan_adv, agg.nan_kh |= h.nan_kh;
@@ -574,21 +586,32 @@ extern "C" int otmb_transportmatrix_stream(otmb_ctx* c, const otmb_tm_params* pr
                 for (int m = 0; m < 5; ++m) prev[m] = tot[m];
                 ++issued;
                 progress = true;
+                mark("copy-out issued");
             }
         }
         if (rc == OTMB_OK && co.front_ready()) {
+            mark("chunk ready");
             guard(co.consume());
             progress = true;
+            mark("chunk consumed");
         }
         if (!progress) _mm_pause();
     }
     up.th.join();
+    mark("loop end");
     if (rc == OTMB_OK && up.status.load() != OTMB_OK) rc = otmb_fail(c, OTMB_ERR_CUDA, "upload of the face fluxes failed");
     cudaEventRecord(c->ev_b1, c->stream);
     // everything enqueued must have left the streams before the caller's arrays (or an error) are handed back
     cudaStreamSynchronize(f->s_up);
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(f->s_dn);
+    mark("streams idle");
+#ifdef OTMB_AB
+    if (getenv("OTMB_STREAM_TRACE")) {
+        for (auto& t : trace) fprintf(stderr, "stream-trace %10.1f us  %s\n", t.second, t.first);
+        fprintf(stderr, "stream-trace ----\n");
+    }
+#endif
     if (rc != OTMB_OK) {
         otmb_reset_flags(c);
         return rc;
