@@ -83,6 +83,9 @@ struct V4Params {
     int ntiles;
     int w0;              // global wet rank of the launch's first column
     int ncols;
+    // a slab context holds a WINDOW of the 3-D arrays (common.cuh): idle threads of the last tile read the cell Lsafe
+    // (the window's first owned cell, i = 0) instead of cell 0, and the two-levels-ahead prefetch stops at Lmax
+    int Lsafe, ksafe, psafe, Lmax;
     i64* colptr[5];
     i64* rowval[5];
     double* nzval[5];
@@ -285,7 +288,7 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
     constexpr bool up = UP;
 
     // ================= phase 0: pattern =================
-    int L = 0, k = 0, p2 = 0;
+    int L = P.Lsafe, k = P.ksafe, p2 = P.psafe;
     unsigned wetm = 0, act = 0, mlm = 0;
     unsigned ord = ORD0;
     bool fold = false, generic = false;
@@ -324,7 +327,7 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
             prefetch_l2(P.pb + L1);
             prefetch_l2(P.thk + L1);
             if (RHO3D) prefetch_l2(P.rho3d + L1);
-            const int L2 = k < g.nz - 2 ? L1 + PP : L1;
+            const int L2 = min(k < g.nz - 2 ? L1 + PP : L1, P.Lmax);
             prefetch_l2(P.pt + L2);
             prefetch_l2(P.v3D + L2);
             prefetch_l2(P.rank3d + L2);
@@ -417,7 +420,7 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
     // Linear index of candidate c (clamped to a valid cell), recomputed from L, k, p2 and the class where it is needed:
     // two or three integer instructions each.  It used to be kept in shared memory; without that array two blocks fit
     // the 132 KB shared-memory carve-out instead of 164 KB, which leaves L1 124 KB instead of 92 KB.
-    if (!valid) ord = ORD1;   // L = 0: keeps every neighbour index of an idle thread inside the arrays
+    if (!valid) ord = ORD1;   // L = Lsafe (i = 0): keeps every neighbour index of an idle thread inside the window
     // first / last cell of a grid row, from the class: ORD1 = west seam; ORD2 = east seam unless the row has one cell
     const bool atW = ord == ORD1, atE = ord == ORD2 || g.nx == 1;
     auto Lc_of = [&](const int c) -> int {
@@ -936,6 +939,10 @@ int otmb_fused_v4_build(otmb_ctx* c, const otmb_tm_params* prm, int build, i64 c
 #ifdef OTMB_AB
     if (getenv("OTMB_V4_NOPREFETCH")) P.prefetch = 0;
 #endif
+    P.Lsafe = (int)c->L_own0;
+    P.ksafe = (int)(c->L_own0 / c->P);
+    P.psafe = (int)(c->L_own0 % c->P);
+    P.Lmax = (int)(c->L_win1 - 1);
     P.w0 = (int)(c->w0 + col0);
     P.ncols = (int)ncols;
     P.flags = c->flags.as<DevFlags>();

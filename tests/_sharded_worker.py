@@ -37,9 +37,9 @@ def main_native(local_rank):
     torch.cuda.set_device(local_rank)
     dist.init_process_group("gloo")                      # host-side rendezvous only: id broadcast + result gather
     rank, size = dist.get_rank(), dist.get_world_size()
-    box = [sharded.NativeSharded.unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(box, src=0)
     for shape, chunks in (((90, 45, 20), 0), ((37, 11, 7), 3), ((64, 33, 9), 64)):
+        box = [sharded.NativeSharded.unique_id() if rank == 0 else None]      # an id makes ONE communicator
+        dist.broadcast_object_list(box, src=0)
         oc = synthetic.make_ocean(*shape, "tripolar", seed=3, land_frac=0.25)
         gm = oracle_gridmetrics(oc)
         ns = sharded.NativeSharded(gridmetrics=gm, rank=rank, nranks=size, id_bytes=box[0], device=local_rank)
