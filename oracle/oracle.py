@@ -57,6 +57,8 @@ def lib():
         L.orc_facefluxes.argtypes = [dp, dp, dp, i64, i64, i64, C.c_int, dbl] + [dp] * 6
         L.orc_tm_build.argtypes = [dp] * 13 + [i64] * 3 + [C.c_int, dp, dbl, dbl, dbl, dbl, C.c_int, C.c_int]
         L.orc_tm_build.restype = C.c_void_p
+        L.orc_tm_build_columns.argtypes = [dp] * 13 + [i64] * 3 + [C.c_int, dp, dbl, dbl, dbl, dbl, C.c_int, C.c_int, i64, i64]
+        L.orc_tm_build_columns.restype = C.c_void_p
         for f in (L.orc_tm_status,):
             f.argtypes = [C.c_void_p]
         L.orc_tm_seconds.argtypes = [C.c_void_p]
@@ -190,6 +192,31 @@ def transportmatrix(phi, mlotst, v3D, thk, area2D, zt, edge, dnbr, topology, rho
                 tr[name] = (I, J, V)
             out["triplets"] = tr
         return out
+    finally:
+        L.orc_tm_free(h)
+
+
+def transportmatrix_columns(phi, mlotst, v3D, thk, area2D, zt, edge, dnbr, topology, rho, col_lo, col_hi, kH=500.0, kVML=0.1,
+                            kVdeep=1.0e-5, upwind=True):
+    """The columns [col_lo, col_hi) (0-based) of the five matrices of `transportmatrix`, built by the same emitters,
+    `sparse` and `+` restricted to the triplets of those columns (orc_tm_build_columns): for grids whose full matrices
+    are too large to hold beside the inputs.  Returns dict name -> CSC with n = col_hi - col_lo columns, colptr local
+    (1-based), rowval global (1-based)."""
+    L = lib()
+    ph = [_f(phi[k]) for k in FACES]
+    mlotst, v3D, thk, area2D, edge, dnbr = map(_f, (mlotst, v3D, thk, area2D, edge, dnbr))
+    zt = np.ascontiguousarray(zt, dtype=np.float64)
+    nx, ny, nz = v3D.shape
+    rho3 = None if np.isscalar(rho) else _f(rho)
+    rs = float(rho) if np.isscalar(rho) else 0.0
+    h = L.orc_tm_build_columns(*map(_p, ph), _p(mlotst), _p(v3D), _p(thk), _p(area2D), _p(zt), _p(edge), _p(dnbr),
+                               nx, ny, nz, TOPO[topology], _p(rho3), rs, float(kH), float(kVML), float(kVdeep),
+                               int(bool(upwind)), 0, int(col_lo), int(col_hi))
+    try:
+        st = L.orc_tm_status(h)
+        if st:
+            raise OracleError(st)
+        return {name: _fetch(L, h, w) for w, name in enumerate(MATS)}
     finally:
         L.orc_tm_free(h)
 

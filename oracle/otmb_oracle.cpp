@@ -281,7 +281,7 @@ void jl_spadd(const CSC& A, const CSC& B, CSC& C) {
     C.nzval.clear();
     C.rowval.reserve(A.rowval.size() + B.rowval.size());
     C.nzval.reserve(A.rowval.size() + B.rowval.size());
-    const i64 sentinel = n + 1;
+    const i64 sentinel = INT64_MAX;   // larger than any row index (the operands may be N x n column blocks)
     i64 Ck = 1;
     for (i64 j = 1; j <= n; ++j) {
         C.colptr[j - 1] = Ck;
@@ -320,14 +320,19 @@ void jl_spadd(const CSC& A, const CSC& B, CSC& C) {
 struct Triplets {
     std::vector<i64> I, J;
     std::vector<double> V;
+    // column window of the streamed build (orc_tm_build_columns): only triplets of the columns jlo..jhi (1-based) are
+    // kept, renumbered from 1.  The order of the kept triplets is the emit order, so sparse() combines them exactly as
+    // it does inside the full matrix.  Default: keep everything.
+    i64 jlo = 1, jhi = INT64_MAX;
     void hint(i64 n) {  // preallocate_sparse_entries, src/matrixbuilding.jl:153-161
         I.reserve(n);
         J.reserve(n);
         V.reserve(n);
     }
     void push(i64 i, i64 j, double v) {
+        if (j < jlo || j > jhi) return;
         I.push_back(i);
-        J.push_back(j);
+        J.push_back(j - jlo + 1);
         V.push_back(v);
     }
     bool anynan() const {
@@ -354,6 +359,7 @@ struct Indices {  // makeindices, src/matrixbuilding.jl:10-24
     std::vector<i64> Lwet3D;    // 1-based wet index, 0 = missing
     std::vector<uint8_t> wet3D;
     i64 N = 0;
+    i64 w_lo = 0, w_hi = 0;     // emitters visited (all of them, or those that can reach a column window)
 };
 
 void makeindices(const double* v3D, i64 M, Indices& ix) {
@@ -363,6 +369,8 @@ void makeindices(const double* v3D, i64 M, Indices& ix) {
     for (i64 L = 0; L < M; ++L)
         if (!std::isnan(v3D[L])) ix.Lwet.push_back(L);
     ix.N = (i64)ix.Lwet.size();
+    ix.w_lo = 0;
+    ix.w_hi = ix.N;
     for (i64 w = 0; w < ix.N; ++w) {
         ix.wet3D[ix.Lwet[w]] = 1;
         ix.Lwet3D[ix.Lwet[w]] = w + 1;
@@ -403,7 +411,7 @@ int advection_entries(const double* const phi[6] /*east,west,north,south,top,bot
         if (wj == 0) { status = ORC_ERR_DRY_NEIGHBOUR; return; }
         pushTadvectionvalues(t, wi, wj, p, rhoi, rho_at(Lj), vi, G.v3D[Lj]);
     };
-    for (i64 w = 0; w < ix.N; ++w) {
+    for (i64 w = ix.w_lo; w < ix.w_hi; ++w) {
         i64 Li = ix.Lwet[w];
         CI Ci = cart(Li, g);
         i64 wi = w + 1;
@@ -439,7 +447,7 @@ int hdiff_entries(const Grid& G, const Indices& ix, double kH, Triplets& t) {
     if (g.kind == TOPO_UNKNOWN) return ORC_ERR_UNKNOWN_GRID;
     t.hint(8 * ix.N);
     const i64 P = G.P();
-    for (i64 w = 0; w < ix.N; ++w) {
+    for (i64 w = ix.w_lo; w < ix.w_hi; ++w) {
         i64 Li = ix.Lwet[w];
         CI Ci = cart(Li, g);
         i64 wi = w + 1;
@@ -468,7 +476,7 @@ int vdiff_entries(const Grid& G, const Indices& ix, double kV, const std::vector
     const Topo& g = G.g;
     if (g.kind == TOPO_UNKNOWN) return ORC_ERR_UNKNOWN_GRID;
     t.hint(4 * ix.N);
-    for (i64 w = 0; w < ix.N; ++w) {
+    for (i64 w = ix.w_lo; w < ix.w_hi; ++w) {
         if (!Omega[w]) continue;
         i64 Li = ix.Lwet[w];
         CI Ci = cart(Li, g);
@@ -617,33 +625,47 @@ int orc_facefluxes(double* umo, double* vmo, const double* v3D, i64 nx, i64 ny, 
 // phi order: east, west, north, south, top, bottom (the NamedTuple of src/velocities.jl:245-252).
 // rho3d may be NULL (then rho_scalar is used, :221-225).  mlotst: NaN = missing.
 // Returns an opaque handle; status via orc_tm_status.
-void* orc_tm_build(const double* pe, const double* pw, const double* pn, const double* ps, const double* pt,
-                   const double* pb, const double* mlotst, const double* v3D, const double* thk,
-                   const double* area2D, const double* zt, const double* edge, const double* dnbr, i64 nx, i64 ny,
-                   i64 nz, int topo, const double* rho3d, double rho_scalar, double kH, double kVML, double kVdeep,
-                   int upwind, int keep_triplets) {
+// col_lo / col_hi (0-based, [col_lo, col_hi)): the STREAMED form used for grids whose full matrices do not fit the
+// checker's memory comfortably — the same emitters visit only the wet cells that can reach those columns (their
+// neighbours: within one level, nx*ny linear cells, either side), only the triplets of those columns are kept, in
+// emit order, and sparse / + run on an N x (col_hi - col_lo) matrix: the result is exactly the column block of the
+// full matrices (colptr local and 1-based, row indices global).  col_hi < 0: everything.
+void* orc_tm_build_columns(const double* pe, const double* pw, const double* pn, const double* ps, const double* pt,
+                           const double* pb, const double* mlotst, const double* v3D, const double* thk,
+                           const double* area2D, const double* zt, const double* edge, const double* dnbr, i64 nx, i64 ny,
+                           i64 nz, int topo, const double* rho3d, double rho_scalar, double kH, double kVML, double kVdeep,
+                           int upwind, int keep_triplets, i64 col_lo, i64 col_hi) {
     TM* tm = new TM();
     auto t0 = std::chrono::steady_clock::now();
     Grid G{Topo{topo, nx, ny, nz}, v3D, thk, area2D, zt, edge, dnbr};
     Indices ix;
     makeindices(v3D, G.M(), ix);
-    const i64 N = ix.N;
+    const i64 Nrows = ix.N;
+    i64 N = ix.N;               // columns of the matrices built below
     const double* phi[6] = {pe, pw, pn, ps, pt, pb};
     Triplets tr[4];
+    if (col_hi >= 0) {
+        if (col_lo < 0 || col_hi > ix.N || col_lo >= col_hi) { tm->status = -1; return tm; }
+        const i64 L_lo = ix.Lwet[col_lo] - G.P(), L_hi = ix.Lwet[col_hi - 1] + G.P();
+        ix.w_lo = std::lower_bound(ix.Lwet.begin(), ix.Lwet.end(), L_lo) - ix.Lwet.begin();
+        ix.w_hi = std::upper_bound(ix.Lwet.begin(), ix.Lwet.end(), L_hi) - ix.Lwet.begin();
+        for (auto& t : tr) t.jlo = col_lo + 1, t.jhi = col_hi;
+        N = col_hi - col_lo;
+    }
     int st;
     // buildTadv :31-44
     st = advection_entries(phi, G, ix, rho3d, rho_scalar, upwind != 0, tr[0]);
     if (st == ORC_OK && tr[0].anynan()) st = ORC_ERR_TADV_NAN;
     if (st != ORC_OK) { tm->status = st; return tm; }
-    jl_sparse(tr[0].I, tr[0].J, tr[0].V, N, N, tm->mats[1]);
+    jl_sparse(tr[0].I, tr[0].J, tr[0].V, Nrows, N, tm->mats[1]);
     // buildTκH :51-66
     st = hdiff_entries(G, ix, kH, tr[1]);
     if (st == ORC_OK && tr[1].anynan()) st = ORC_ERR_TKH_NAN;
     if (st != ORC_OK) { tm->status = st; return tm; }
-    jl_sparse(tr[1].I, tr[1].J, tr[1].V, N, N, tm->mats[2]);
+    jl_sparse(tr[1].I, tr[1].J, tr[1].V, Nrows, N, tm->mats[2]);
     // buildTκVML :74-95 ; Ω = (zt[k] < mlotst[i,j], missing -> false)[Lwet]  :85
-    std::vector<uint8_t> Omega(N);
-    for (i64 w = 0; w < N; ++w) {
+    std::vector<uint8_t> Omega(Nrows);
+    for (i64 w = 0; w < Nrows; ++w) {
         CI c = cart(ix.Lwet[w], G.g);
         double ml = mlotst[lin2(c, G.g)];
         Omega[w] = (zt[c.k - 1] < ml) ? 1 : 0;  // comparison with NaN is false
@@ -651,13 +673,13 @@ void* orc_tm_build(const double* pe, const double* pw, const double* pn, const d
     st = vdiff_entries(G, ix, kVML, Omega, tr[2]);
     if (st == ORC_OK && tr[2].anynan()) st = ORC_ERR_TKVML_NAN;
     if (st != ORC_OK) { tm->status = st; return tm; }
-    jl_sparse(tr[2].I, tr[2].J, tr[2].V, N, N, tm->mats[3]);
+    jl_sparse(tr[2].I, tr[2].J, tr[2].V, Nrows, N, tm->mats[3]);
     // buildTκVdeep :103-120 ; Ω = trues(N)
     std::fill(Omega.begin(), Omega.end(), 1);
     st = vdiff_entries(G, ix, kVdeep, Omega, tr[3]);
     if (st == ORC_OK && tr[3].anynan()) st = ORC_ERR_TKVDEEP_NAN;
     if (st != ORC_OK) { tm->status = st; return tm; }
-    jl_sparse(tr[3].I, tr[3].J, tr[3].V, N, N, tm->mats[4]);
+    jl_sparse(tr[3].I, tr[3].J, tr[3].V, Nrows, N, tm->mats[4]);
     // T = Tadv + TκH + TκVML + TκVdeep :147
     CSC t1, t2;
     jl_spadd(tm->mats[1], tm->mats[2], t1);
@@ -667,6 +689,14 @@ void* orc_tm_build(const double* pe, const double* pw, const double* pn, const d
     if (keep_triplets)
         for (int q = 0; q < 4; ++q) tm->trip[q] = std::move(tr[q]);
     return tm;
+}
+void* orc_tm_build(const double* pe, const double* pw, const double* pn, const double* ps, const double* pt,
+                   const double* pb, const double* mlotst, const double* v3D, const double* thk,
+                   const double* area2D, const double* zt, const double* edge, const double* dnbr, i64 nx, i64 ny,
+                   i64 nz, int topo, const double* rho3d, double rho_scalar, double kH, double kVML, double kVdeep,
+                   int upwind, int keep_triplets) {
+    return orc_tm_build_columns(pe, pw, pn, ps, pt, pb, mlotst, v3D, thk, area2D, zt, edge, dnbr, nx, ny, nz, topo, rho3d,
+                                rho_scalar, kH, kVML, kVdeep, upwind, keep_triplets, 0, -1);
 }
 int orc_tm_status(void* h) { return ((TM*)h)->status; }
 double orc_tm_seconds(void* h) { return ((TM*)h)->seconds; }

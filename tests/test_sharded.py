@@ -262,3 +262,63 @@ def test_native_driver_single_rank_and_chunked_columns(nchunks):
     ns.facefluxes_enqueue(nchunks)
     assert ns.build(oc.mlotst, 1035.0, upload=False) == ns.nnz_total
     ns.close()
+
+
+@pytest.mark.gpu
+def test_c4_quarter_degree_sharded_matches_streamed_oracle():
+    """BASELINE configs[3] at FULL size (1440x1080x50, 40.4 M wet cells, 280 M entries in T): the row-slab sharded
+    assembly (8 slabs, cuts inside levels, one context each on this GPU) against the oracle, bit for bit.  The oracle
+    cannot hold the five full matrices beside the inputs, so it is streamed (orc_tm_build_columns): three windows of
+    columns — the first million (surface, mixed layer), a million straddling the cut between ranks 3 and 4 (a cut
+    inside a level: halo rows, carry plane, rank offsets), and the last million (sea floor).  Both sides get the same
+    geometry (the GPU's) and the same umo / vmo; the oracle computes its own face fluxes."""
+    import otmb_b200.api as A
+    from _util import fields
+    R = 8
+    oc = synthetic.make_config("C4", seed=0)
+    f = fields(oc)
+    ctx = A.Context(0)
+    gm = A.makegridmetrics(areacello=f["areacello"], volcello=f["volcello"], lon=f["lon"], lat=f["lat"], lev=f["lev"],
+                           lon_vertices=f["lon_vertices"], lat_vertices=f["lat_vertices"], ctx=ctx)
+    ctx.close()
+    slabs, wet = sharded.plan_slabs(gm.v3D, R)
+    N = sum(wet)
+    col0 = np.concatenate([[0], np.cumsum(wet)])
+    assert max(abs(w - N / R) for w in wet) <= gm.v3D.shape[0] and any(a % gm.v3D.shape[1] for a, _ in slabs[1:])
+    windows = [(0, 1_000_000), (int(col0[4]) - 500_000, int(col0[4]) + 500_000), (N - 1_000_000, N)]
+    need = {r for lo, hi in windows for r in range(R) if col0[r] < hi and col0[r + 1] > lo}
+
+    def fn(ex):
+        slab, w0, n, info = sharded.prepare_sharded(exchange=ex, gridmetrics=gm, umo=oc.umo, vmo=oc.vmo, FillValue=oc.fill)
+        nnz = slab.build(oc.mlotst, 1035.0, 500.0, 0.1, 1.0e-5, True)
+        nnz_all = ex.allgather_ints(nnz)
+        local = slab.fetch() if ex.rank in need else None
+        slab.ctx.close()
+        return w0, n, nnz_all, local
+
+    res = sharded.run_threaded(R, fn)
+    assert [r[0] for r in res] == [int(c) for c in col0[:-1]] and all(r[1] == N for r in res)
+    nnz_all = res[0][2]
+    phi = O.facefluxes(oc.umo, oc.vmo, gm.v3D, oc.topology, oc.fill)
+    edge = np.asfortranarray(np.stack([gm.edge_length_2D[d] for d in A.DIRS], axis=-1))
+    dnbr = np.asfortranarray(np.stack([gm.distance_to_neighbour_2D[d] for d in A.DIRS], axis=-1))
+    for lo, hi in windows:
+        want = O.transportmatrix_columns(phi, oc.mlotst, gm.v3D, gm.thkcello, gm.area2D, oc.lev, edge, dnbr, oc.topology, 1035.0, lo, hi)
+        for m, (gname, oname) in enumerate(NAMES.items()):
+            w = want[oname]
+            # the GPU's columns lo..hi from the rank segments that hold them (local colptr + entries of the lower ranks)
+            cps, rvs, nzs = [], [], []
+            for r in sorted(need):
+                a, b = max(lo, int(col0[r])) - int(col0[r]), min(hi, int(col0[r + 1])) - int(col0[r])
+                if a >= b:
+                    continue
+                cp, rv, nz = res[r][3][gname]
+                off = sum(nnz_all[q][m] for q in range(r))
+                cps.append(cp[a:b] + off)
+                rvs.append(rv[cp[a]:cp[b]])
+                nzs.append(nz[cp[a]:cp[b]])
+                last = cp[b] + off
+            cp = np.concatenate(cps + [np.array([last])])
+            assert np.array_equal(cp - cp[0] + 1, w.colptr), f"{gname} colptr, columns {lo}:{hi}"
+            assert np.array_equal(np.concatenate(rvs) + 1, w.rowval), f"{gname} rowval, columns {lo}:{hi}"
+            assert np.array_equal(np.concatenate(nzs).view(np.int64), w.nzval.view(np.int64)), f"{gname} nzval, columns {lo}:{hi}"
