@@ -1,37 +1,45 @@
 # OceanTransportMatrixBuilderB200.jl — the Julia side of the drop-in boundary.
 #
-# A thin shim that keeps the reference's exported API (src/OceanTransportMatrixBuilder.jl:31-36)
-# and forwards the hot path to libotmb.so (include/otmb.h) with `ccall`.  No CUDA.jl, no kernel
-# code generation, no CPU fallback: if the library or a B200 is missing, the calls throw.
+# A thin shim that keeps the reference's exported API (src/OceanTransportMatrixBuilder.jl:31-36) and forwards the
+# hot path to libotmb.so (include/otmb.h) with `ccall`.  No CUDA.jl, no kernel code generation, no CPU fallback: if
+# the library or a B200 is missing, the calls throw.
 #
-# NOT EXECUTED IN THIS REPOSITORY'S CI: Julia is not installed in the build image.  The Python
-# shim (api.py) is the same layer, exercised by the tests.  See INTEGRATION.md.
+# It sits NEXT TO the reference package and uses it for what stays host work (SURVEY.md §8a row A3): the package's own
+# `getgridtopology`, `vertexpermutation`, `getarakawagrid`, `interpolateontodefaultCgrid` dispatch and topology types
+# are called, not restated.  `using OceanTransportMatrixBuilderB200` instead of `using OceanTransportMatrixBuilder`
+# is the whole switch (INTEGRATION.md §2).
+#
+# Every entry point of include/otmb.h that a host program needs is bound here (INTEGRATION.md §1 has the table).
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: Julia is not installed in the build image.  The Python shim (api.py) is the
+# same layer, exercised by the tests; tests/abi_driver.c exercises the ABI from C.
 module OceanTransportMatrixBuilderB200
 
 using SparseArrays
+import OceanTransportMatrixBuilder as REF      # host-only pieces and types of the reference
 
 export makegridmetrics, makeindices, facefluxesfrommasstransport, facefluxesfromvelocities, velocity2fluxes,
        fluxes2velocity, transportmatrix, lump_and_spray
 
 const LIBOTMB = get(ENV, "LIBOTMB", joinpath(@__DIR__, "..", "libotmb.so"))
+const PF, PI, PV = Ptr{Float64}, Ptr{Int64}, Ptr{Cvoid}
 
-# the reference's topology structs (src/gridtopology.jl:1-16), reduced to a tag the library understands
-abstract type AbstractGridTopology end
-struct BipolarGridTopology <: AbstractGridTopology; nx::Int64; ny::Int64; nz::Int64; end
-struct TripolarGridTopology <: AbstractGridTopology; nx::Int64; ny::Int64; nz::Int64; end
-struct UnknownGridTopology <: AbstractGridTopology; nx::Int64; ny::Int64; nz::Int64; end
-topotag(::BipolarGridTopology) = Cint(0)
-topotag(::TripolarGridTopology) = Cint(1)
-topotag(::UnknownGridTopology) = Cint(2)
+topotag(::REF.BipolarGridTopology) = Cint(0)
+topotag(::REF.TripolarGridTopology) = Cint(1)
+topotag(::REF.AbstractGridTopology) = Cint(2)          # UnknownGridTopology: the kernels refuse it with the reference's message
 
+# ------------------------------------------------------------------------------------------------------------------
+# context, errors, page-locked arrays
+# ------------------------------------------------------------------------------------------------------------------
 mutable struct Context
-    h::Ptr{Cvoid}
+    h::PV
+    serial::Int            # bumped whenever the resident grid / metrics change
     function Context(device::Integer = 0)
-        r = Ref{Ptr{Cvoid}}(C_NULL)
-        st = ccall((:otmb_create, LIBOTMB), Cint, (Ref{Ptr{Cvoid}}, Cint), r, device)
+        r = Ref{PV}(C_NULL)
+        st = ccall((:otmb_create, LIBOTMB), Cint, (Ref{PV}, Cint), r, device)
         st == 0 || error(unsafe_string(ccall((:otmb_status_string, LIBOTMB), Cstring, (Cint,), st)))
-        c = new(r[])
-        finalizer(c -> ccall((:otmb_destroy, LIBOTMB), Cint, (Ptr{Cvoid},), c.h), c)
+        c = new(r[], 0)
+        finalizer(c -> ccall((:otmb_destroy, LIBOTMB), Cint, (PV,), c.h), c)
         return c
     end
 end
@@ -42,33 +50,35 @@ ctx() = (CTX[] === nothing && (CTX[] = Context()); CTX[]::Context)
 # src/gridtopology.jl:111-116; src/velocities.jl:199-200)
 function check(c::Context, st::Cint)
     st == 0 && return nothing
-    msg = unsafe_string(ccall((:otmb_last_error, LIBOTMB), Cstring, (Ptr{Cvoid},), c.h))
+    msg = unsafe_string(ccall((:otmb_last_error, LIBOTMB), Cstring, (PV,), c.h))
+    isempty(msg) && (msg = unsafe_string(ccall((:otmb_status_string, LIBOTMB), Cstring, (Cint,), st)))
     st == 7 && throw(AssertionError(msg))
     error(msg)
 end
 
-isapprox_lon(a, b) = isapprox((@. mod(a - b + 180, 360) - 180), zeros(size(a)), atol = eps(180.0))
-function getgridtopology(lon_vertices, lat_vertices, lev)      # src/gridtopology.jl:33-53, host work
-    nx, ny, nz = size(lon_vertices, 2), size(lon_vertices, 3), length(lev)
-    NPlon = @view lon_vertices[3:4, :, end]
-    NPlat = @view lat_vertices[3:4, :, end]
-    all(NPlat .== 90) && return BipolarGridTopology(nx, ny, nz)
-    (isapprox_lon(NPlon, rot180(NPlon)) && isapprox(NPlat, rot180(NPlat))) && return TripolarGridTopology(nx, ny, nz)
-    @warn "Unknown grid topology detected. Things might not work as expected."
-    return UnknownGridTopology(nx, ny, nz)
-end
-function vertexpermutation(lon_vertices, lat_vertices)          # src/gridcellgeometry.jl:158-178, host work
-    pts = collect(zip(lon_vertices[:, 1, 1], lat_vertices[:, 1, 1]))
-    pe = Set(zip(lon_vertices[:, 2, 1], lat_vertices[:, 2, 1]))
-    pn = Set(zip(lon_vertices[:, 1, 2], lat_vertices[:, 1, 2]))
-    ie, in_ = findall(in(pe), pts), findall(in(pn), pts)
-    i3 = only(ie ∩ in_); i2 = only(setdiff(ie, i3)); i4 = only(setdiff(in_, i3)); i1 = only(setdiff(1:4, i2, i3, i4))
-    return [i1, i2, i3, i4]
+# Result arrays live in page-locked memory (otmb_host_alloc): a copy from the GPU into ordinary (pageable) Julia
+# arrays runs at a fraction of the PCIe rate.  The vectors are ordinary `Vector`s to every consumer (SparseMatrixCSC,
+# mul!, \\); they cannot be resized (the library sizes them exactly), and the memory goes back when they are collected.
+function pinned(::Type{T}, dims::Integer...) where {T}
+    n = prod(dims)
+    p = Ref{PV}(C_NULL)
+    st = ccall((:otmb_host_alloc, LIBOTMB), Cint, (Ref{PV}, Int64), p, max(n * sizeof(T), 8))
+    st == 0 || return Array{T}(undef, dims...)                 # no pinnable memory left: a pageable array still works
+    a = unsafe_wrap(Array, Ptr{T}(p[]), dims; own = false)
+    finalizer(_ -> ccall((:otmb_host_free, LIBOTMB), Cint, (PV,), p[]), a)
+    return a
 end
 
-"makegridmetrics, src/gridcellgeometry.jl:265-311"
+# what the library holds resident for a NamedTuple this module returned: (context serial) in a hidden field.  Arrays of
+# such a NamedTuple must not be modified in place (Julia cannot make them read-only); call `invalidate!()` if they were.
+invalidate!(c::Context = ctx()) = (c.serial += 1; nothing)
+resident(c::Context, nt) = hasproperty(nt, :b200) && nt.b200 == (objectid(c), c.serial)
+
+# ------------------------------------------------------------------------------------------------------------------
+# makegridmetrics, src/gridcellgeometry.jl:265-311
+# ------------------------------------------------------------------------------------------------------------------
 function makegridmetrics(; areacello, volcello, lon, lat, lev, lon_vertices, lat_vertices)
-    toreplace = Set{Any}((missing, nothing, 0))
+    toreplace = Set{Any}((missing, nothing, 0))                                        # :269-280, host work
     haskey(areacello.properties, "_FillValue") && push!(toreplace, areacello.properties["_FillValue"])
     haskey(volcello.properties, "_FillValue") && push!(toreplace, volcello.properties["_FillValue"])
     replacelist = (x => NaN for x in toreplace)
@@ -76,40 +86,59 @@ function makegridmetrics(; areacello, volcello, lon, lat, lev, lon_vertices, lat
     area2D = Array{Float64}(replace(areacello |> Array{Union{Missing, Float64}}, replacelist...))
     zt = Array{Float64}(lev |> Array); lat = Array{Float64}(lat |> Array); lon = Array{Float64}(lon |> Array)
     lon_vertices = lon_vertices |> Array{Float64}; lat_vertices = lat_vertices |> Array{Float64}
-    p = vertexpermutation(lon_vertices, lat_vertices)
+    p = REF.vertexpermutation(lon_vertices, lat_vertices)                              # :158-178, the package's own
     lon_vertices = lon_vertices[p, :, :]; lat_vertices = lat_vertices[p, :, :]
-    gridtopology = getgridtopology(lon_vertices, lat_vertices, zt)
+    gridtopology = REF.getgridtopology(lon_vertices, lat_vertices, zt)                 # src/gridtopology.jl:33-53
     nx, ny, nz = size(v3D)
     c = ctx(); N = Ref{Int64}(0)
-    check(c, ccall((:otmb_set_grid, LIBOTMB), Cint, (Ptr{Cvoid}, Int64, Int64, Int64, Cint), c.h, nx, ny, nz, topotag(gridtopology)))
-    check(c, ccall((:otmb_makeindices, LIBOTMB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Int64}), c.h, v3D, N))
+    invalidate!(c)
+    check(c, ccall((:otmb_set_grid, LIBOTMB), Cint, (PV, Int64, Int64, Int64, Cint), c.h, nx, ny, nz, topotag(gridtopology)))
+    check(c, ccall((:otmb_makeindices, LIBOTMB), Cint, (PV, PF, Ref{Int64}), c.h, v3D, N))
     thkcello = similar(v3D); Z3D = similar(v3D)
     edge = Array{Float64}(undef, nx, ny, 4); dedge = similar(edge); dnbr = similar(edge)
-    check(c, ccall((:otmb_gridmetrics, LIBOTMB), Cint,
-        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
-         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-        c.h, area2D, lon, lat, lon_vertices, lat_vertices, zt, thkcello, Z3D, edge, dedge, dnbr))
-    dirs = (:south, :east, :north, :west)                      # src/gridcellgeometry.jl:304
+    check(c, ccall((:otmb_gridmetrics, LIBOTMB), Cint, (PV, PF, PF, PF, PF, PF, PF, PF, PF, PF, PF, PF),
+                   c.h, area2D, lon, lat, lon_vertices, lat_vertices, zt, thkcello, Z3D, edge, dedge, dnbr))
+    dirs = (:south, :east, :north, :west)                                              # :304
     asdict(a) = Dict(d => a[:, :, q] for (q, d) in enumerate(dirs))
     edge_length_2D, distance_to_edge_2D, distance_to_neighbour_2D = asdict(edge), asdict(dedge), asdict(dnbr)
-    return (; area2D, v3D, thkcello, lon_vertices, lat_vertices, lon, lat, Z3D, zt, edge_length_2D, distance_to_edge_2D, distance_to_neighbour_2D, gridtopology)
+    b200 = (objectid(c), c.serial)        # v3D, thkcello, Z3D, area2D, zt, edge lengths, distances, lon, lat are resident
+    return (; area2D, v3D, thkcello, lon_vertices, lat_vertices, lon, lat, Z3D, zt, edge_length_2D, distance_to_edge_2D,
+              distance_to_neighbour_2D, gridtopology, b200)
+end
+
+# upload grid + metrics of a gridmetrics NamedTuple that is not the resident one (e.g. built by the reference itself)
+function ensure_metrics(c::Context, gm)
+    resident(c, gm) && return nothing
+    nx, ny, nz = size(gm.v3D)
+    invalidate!(c)
+    N = Ref{Int64}(0)
+    check(c, ccall((:otmb_set_grid, LIBOTMB), Cint, (PV, Int64, Int64, Int64, Cint), c.h, nx, ny, nz, topotag(gm.gridtopology)))
+    check(c, ccall((:otmb_makeindices, LIBOTMB), Cint, (PV, PF, Ref{Int64}), c.h, Array{Float64}(gm.v3D), N))
+    dirs = (:south, :east, :north, :west)
+    edge = cat((gm.edge_length_2D[d] for d in dirs)...; dims = 3)
+    dnbr = cat((gm.distance_to_neighbour_2D[d] for d in dirs)...; dims = 3)
+    check(c, ccall((:otmb_set_gridmetrics, LIBOTMB), Cint, (PV, PF, PF, PF, PF, PF, PF, PF, PF),
+                   c.h, gm.area2D, gm.thkcello, gm.zt, edge, dnbr, gm.Z3D, gm.lon, gm.lat))
+    return nothing
 end
 
 "makeindices(v3D), src/matrixbuilding.jl:10-24"
 function makeindices(v3D)
-    nxyz = size(v3D); M = length(v3D)
+    nxyz = size(v3D)
     c = ctx(); N = Ref{Int64}(0)
-    # the grid tag does not matter for indices; keep whatever makegridmetrics set, else bipolar
-    check(c, ccall((:otmb_makeindices, LIBOTMB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Int64}), c.h, v3D, N))
+    # (re-runs on the resident grid: the topology tag plays no role for the indices)
+    check(c, ccall((:otmb_makeindices, LIBOTMB), Cint, (PV, PF, Ref{Int64}), c.h, Array{Float64}(v3D), N))
     wet3D = falses(nxyz...)                                     # BitArray chunks are filled in place
     Lwet = Vector{Int64}(undef, N[]); L3 = Array{Int64}(undef, nxyz...)
-    check(c, ccall((:otmb_get_indices, LIBOTMB), Cint, (Ptr{Cvoid}, Ptr{UInt64}, Ptr{Int64}, Ptr{Int64}), c.h, wet3D.chunks, Lwet, L3))
+    check(c, ccall((:otmb_get_indices, LIBOTMB), Cint, (PV, Ptr{UInt64}, PI, PI), c.h, wet3D.chunks, Lwet, L3))
     Lwet3D = Array{Union{Int, Missing}, 3}(missing, nxyz...)    # isbits-Union arrays cannot be filled through a pointer
     Lwet3D[Lwet] .= 1:N[]
     return (; wet3D, L = LinearIndices(nxyz), Lwet, N = N[], Lwet3D, C = CartesianIndices(nxyz))
 end
 
-"facefluxesfrommasstransport, src/velocities.jl:118-130"
+# ------------------------------------------------------------------------------------------------------------------
+# face fluxes, src/velocities.jl:118-130, 154-255
+# ------------------------------------------------------------------------------------------------------------------
 function facefluxesfrommasstransport(; umo, vmo, gridmetrics, indices)
     FillValue = umo.properties["_FillValue"]
     @assert isequal(FillValue, vmo.properties["_FillValue"])
@@ -119,94 +148,146 @@ end
 "facefluxes (+ nofluxboundaries!), src/velocities.jl:154-255; umo / vmo are not modified"
 function facefluxes(u::Array{Float64, 3}, v::Array{Float64, 3}, gridmetrics, indices; FillValue)
     c = ctx()
-    east = similar(u); west = similar(u); north = similar(u); south = similar(u); top = similar(u); bottom = similar(u)
-    check(c, ccall((:otmb_facefluxes, LIBOTMB), Cint,
-        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-        c.h, u, v, Float64(FillValue), east, west, north, south, top, bottom))
+    ensure_metrics(c, gridmetrics)
+    dims = size(u)
+    east, west, north, south, top, bottom = (pinned(Float64, dims...) for _ in 1:6)
+    check(c, ccall((:otmb_facefluxes, LIBOTMB), Cint, (PV, PF, PF, Float64, PF, PF, PF, PF, PF, PF),
+                   c.h, u, v, Float64(FillValue), east, west, north, south, top, bottom))
     return (; east, west, north, south, top, bottom)
 end
 
-struct TMParams
+"""
+    facefluxes_GM(; umo, vmo, gridmetrics, indices, ρ, κGM = 600, maxslope = 0.01, ρ_flux = nothing)
+
+EXTENSION (BASELINE configs[2]; the reference has the pieces, not the chain — parity unpinned): face fluxes of the mass
+transport plus the Gent-McWilliams bolus transport, `bolus_GM_velocity` (src/RediGM.jl:46-79) -> `velocity2fluxes`
+(src/velocities.jl:10-39) -> `+ umo/vmo` -> `facefluxes`, chained on the device (`otmb_facefluxes_gm`).
+"""
+function facefluxes_GM(; umo, vmo, gridmetrics, indices, ρ, κGM = 600, maxslope = 0.01, ρ_flux = nothing)
+    FillValue = umo.properties["_FillValue"]
+    @assert isequal(FillValue, vmo.properties["_FillValue"])
+    c = ctx()
+    ensure_metrics(c, gridmetrics)
+    u, v, ρ3 = umo |> Array{Float64}, vmo |> Array{Float64}, Array{Float64}(ρ)
+    east, west, north, south, top, bottom = (pinned(Float64, size(u)...) for _ in 1:6)
+    check(c, ccall((:otmb_facefluxes_gm, LIBOTMB), Cint,
+                   (PV, PF, PF, Float64, PF, Float64, Float64, Float64, Int32, PF, PF, PF, PF, PF, PF, PF, PF),
+                   c.h, u, v, Float64(FillValue), ρ3, Float64(κGM), Float64(maxslope), isnothing(ρ_flux) ? 0.0 : Float64(ρ_flux),
+                   Int32(isnothing(ρ_flux)), east, west, north, south, top, bottom, C_NULL, C_NULL))
+    return (; east, west, north, south, top, bottom)
+end
+
+# ------------------------------------------------------------------------------------------------------------------
+# transportmatrix, src/matrixbuilding.jl:128-150
+# ------------------------------------------------------------------------------------------------------------------
+struct TMParams            # mirrors otmb_tm_params (include/otmb.h)
     kH::Float64; kVML::Float64; kVdeep::Float64; rho::Float64
     upwind::Int32; index_base::Int32; path::Int32; build_mask::Int32
 end
 
-"transportmatrix, src/matrixbuilding.jl:128-150"
 function transportmatrix(; ϕ, mlotst, gridmetrics, indices, ρ, κH = 500.0, κVML = 0.1, κVdeep = 1.0e-5,
         Tadv = nothing, TκH = nothing, TκVML = nothing, TκVdeep = nothing, upwind = true)
     c = ctx(); N = indices.N
-    (; area2D, thkcello, zt, edge_length_2D, distance_to_neighbour_2D, Z3D, lon, lat) = gridmetrics
-    dirs = (:south, :east, :north, :west)
-    edge = cat((edge_length_2D[d] for d in dirs)...; dims = 3); dnbr = cat((distance_to_neighbour_2D[d] for d in dirs)...; dims = 3)
-    P = Ptr{Float64}
-    check(c, ccall((:otmb_set_gridmetrics, LIBOTMB), Cint, (Ptr{Cvoid}, P, P, P, P, P, P, P, P), c.h, area2D, thkcello, zt, edge, dnbr, Z3D, lon, lat))
-    faces = [ϕ.east, ϕ.west, ϕ.north, ϕ.south, ϕ.top, ϕ.bottom]
-    GC.@preserve faces begin
-        check(c, ccall((:otmb_set_facefluxes, LIBOTMB), Cint, (Ptr{Cvoid}, Ptr{Ptr{Float64}}), c.h, pointer.(faces)))
-    end
+    ensure_metrics(c, gridmetrics)                  # nothing to do for the NamedTuple makegridmetrics returned
     ml = Array{Float64}(replace(mlotst |> Array, missing => NaN))
-    check(c, ccall((:otmb_set_mlotst, LIBOTMB), Cint, (Ptr{Cvoid}, P), c.h, ml))
-    if ρ isa Number
-        check(c, ccall((:otmb_set_rho3d, LIBOTMB), Cint, (Ptr{Cvoid}, P), c.h, C_NULL))
-    else
-        check(c, ccall((:otmb_set_rho3d, LIBOTMB), Cint, (Ptr{Cvoid}, P), c.h, Array{Float64}(ρ)))
+    ρ3 = ρ isa Number ? nothing : Array{Float64}(ρ)
+    faces = [Array{Float64}(getfield(ϕ, k)) for k in (:east, :west, :north, :south, :top, :bottom)]   # no copy if already Float64
+    pre = (Tadv, TκH, TκVML, TκVdeep)
+    if all(isnothing, pre)
+        # all four operators to build: upload of ϕ, slab-wise assembly and copy-out overlap inside ONE call.
+        # nnz is data dependent: the arrays hold the upper bound N x (7,7,5,3,3); the matrices are their first nnz entries.
+        caps = N .* [7, 7, 5, 3, 3]
+        colptrs = [pinned(Int64, N + 1) for _ in 1:5]
+        rowvals = [pinned(Int64, caps[m]) for m in 1:5]
+        nzvals = [pinned(Float64, caps[m]) for m in 1:5]
+        prm = Ref(TMParams(κH, κVML, κVdeep, ρ isa Number ? Float64(ρ) : 0.0, upwind, 1, 0, 0))
+        nnzs = zeros(Int64, 5)
+        GC.@preserve faces colptrs rowvals nzvals ρ3 begin
+            check(c, ccall((:otmb_transportmatrix_stream, LIBOTMB), Cint,
+                           (PV, Ref{TMParams}, Ptr{PF}, PF, PF, Int32, PI, Ptr{PI}, Ptr{PI}, Ptr{PF}, PI),
+                           c.h, prm, pointer.(faces), ml, isnothing(ρ3) ? PF(C_NULL) : pointer(ρ3), 0, caps,
+                           pointer.(colptrs), pointer.(rowvals), pointer.(nzvals), nnzs))
+        end
+        # views of the first nnz entries, as plain Vectors over the same page-locked memory (kept alive by `keep`)
+        head(a, n) = (v = unsafe_wrap(Array, pointer(a), n; own = false); finalizer(_ -> (a; nothing), v); v)
+        csc(m) = SparseMatrixCSC{Float64, Int64}(N, N, colptrs[m], head(rowvals[m], nnzs[m]), head(nzvals[m], nnzs[m]))
+        return (; T = csc(1), Tadv = csc(2), TκH = csc(3), TκVML = csc(4), TκVdeep = csc(5))
     end
-    pre = (Tadv, TκH, TκVML, TκVdeep); mask = Int32(32)
+    # some operators were passed in pre-built (the reference's caching hook, :133-143): upload, build the rest, fetch
+    GC.@preserve faces check(c, ccall((:otmb_set_facefluxes, LIBOTMB), Cint, (PV, Ptr{PF}), c.h, pointer.(faces)))
+    check(c, ccall((:otmb_set_mlotst, LIBOTMB), Cint, (PV, PF), c.h, ml))
+    check(c, ccall((:otmb_set_rho3d, LIBOTMB), Cint, (PV, PF), c.h, isnothing(ρ3) ? PF(C_NULL) : pointer(ρ3)))
+    mask = Int32(32)
     for (m, A) in enumerate(pre)
         if isnothing(A)
             mask |= Int32(1) << m
         else
-            check(c, ccall((:otmb_set_operator, LIBOTMB), Cint, (Ptr{Cvoid}, Cint, Int64, Ptr{Int64}, Ptr{Int64}, P, Int32),
-                c.h, m, nnz(A), A.colptr, A.rowval, A.nzval, 1))
+            check(c, ccall((:otmb_set_operator, LIBOTMB), Cint, (PV, Cint, Int64, PI, PI, PF, Int32),
+                           c.h, m, nnz(A), A.colptr, A.rowval, A.nzval, 1))
         end
     end
     prm = Ref(TMParams(κH, κVML, κVdeep, ρ isa Number ? Float64(ρ) : 0.0, upwind, 1, 0, mask))
     nnzs = zeros(Int64, 5)
-    check(c, ccall((:otmb_transportmatrix_build, LIBOTMB), Cint, (Ptr{Cvoid}, Ref{TMParams}, Ptr{Int64}), c.h, prm, nnzs))
-    # one pipelined fetch for every matrix that was built (otmb_transportmatrix_fetch_all: Int32 indices on the PCIe
-    # link, widened into these Int64 vectors by host threads while the values are in flight)
+    check(c, ccall((:otmb_transportmatrix_build, LIBOTMB), Cint, (PV, Ref{TMParams}, PI), c.h, prm, nnzs))
     want = [true, isnothing(Tadv), isnothing(TκH), isnothing(TκVML), isnothing(TκVdeep)]
-    colptrs = [want[m] ? Vector{Int64}(undef, N + 1) : Int64[] for m in 1:5]
-    rowvals = [want[m] ? Vector{Int64}(undef, nnzs[m]) : Int64[] for m in 1:5]
-    nzvals = [want[m] ? Vector{Float64}(undef, nnzs[m]) : Float64[] for m in 1:5]
+    colptrs = [want[m] ? pinned(Int64, N + 1) : Int64[] for m in 1:5]
+    rowvals = [want[m] ? pinned(Int64, nnzs[m]) : Int64[] for m in 1:5]
+    nzvals = [want[m] ? pinned(Float64, nnzs[m]) : Float64[] for m in 1:5]
     fmask = Cint(sum(want[m] ? 1 << (m - 1) : 0 for m in 1:5))
     GC.@preserve colptrs rowvals nzvals begin
-        pc = [want[m] ? pointer(colptrs[m]) : Ptr{Int64}(C_NULL) for m in 1:5]
-        pr = [want[m] ? pointer(rowvals[m]) : Ptr{Int64}(C_NULL) for m in 1:5]
-        pv = [want[m] ? pointer(nzvals[m]) : Ptr{Float64}(C_NULL) for m in 1:5]
-        check(c, ccall((:otmb_transportmatrix_fetch_all, LIBOTMB), Cint, (Ptr{Cvoid}, Cint, Ptr{Ptr{Int64}}, Ptr{Ptr{Int64}}, Ptr{Ptr{Float64}}),
-                       c.h, fmask, pc, pr, pv))
+        pc = [want[m] ? pointer(colptrs[m]) : PI(C_NULL) for m in 1:5]
+        pr = [want[m] ? pointer(rowvals[m]) : PI(C_NULL) for m in 1:5]
+        pv = [want[m] ? pointer(nzvals[m]) : PF(C_NULL) for m in 1:5]
+        check(c, ccall((:otmb_transportmatrix_fetch_all, LIBOTMB), Cint, (PV, Cint, Ptr{PI}, Ptr{PI}, Ptr{PF}), c.h, fmask, pc, pr, pv))
     end
     csc(m) = SparseMatrixCSC{Float64, Int64}(N, N, colptrs[m], rowvals[m], nzvals[m])   # already sorted, 1-based: no copy
-    T = csc(1)
-    Tadv = isnothing(Tadv) ? csc(2) : Tadv
-    TκH = isnothing(TκH) ? csc(3) : TκH
-    TκVML = isnothing(TκVML) ? csc(4) : TκVML
-    TκVdeep = isnothing(TκVdeep) ? csc(5) : TκVdeep
-    return (; T, Tadv, TκH, TκVML, TκVdeep)
+    return (; T = csc(1), Tadv = something(Tadv, want[2] ? csc(2) : nothing), TκH = something(TκH, want[3] ? csc(3) : nothing),
+              TκVML = something(TκVML, want[4] ? csc(4) : nothing), TκVdeep = something(TκVdeep, want[5] ? csc(5) : nothing))
 end
 
-# ---- velocities <-> mass fluxes (src/velocities.jl:10-108, 140-151).  The Arakawa-grid detection and the
-# C/A/B dispatch of interpolateontodefaultCgrid (src/gridcellgeometry.jl:50-140) are host work on one cell and
-# keep their Julia code; only the B-grid stencil and the per-cell conversion run on the GPU.
+"y = X*x (or X'*x) with X the RESIDENT result matrix `which` (:T, :Tadv, :TκH, :TκVML, :TκVdeep) of the last transportmatrix
+call: the products of the reference's conservation checks (test/online.jl:110-115) without moving the matrix"
+function resident_matvec(which::Symbol, x::Vector{Float64}; transpose = false)
+    c = ctx(); y = similar(x)
+    m = findfirst(==(which), (:T, :Tadv, :TκH, :TκVML, :TκVdeep)) - 1
+    check(c, ccall((:otmb_spmv, LIBOTMB), Cint, (PV, Cint, Cint, PF, PF), c.h, m, transpose ? 1 : 0, x, y))
+    return y
+end
+
+# ------------------------------------------------------------------------------------------------------------------
+# velocities <-> mass fluxes (src/velocities.jl:10-108, 140-151).  The Arakawa-grid detection and the C/A/B dispatch
+# (src/gridcellgeometry.jl:50-140) are host work on one cell: the package's own `getarakawagrid` decides, only the
+# B-grid stencil and the per-cell conversions run on the GPU.
+# ------------------------------------------------------------------------------------------------------------------
 function bgrid_to_cgrid(u::Array{Float64, 3}, v::Array{Float64, 3}, fill)
     c = ctx(); u2 = similar(u); v2 = similar(v)
-    check(c, ccall((:otmb_bgrid_to_cgrid, LIBOTMB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}, Ptr{Float64}),
-                   c.h, u, v, fill, u2, v2))
+    check(c, ccall((:otmb_bgrid_to_cgrid, LIBOTMB), Cint, (PV, PF, PF, Float64, PF, PF), c.h, u, v, Float64(fill), u2, v2))
     return u2, v2
 end
-function _velflux(sym, a::Array{Float64, 3}, b::Array{Float64, 3}, ρ)
+function oncgrid(u, u_lon, u_lat, v, v_lon, v_lat, gridmetrics)
+    grid = REF.getarakawagrid(u_lon, u_lat, v_lon, v_lat, gridmetrics)                # src/gridcellgeometry.jl:50-95
+    grid isa REF.CGridCell && return Array{Float64}(u |> Array), Array{Float64}(v |> Array)                  # :104
+    if grid isa REF.BGridCell && grid.u_pos == grid.v_pos == :NE
+        ensure_metrics(ctx(), gridmetrics)
+        return bgrid_to_cgrid(Array{Float64}(u |> Array), Array{Float64}(v |> Array), u.properties["_FillValue"])   # :118-128
+    end
+    # A-grid, other B-grid layouts: the package's own method raises its own error (:105, :109)
+    r = REF.interpolateontodefaultCgrid(u, u_lon, u_lat, v, v_lon, v_lat, gridmetrics, grid)
+    return Array{Float64}(r[1]), Array{Float64}(r[4])
+end
+function _velflux(sym, a::Array{Float64, 3}, b::Array{Float64, 3}, gridmetrics, ρ)
     c = ctx(); oa = similar(a); ob = similar(b)
-    ρ3 = ρ isa Number ? Ptr{Float64}(C_NULL) : pointer(ρ)
-    GC.@preserve ρ check(c, ccall((sym, LIBOTMB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}, Ptr{Float64}),
-                                  c.h, a, b, ρ3, ρ isa Number ? Float64(ρ) : 0.0, oa, ob))
+    ensure_metrics(c, gridmetrics)
+    ρ3 = ρ isa Number ? nothing : Array{Float64}(ρ)
+    GC.@preserve ρ3 check(c, ccall((sym, LIBOTMB), Cint, (PV, PF, PF, PF, Float64, PF, PF),
+                                   c.h, a, b, isnothing(ρ3) ? PF(C_NULL) : pointer(ρ3), ρ isa Number ? Float64(ρ) : 0.0, oa, ob))
     return oa, ob
 end
 function velocity2fluxes(u, u_lon, u_lat, v, v_lon, v_lat, gridmetrics, ρ)          # src/velocities.jl:10-39
-    u, _, _, v, _, _ = interpolateontodefaultCgrid(u, u_lon, u_lat, v, v_lon, v_lat, gridmetrics)   # host dispatch, B-grid -> bgrid_to_cgrid
-    return _velflux(:otmb_velocity2fluxes, Array{Float64}(u), Array{Float64}(v), ρ)
+    uc, vc = oncgrid(u, u_lon, u_lat, v, v_lon, v_lat, gridmetrics)
+    return _velflux(:otmb_velocity2fluxes, uc, vc, gridmetrics, ρ)
 end
-fluxes2velocity(ϕᵢ, ϕⱼ, gridmetrics, ρ) = _velflux(:otmb_fluxes2velocity, Array{Float64}(ϕᵢ), Array{Float64}(ϕⱼ), ρ)   # :50-74
+fluxes2velocity(ϕᵢ, ϕⱼ, gridmetrics, ρ) = _velflux(:otmb_fluxes2velocity, Array{Float64}(ϕᵢ), Array{Float64}(ϕⱼ), gridmetrics, ρ)   # :50-74
 function facefluxesfromvelocities(; uo, uo_lon, uo_lat, vo, vo_lon, vo_lat, gridmetrics, indices, ρ)   # :140-151
     FillValue = uo.properties["_FillValue"]
     @assert isequal(FillValue, vo.properties["_FillValue"])
@@ -214,21 +295,120 @@ function facefluxesfromvelocities(; uo, uo_lon, uo_lat, vo, vo_lon, vo_lat, grid
     return facefluxes(umo, vmo, gridmetrics, indices; FillValue)
 end
 
-# ---- lump_and_spray, src/extratools.jl:38-112.  Default mask: on the device; a custom mask makes the reference's
-# sweep greedy and data dependent, so that case keeps the reference's Julia body (not repeated here).
+# ------------------------------------------------------------------------------------------------------------------
+# Redi/GM helpers (experimental and non-exported in the reference): fields, not matrices
+# ------------------------------------------------------------------------------------------------------------------
+"globalverticalfacetriadderivative, src/triads.jl:134-146; dir = :I or :J (Icoord / Jcoord)"
+function globalverticalfacetriadderivative(χ, gridmetrics, indices, dir::Symbol)
+    c = ctx(); ensure_metrics(c, gridmetrics)
+    chi = Array{Float64}(χ); out = similar(chi)
+    check(c, ccall((:otmb_triad_derivative, LIBOTMB), Cint, (PV, PF, Cint, PF), c.h, chi, dir === :I ? 0 : 1, out))
+    return out
+end
+"globalverticaldyadderivative, src/dyads.jl:66-78"
+function globalverticaldyadderivative(χ, gridmetrics, indices)
+    c = ctx(); ensure_metrics(c, gridmetrics)
+    chi = Array{Float64}(χ); out = similar(chi)
+    check(c, ccall((:otmb_dyad_derivative, LIBOTMB), Cint, (PV, PF, PF), c.h, chi, out))
+    return out
+end
+"bolus_GM_velocity, src/RediGM.jl:46-79"
+function bolus_GM_velocity(ρ, gridmetrics, indices; κGM = 600, maxslope = 0.01)
+    c = ctx(); ensure_metrics(c, gridmetrics)
+    rho = Array{Float64}(ρ); u = similar(rho); v = similar(rho)
+    check(c, ccall((:otmb_bolus_gm_velocity, LIBOTMB), Cint, (PV, PF, Float64, Float64, PF, PF), c.h, rho, Float64(κGM), Float64(maxslope), u, v))
+    return u, v
+end
+
+# ------------------------------------------------------------------------------------------------------------------
+# lump_and_spray, src/extratools.jl:38-112.  Default mask: on the device; a custom mask makes the reference's sweep
+# greedy and data dependent, so that case is handed to the package's own function.
+# ------------------------------------------------------------------------------------------------------------------
 function lump_and_spray(wet3D, vol, T::SparseMatrixCSC{Float64, Int64}, mask = trues(size(wet3D)); di = 2, dj = 2, dk = 1)
-    all(mask) || error("lump_and_spray with a custom mask: use the reference implementation")
+    all(mask) || return REF.lump_and_spray(wet3D, vol, T, mask; di, dj, dk)
     c = ctx(); N = length(vol); Nc = Ref{Int64}(0)
-    check(c, ccall((:otmb_lump_and_spray_build, LIBOTMB), Cint,
-                   (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Int32, Int32, Ref{Int64}),
+    check(c, ccall((:otmb_lump_and_spray_build, LIBOTMB), Cint, (PV, Int64, Int64, Int64, PF, PI, PI, Int32, Int32, Ref{Int64}),
                    c.h, di, dj, dk, vol, T.colptr, T.rowval, 1, 1, Nc))
     lcp = Vector{Int64}(undef, N + 1); lrv = Vector{Int64}(undef, N); lnz = Vector{Float64}(undef, N)
     scp = Vector{Int64}(undef, Nc[] + 1); srv = Vector{Int64}(undef, N); snz = Vector{Float64}(undef, N)
     vol_c = Vector{Float64}(undef, Nc[])
-    check(c, ccall((:otmb_lump_and_spray_fetch, LIBOTMB), Cint,
-                   (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}),
-                   c.h, lcp, lrv, lnz, scp, srv, snz, vol_c))
+    check(c, ccall((:otmb_lump_and_spray_fetch, LIBOTMB), Cint, (PV, PI, PI, PF, PI, PI, PF, PF), c.h, lcp, lrv, lnz, scp, srv, snz, vol_c))
     return SparseMatrixCSC(Nc[], N, lcp, lrv, lnz), SparseMatrixCSC(N, Nc[], scp, srv, snz), vol_c
 end
+
+# ------------------------------------------------------------------------------------------------------------------
+# ONE matrix sharded over the GPUs of a box (include/otmb.h, "ONE matrix sharded across the GPUs"): one Julia process
+# per GPU (e.g. under mpiexec), the exchanges run inside the library over NCCL.  The host program only has to hand every
+# rank the same 128-byte id, e.g. with MPI.jl:
+#     id = rank == 0 ? Sharded.unique_id() : zeros(UInt8, 128);  MPI.Bcast!(id, 0, comm)
+#     s  = Sharded.setup(gridmetrics; rank, nranks, id, device = rank)
+#     Sharded.facefluxes!(s, umo, vmo, FillValue);  seg = Sharded.transportmatrix(s; mlotst, ρ)
+# `seg.X` holds this rank's columns [w0+1, w0+ncols] of matrix X: colptr with GLOBAL entry offsets (1-based), rowval with
+# global row indices, nzval; the ranks' (colptr[1:end-1], rowval, nzval) concatenate to the SparseMatrixCSC fields.
+# ------------------------------------------------------------------------------------------------------------------
+module Sharded
+import ..LIBOTMB, ..Context, ..check, ..topotag, ..TMParams, ..PF, ..PI, ..PV
+
+unique_id() = (id = zeros(UInt8, 128); ccall((:otmb_comm_unique_id, LIBOTMB), Cint, (Ptr{UInt8},), id) == 0 || error("NCCL unavailable"); id)
+
+struct Slab
+    c::Context
+    rank::Int; nranks::Int
+    rows::Tuple{Int64, Int64}     # owned grid rows [row0, row1), row = (j-1) + ny*(k-1)
+    N::Int64; w0::Int64; ncols::Int64
+end
+
+function setup(gridmetrics; rank::Integer, nranks::Integer, id::Vector{UInt8}, device::Integer = rank, level_cuts_only = false)
+    v3D = Array{Float64}(gridmetrics.v3D); nx, ny, nz = size(v3D)
+    cuts = zeros(Int64, nranks + 1)
+    st = ccall((:otmb_plan_slabs, LIBOTMB), Cint, (PF, Int64, Int64, Int64, Int32, Int32, PI, PI), v3D, nx, ny, nz, nranks, level_cuts_only, cuts, C_NULL)
+    st == 0 || error("otmb_plan_slabs: more ranks than grid rows / levels")
+    c = Context(device)
+    check(c, ccall((:otmb_set_grid, LIBOTMB), Cint, (PV, Int64, Int64, Int64, Cint), c.h, nx, ny, nz, topotag(gridmetrics.gridtopology)))
+    check(c, ccall((:otmb_set_slab_rows, LIBOTMB), Cint, (PV, Int64, Int64), c.h, cuts[rank + 1], cuts[rank + 2]))
+    check(c, ccall((:otmb_comm_init, LIBOTMB), Cint, (PV, Int32, Int32, Ptr{UInt8}), c.h, nranks, rank, id))
+    N, w0, own = Ref{Int64}(0), Ref{Int64}(0), Ref{Int64}(0)
+    check(c, ccall((:otmb_sharded_makeindices, LIBOTMB), Cint, (PV, PF, Ref{Int64}, Ref{Int64}, Ref{Int64}), c.h, v3D, N, w0, own))
+    dirs = (:south, :east, :north, :west)
+    edge = cat((gridmetrics.edge_length_2D[d] for d in dirs)...; dims = 3)
+    dnbr = cat((gridmetrics.distance_to_neighbour_2D[d] for d in dirs)...; dims = 3)
+    check(c, ccall((:otmb_set_gridmetrics, LIBOTMB), Cint, (PV, PF, PF, PF, PF, PF, PF, PF, PF),
+                   c.h, gridmetrics.area2D, gridmetrics.thkcello, gridmetrics.zt, edge, dnbr, C_NULL, C_NULL, C_NULL))
+    return Slab(c, rank, nranks, (cuts[rank + 1], cuts[rank + 2]), N[], w0[], own[])
+end
+
+"the chunk-pipelined continuity chain (src/velocities.jl:234-243) over all ranks; ϕ stays resident on each rank's slab"
+function facefluxes!(s::Slab, umo::Array{Float64, 3}, vmo::Array{Float64, 3}, FillValue; nchunks = 0)
+    check(s.c, ccall((:otmb_set_masstransport, LIBOTMB), Cint, (PV, PF, PF, Float64), s.c.h, umo, vmo, Float64(FillValue)))
+    check(s.c, ccall((:otmb_sharded_facefluxes, LIBOTMB), Cint, (PV, Int32, PF, PF, PF, PF, PF, PF), s.c.h, nchunks,
+                     C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL))
+end
+
+function transportmatrix(s::Slab; mlotst, ρ, κH = 500.0, κVML = 0.1, κVdeep = 1.0e-5, upwind = true)
+    c = s.c
+    ml = Array{Float64}(replace(mlotst |> Array, missing => NaN))
+    check(c, ccall((:otmb_set_mlotst, LIBOTMB), Cint, (PV, PF), c.h, ml))
+    ρ3 = ρ isa Number ? nothing : Array{Float64}(ρ)
+    GC.@preserve ρ3 check(c, ccall((:otmb_set_rho3d, LIBOTMB), Cint, (PV, PF), c.h, isnothing(ρ3) ? PF(C_NULL) : pointer(ρ3)))
+    prm = Ref(TMParams(κH, κVML, κVdeep, ρ isa Number ? Float64(ρ) : 0.0, upwind, 1, 0, 0))
+    loc, before, total = zeros(Int64, 5), zeros(Int64, 5), zeros(Int64, 5)
+    check(c, ccall((:otmb_sharded_transportmatrix_build, LIBOTMB), Cint, (PV, Ref{TMParams}, PI, PI, PI), c.h, prm, loc, before, total))
+    seg(m) = begin
+        cp = Vector{Int64}(undef, s.ncols + 1); rv = Vector{Int64}(undef, loc[m]); nz = Vector{Float64}(undef, loc[m])
+        check(c, ccall((:otmb_transportmatrix_fetch, LIBOTMB), Cint, (PV, Cint, PI, PI, PF), c.h, m - 1, cp, rv, nz))
+        (; colptr = cp .+ before[m], rowval = rv, nzval = nz)
+    end
+    return (; T = seg(1), Tadv = seg(2), TκH = seg(3), TκVML = seg(4), TκVdeep = seg(5), N = s.N, w0 = s.w0, nnz_total = total)
+end
+
+"position-dependent checksums (colptr, rowval, nzval bits) of this rank's segment of matrix m (0-based): the ranks' sums equal the 1-GPU matrix's"
+function checksum(s::Slab, m::Integer, entry_offset::Integer)
+    out = zeros(UInt64, 3)
+    check(s.c, ccall((:otmb_result_checksum, LIBOTMB), Cint, (PV, Cint, Int64, Int64, Ptr{UInt64}), s.c.h, m, s.w0, entry_offset, out))
+    return out
+end
+
+close(s::Slab) = ccall((:otmb_comm_free, LIBOTMB), Cint, (PV,), s.c.h)
+end # module Sharded
 
 end # module

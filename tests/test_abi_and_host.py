@@ -149,3 +149,28 @@ def test_host_widening_of_the_fetch_pipeline(threads):
             assert np.array_equal(dst, src.astype(np.int64))
             assert (buf[:shift] == -99).all() and (buf[shift + n:] == -99).all()      # nothing written outside
     assert lib.otmb_host_widen(None, None, -1, 0) != 0
+
+
+def _abi_driver(tmp_path):
+    exe = tmp_path / "abi_driver"
+    r = subprocess.run(["gcc", "-O1", "-Wall", "-Werror", "-o", str(exe), str(ROOT / "tests" / "abi_driver.c"), "-ldl", "-lm"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return subprocess.run([str(exe), str(_lib.LIB_PATH)], capture_output=True, text=True, timeout=120)
+
+
+def test_c_driver_resolves_the_abi_and_fails_loudly_without_a_gpu(tmp_path):
+    """tests/abi_driver.c: the ABI from plain C (dlopen).  Here (no GPU) it must resolve every symbol it needs and
+    report the missing GPU as OTMB_ERR_NO_GPU; on the GPU box the same program checks a hand-derived matrix."""
+    n = C.c_int(-1)
+    _lib.load().otmb_device_count(C.byref(n))
+    if n.value > 0:
+        pytest.skip("a GPU is present: covered by test_c_driver_on_gpu")
+    r = _abi_driver(tmp_path)
+    assert r.returncode == 0 and "ABI-DRIVER: no GPU" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_c_driver_on_gpu(tmp_path):
+    r = _abi_driver(tmp_path)
+    assert r.returncode == 0 and "ABI-DRIVER: OK" in r.stdout, r.stdout + r.stderr
