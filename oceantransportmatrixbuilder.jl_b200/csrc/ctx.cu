@@ -12,26 +12,6 @@
 
 namespace {
 
-// one warp per 64-cell word: two coalesced loads per lane, two ballots -> the chunk
-// (v3D, mask, wcount are window-biased pointers indexed by global cell / word; cells outside [L0, L1) read as dry)
-__global__ void __launch_bounds__(256) k_wetmask(const double* __restrict__ v3D, i64 L0, i64 L1, u64* __restrict__ mask,
-                                                 uint32_t* __restrict__ wcount, i64 word0, i64 word1) {
-    const int lane = threadIdx.x & 31;
-    const i64 gw = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
-    for (i64 w = word0 + gw; w < word1; w += nwarps) {
-        const i64 a = w * 64 + lane, b = a + 32;
-        const double va = (a >= L0 && a < L1) ? __ldg(v3D + a) : __longlong_as_double(0x7ff8000000000000ll);
-        const double vb = (b >= L0 && b < L1) ? __ldg(v3D + b) : __longlong_as_double(0x7ff8000000000000ll);
-        const unsigned lo = __ballot_sync(0xffffffffu, !isnan(va));
-        const unsigned hi = __ballot_sync(0xffffffffu, !isnan(vb));
-        if (lane == 0) {
-            mask[w] = (u64)lo | ((u64)hi << 32);
-            wcount[w] = (uint32_t)(__popc(lo) + __popc(hi));
-        }
-    }
-}
-
 __global__ void __launch_bounds__(256) k_fill_indices(const u64* __restrict__ mask, const uint32_t* __restrict__ wpre,
                                                       i64 M, i64* __restrict__ Lwet, i64* __restrict__ Lwet3D) {
     const i64 L = (i64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -52,6 +32,100 @@ __global__ void __launch_bounds__(256) k_fill_lwet32(const u64* __restrict__ mas
     // the reference's Lwet3D (0-based, -1 = missing), src/matrixbuilding.jl:18-20; global rank when sharded
     rank3d[L] = wet ? r + rank_offset : -1;
     if (wet) lwet[r] = (int)L;
+}
+
+// makeindices in ONE pass (src/matrixbuilding.jl:10-24): wet mask (ballots -> the BitArray chunks), wet count per chunk,
+// exclusive scan over the whole grid (decoupled look-back over the blocks, one counter) and — when the wet-rank offset is
+// already known (FILL: unsharded contexts) — Lwet3D (`rank3d`, -1 = dry) and the compacted wet list, all from the one read
+// of v3D.  A block owns 32 chunks = 2048 cells (8 warps x 4 chunks); blocks publish in index order.
+// Algorithmic bytes: read 8 per cell; write 1/8 + 1/16 per cell, and with FILL 4 per cell + 4 per wet cell.
+constexpr int MI_WPW = 4, MI_WARPS = 8, MI_WORDS = MI_WPW * MI_WARPS;
+template <bool FILL>
+__global__ void __launch_bounds__(32 * MI_WARPS) k_makeindices(const double* __restrict__ v3D, i64 L0, i64 L1, i64 word0, i64 word1,
+                                                               u64* __restrict__ mask, uint32_t* __restrict__ wpre,
+                                                               int* __restrict__ rank3d, int* __restrict__ lwet, int rank_offset,
+                                                               u64* __restrict__ desc, u64* __restrict__ total) {
+    constexpr u64 AGG = 1ull << 62, PRE = 2ull << 62, VAL = (1ull << 62) - 1;
+    __shared__ unsigned s_wtot[MI_WARPS];
+    __shared__ unsigned s_base;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const i64 wfirst = word0 + (i64)blockIdx.x * MI_WORDS + wid * MI_WPW;
+    unsigned lo[MI_WPW], hi[MI_WPW], cnt[MI_WPW];
+    const double dry = __longlong_as_double(0x7ff8000000000000ll);
+    double va[MI_WPW], vb[MI_WPW];
+#pragma unroll
+    for (int q = 0; q < MI_WPW; ++q) {   // all eight loads of a lane in flight at once
+        const i64 a = (wfirst + q) * 64 + lane, b = a + 32;
+        va[q] = (wfirst + q < word1 && a >= L0 && a < L1) ? __ldg(v3D + a) : dry;
+        vb[q] = (wfirst + q < word1 && b >= L0 && b < L1) ? __ldg(v3D + b) : dry;
+    }
+    unsigned wsum = 0;
+#pragma unroll
+    for (int q = 0; q < MI_WPW; ++q) {
+        lo[q] = __ballot_sync(0xffffffffu, !isnan(va[q]));
+        hi[q] = __ballot_sync(0xffffffffu, !isnan(vb[q]));
+        cnt[q] = __popc(lo[q]) + __popc(hi[q]);
+        wsum += cnt[q];
+    }
+    if (lane == 0) s_wtot[wid] = wsum;
+    __syncthreads();
+    if (wid == 0) {   // block total -> publish -> look back over the lower blocks, 32 at a time
+        unsigned tot = 0;
+#pragma unroll
+        for (int q = 0; q < MI_WARPS; ++q) tot += s_wtot[q];
+        const int b = blockIdx.x;
+        if (lane == 0) {
+            const u64 d = (b == 0 ? PRE : AGG) | (u64)tot;
+            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(desc + b), "l"(d) : "memory");
+        }
+        u64 excl = 0;
+        int look = b - 1;
+        while (look >= 0) {
+            const int t = look - lane;
+            u64 v = PRE;   // before the first block: prefix 0
+            if (t >= 0) do {
+                    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(desc + t) : "memory");
+                } while ((v >> 62) == 0);
+            const unsigned pm = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+            const int first = pm ? __ffs(pm) - 1 : 32;
+            u64 part = lane <= first ? (v & VAL) : 0ull;   // aggregates up to and including the first inclusive prefix
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            excl += part;
+            if (pm) break;
+            look -= 32;
+        }
+        if (lane == 0) {
+            if (b > 0) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(desc + b), "l"(PRE | (excl + tot)) : "memory");
+            s_base = (unsigned)excl;
+            if (b == (int)gridDim.x - 1) *total = excl + tot;
+        }
+    }
+    __syncthreads();
+    unsigned pre = s_base;
+#pragma unroll
+    for (int q = 0; q < MI_WARPS; ++q) pre += q < wid ? s_wtot[q] : 0u;
+#pragma unroll
+    for (int q = 0; q < MI_WPW; ++q) {
+        const i64 w = wfirst + q;
+        if (w < word1) {
+            if (lane == 0) {
+                mask[w] = (u64)lo[q] | ((u64)hi[q] << 32);
+                wpre[w] = pre;
+            }
+            if (FILL) {
+                const i64 a = w * 64 + lane, b = a + 32;
+                const unsigned below = (1u << lane) - 1u;
+                const int ra = (int)(pre + __popc(lo[q] & below)), rb = (int)(pre + __popc(lo[q]) + __popc(hi[q] & below));
+                const bool wa = lo[q] >> lane & 1u, wb = hi[q] >> lane & 1u;
+                if (a >= L0 && a < L1) rank3d[a] = wa ? ra + rank_offset : -1;
+                if (b >= L0 && b < L1) rank3d[b] = wb ? rb + rank_offset : -1;
+                if (wa) lwet[ra] = (int)a;
+                if (wb) lwet[rb] = (int)b;
+            }
+        }
+        pre += cnt[q];
+    }
 }
 
 __global__ void k_l2_flush(uint4* __restrict__ buf, i64 n) {
@@ -325,21 +399,31 @@ int otmb_makeindices(otmb_ctx* c, const double* v3D, int64_t* N) {
     const i64 word0 = c->L_win0 >> 6, word1 = (c->L_win1 + 63) >> 6;
     c->nwords = word1 - word0;
     CU_TRY(c, c->mask.ensure((size_t)(c->nwords + 1) * 8));
-    CU_TRY(c, c->wcount.ensure((size_t)(c->nwords + 1) * 4));
     CU_TRY(c, c->wpre.ensure((size_t)(c->nwords + 1) * 4));
-    const int blocks = (int)std::min<i64>((c->nwords + 7) / 8, (i64)c->sm_count * 16);
-    k_wetmask<<<blocks > 0 ? blocks : 1, 256, 0, c->stream>>>(c->win<double>(c->v3D), c->L_win0, c->L_win1, c->mask_win(),
-                                                              c->wcount.as<uint32_t>() - word0, word0, word1);
+    // one pass: mask, per-chunk prefix, and (unsharded: the rank offset is 0) Lwet3D + the wet list
+    const int blocks = (int)((c->nwords + MI_WORDS - 1) / MI_WORDS);
+    CU_TRY(c, c->scan_tmp.ensure((size_t)(blocks + 1) * 8));
+    CU_TRY(c, cudaMemsetAsync(c->scan_tmp.p, 0, (size_t)(blocks + 1) * 8, c->stream));
+    OT_TRY(otmb_reset_flags(c));
+    c->h_up = 0;
+    c->w0 = 0;
+    if (!c->sharded) {
+        // the wet list cannot be longer than the window; N is only known afterwards
+        CU_TRY(c, c->lwet.ensure((c->win_cells() + 1) * 4));
+        CU_TRY(c, c->rank3d.ensure((c->win_cells() + 1) * 4));
+        k_makeindices<true><<<blocks, 32 * MI_WARPS, 0, c->stream>>>(c->win<double>(c->v3D), c->L_win0, c->L_win1, word0, word1, c->mask_win(),
+                                                                      c->wpre_win(), c->win<int>(c->rank3d), c->lwet.as<int>(), 0,
+                                                                      c->scan_tmp.as<u64>(), &c->flags.as<DevFlags>()->nnz[0]);
+    } else {
+        k_makeindices<false><<<blocks, 32 * MI_WARPS, 0, c->stream>>>(c->win<double>(c->v3D), c->L_win0, c->L_win1, word0, word1, c->mask_win(),
+                                                                       c->wpre_win(), nullptr, nullptr, 0, c->scan_tmp.as<u64>(),
+                                                                       &c->flags.as<DevFlags>()->nnz[0]);
+    }
     LAUNCHED(c);
     CU_TRY(c, cudaGetLastError());
-    OT_TRY(otmb_reset_flags(c));
-    OT_TRY(otmb_scan_u32(c, c->wcount.as<uint32_t>(), c->wpre.as<uint32_t>(), c->nwords,
-                         &c->flags.as<DevFlags>()->nnz[0]));
     OT_TRY(otmb_fetch_flags(c));
     c->N = (i64)c->h_flags->nnz[0];
-    c->h_up = 0;
     c->ncols = c->N;
-    c->w0 = 0;
     if (c->sharded) {
         i64 below_own = 0, below_end = 0;
         OT_TRY(wet_below(c, c->L_own0, &below_own));
@@ -348,8 +432,7 @@ int otmb_makeindices(otmb_ctx* c, const double* v3D, int64_t* N) {
         c->ncols = below_end - below_own;
         c->have_rank_offset = false;   // global ranks need otmb_set_rank_offset (sum of the lower ranks' counts)
     } else {
-        // compacted wet list (0-based linear index per wet rank) and Lwet3D for the thread-per-wet-cell kernels
-        OT_TRY(fill_ranks(c));
+        c->have_rank_offset = true;   // Lwet3D and the wet list were filled by the same pass
     }
     c->have_indices = true;
     c->level_cum.clear();

@@ -8,6 +8,8 @@
 // Threads are consecutive in i, so every load/store of a level is a coalesced row segment;
 // the west/south operands are the east/north values of the i-1 / j-1 columns re-read through
 // L1 (same or adjacent cache lines).  The wet tests use the packed bit mask.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -136,7 +138,14 @@ int otmb_faceflux_begin(otmb_ctx* c, double fill) {
 int otmb_faceflux_columns(otmb_ctx* c, double fill, i64 p_begin, i64 p_end, const double* d_in, double* d_out) {
     if (p_end <= p_begin) return OTMB_OK;
     GridDims g{(int)c->nx, (int)c->ny, (int)c->nz, c->topo, (int)c->P, (int)c->M};
-    k_faceflux<5><<<grid_for(p_end - p_begin, 128), 128, 0, c->stream>>>(
+    // One thread per column: a 1-degree grid has only 108 000 of them (a third of the GPU's thread slots), so each keeps
+    // ten levels of loads in flight; with many columns (0.25 degree: 1.5 M) five are enough and leave more registers.
+    int unroll = (p_end - p_begin) < (i64)c->sm_count * 2048 ? 10 : 5;
+#ifdef OTMB_AB
+    if (const char* e = getenv("OTMB_FACEFLUX_UNROLL")) unroll = atoi(e);
+#endif
+    auto kern = unroll == 10 ? k_faceflux<10> : k_faceflux<5>;
+    kern<<<grid_for(p_end - p_begin, 128), 128, 0, c->stream>>>(
         c->win<double>(c->stage_a), c->win<double>(c->stage_b), c->mask_win(), g, fill,
         c->win<double>(c->phi[OTMB_FACE_EAST]), c->win<double>(c->phi[OTMB_FACE_WEST]), c->win<double>(c->phi[OTMB_FACE_NORTH]),
         c->win<double>(c->phi[OTMB_FACE_SOUTH]), c->win<double>(c->phi[OTMB_FACE_TOP]), c->win<double>(c->phi[OTMB_FACE_BOTTOM]),

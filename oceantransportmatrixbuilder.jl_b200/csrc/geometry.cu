@@ -11,20 +11,31 @@
 
 namespace {
 
-// K2: one thread per (i,j) column, sequential in k like cumsum(dims=3)
+// K2: one thread per (i,j) column, sequential in k like cumsum(dims=3).  There are only nx*ny threads (108 000 at 1
+// degree: a third of the GPU's thread slots), so each keeps UNROLL levels in flight: the loads of a batch are issued
+// before the first quotient is formed, the UNROLL divisions are independent, and only the running sum is serial.
+template <int UNROLL>
 __global__ void __launch_bounds__(128) k_metrics3d(const double* __restrict__ v3D, const double* __restrict__ area2D, int P,
                                                    int nz, double* __restrict__ thk, double* __restrict__ Z3D) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
     const double a = __ldg(area2D + p);
     double zbot = 0.0;
-#pragma unroll 5
-    for (int k = 0; k < nz; ++k) {
-        const size_t L = (size_t)p + (size_t)P * k;
-        const double t = __ldg(v3D + L) / a;
-        thk[L] = t;
-        zbot = (k == 0) ? t : zbot + t;
-        Z3D[L] = zbot - 0.5 * t;
+    for (int k0 = 0; k0 < nz; k0 += UNROLL) {
+        double v[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) v[u] = k0 + u < nz ? __ldg(v3D + (size_t)p + (size_t)P * (k0 + u)) : 0.0;
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) v[u] = v[u] / a;                       // thkcello = v3D ./ area2D  (:283)
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            if (k0 + u >= nz) break;
+            const size_t L = (size_t)p + (size_t)P * (k0 + u);
+            const double t = v[u];
+            __stcs(thk + L, t);
+            zbot = (k0 + u == 0) ? t : zbot + t;                                // cumsum(thkcello, dims = 3)  (:284)
+            __stcs(Z3D + L, zbot - 0.5 * t);                                    // - 0.5 thkcello             (:285)
+        }
     }
 }
 
@@ -85,6 +96,9 @@ extern "C" int otmb_gridmetrics(otmb_ctx* c, const double* area2D, const double*
                                 double* edge, double* dedge, double* dnbr) {
     if (!c || !area2D || !lon || !lat || !lonv || !latv || !zt) return OTMB_ERR_BADARG;
     OT_TRY(otmb_need(c, c->have_indices, "otmb_makeindices"));
+    if (c->sharded)
+        return otmb_fail(c, OTMB_ERR_STATE, "otmb_gridmetrics needs the whole grid (Z3D is a top-down cumsum): compute the metrics on an "
+                                            "unsharded context and give the slab contexts otmb_set_gridmetrics");
     CU_TRY(c, cudaSetDevice(c->device));
     const size_t P8 = (size_t)c->P * 8, M8 = (size_t)c->M * 8;
     OT_TRY(upload(c, c->area2D, area2D, P8));
@@ -99,8 +113,8 @@ extern "C" int otmb_gridmetrics(otmb_ctx* c, const double* area2D, const double*
     CU_TRY(c, c->dedge.ensure(4 * P8));
     CU_TRY(c, c->dnbr.ensure(4 * P8));
     GridDims g{(int)c->nx, (int)c->ny, (int)c->nz, c->topo, (int)c->P, (int)c->M};
-    k_metrics3d<<<grid_for(c->P, 128), 128, 0, c->stream>>>(c->v3D.as<double>(), c->area2D.as<double>(), g.P, g.nz,
-                                                            c->thk.as<double>(), c->Z3D.as<double>());
+    k_metrics3d<10><<<grid_for(c->P, 128), 128, 0, c->stream>>>(c->v3D.as<double>(), c->area2D.as<double>(), g.P, g.nz,
+                                                                c->thk.as<double>(), c->Z3D.as<double>());
     LAUNCHED(c);
     CU_TRY(c, cudaGetLastError());
     c->have_z3d = true;
