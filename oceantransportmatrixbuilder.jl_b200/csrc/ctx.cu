@@ -37,9 +37,12 @@ __global__ void __launch_bounds__(256) k_fill_lwet32(const u64* __restrict__ mas
 // makeindices in ONE pass (src/matrixbuilding.jl:10-24): wet mask (ballots -> the BitArray chunks), wet count per chunk,
 // exclusive scan over the whole grid (decoupled look-back over the blocks, one counter) and — when the wet-rank offset is
 // already known (FILL: unsharded contexts) — Lwet3D (`rank3d`, -1 = dry) and the compacted wet list, all from the one read
-// of v3D.  A block owns 32 chunks = 2048 cells (8 warps x 4 chunks); blocks publish in index order.
+// of v3D.  A block owns MI_WORDS chunks of 64 cells (8 warps x MI_WPW chunks); blocks publish in index order.
 // Algorithmic bytes: read 8 per cell; write 1/8 + 1/16 per cell, and with FILL 4 per cell + 4 per wet cell.
-constexpr int MI_WPW = 4, MI_WARPS = 8, MI_WORDS = MI_WPW * MI_WARPS;
+#ifndef OTMB_MI_WPW
+#define OTMB_MI_WPW 4
+#endif
+constexpr int MI_WPW = OTMB_MI_WPW, MI_WARPS = 8, MI_WORDS = MI_WPW * MI_WARPS;
 template <bool FILL>
 __global__ void __launch_bounds__(32 * MI_WARPS) k_makeindices(const double* __restrict__ v3D, i64 L0, i64 L1, i64 word0, i64 word1,
                                                                u64* __restrict__ mask, uint32_t* __restrict__ wpre,

@@ -138,9 +138,9 @@ int otmb_faceflux_begin(otmb_ctx* c, double fill) {
 int otmb_faceflux_columns(otmb_ctx* c, double fill, i64 p_begin, i64 p_end, const double* d_in, double* d_out) {
     if (p_end <= p_begin) return OTMB_OK;
     GridDims g{(int)c->nx, (int)c->ny, (int)c->nz, c->topo, (int)c->P, (int)c->M};
-    // One thread per column: a 1-degree grid has only 108 000 of them (a third of the GPU's thread slots), so each keeps
-    // ten levels of loads in flight; with many columns (0.25 degree: 1.5 M) five are enough and leave more registers.
-    int unroll = (p_end - p_begin) < (i64)c->sm_count * 2048 ? 10 : 5;
+    // Five levels of loads in flight per column.  Ten were measured slower even on the 1-degree grid, where there are
+    // only 108 000 columns (74 us vs 121 us, profiles/README.md): the batch then no longer fits the registers.
+    int unroll = 5;
 #ifdef OTMB_AB
     if (const char* e = getenv("OTMB_FACEFLUX_UNROLL")) unroll = atoi(e);
 #endif

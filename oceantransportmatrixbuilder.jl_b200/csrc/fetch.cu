@@ -380,8 +380,10 @@ __global__ void k_level_prefix(const u64* __restrict__ mask, const uint32_t* __r
 struct Uploader {
     std::thread th;
     std::atomic<int> recorded{0};   // slabs whose upload has been enqueued and its event recorded
+    std::atomic<int> allowed{0};    // slabs the uploader may enqueue (pacing, see below)
     std::atomic<int> status{OTMB_OK};
     ~Uploader() {
+        allowed.store(1 << 30);   // never leave the thread waiting for its turn
         if (th.joinable()) th.join();
     }
 };
@@ -495,6 +497,8 @@ extern "C" int otmb_transportmatrix_stream(otmb_ctx* c, const otmb_tm_params* pr
         if (fail(cudaSetDevice(c->device))) return;
         if (fail(cudaMemcpyAsync(c->mlotst.p, mlotst, (size_t)c->P * 8, cudaMemcpyHostToDevice, f->s_up))) return;
         for (int s = 0; s < S; ++s) {
+            while (up.allowed.load(std::memory_order_acquire) <= s && up.status.load() == OTMB_OK) _mm_pause();
+            if (up.status.load() != OTMB_OK) return;
             const size_t a = (size_t)cut[s] * c->P, n = (size_t)(cut[s + 1] - cut[s]) * c->P;
             for (int q = 0; q < 6; ++q)
                 if (fail(cudaMemcpyAsync(c->phi[q].as<double>() + a, phi[q] + a, n * 8, cudaMemcpyHostToDevice, f->s_up))) return;
@@ -513,6 +517,16 @@ extern "C" int otmb_transportmatrix_stream(otmb_ctx* c, const otmb_tm_params* pr
 #else
     auto mark = [](const char*) {};
 #endif
+    // Pacing of the uploads.  With both directions busy the link moves about 72 GB/s in total (57 GB/s one way), and the
+    // copy-out is 2.7 times the upload: uploading everything as fast as possible finishes the upload early and leaves the
+    // copy-out alone on a half-used link for the rest of the call.  So the uploader stays only `lead` slabs ahead of the
+    // copy-out that has been issued, which spreads the upload over the whole call.
+    int lead = 3;
+#ifdef OTMB_AB
+    if (const char* e = getenv("OTMB_STREAM_LEAD")) lead = atoi(e);
+#endif
+    lead = std::max(lead, 2);   // slab s is launched once slab s+1 has been uploaded
+    up.allowed.store(std::min(S, lead), std::memory_order_release);
     // ---- event loop: launch slabs as their inputs are enqueued, send results out as slabs complete, do the host half
     int launched = 0, issued = 0;
     u64 serial[otmb_ctx::DONE_RING];
@@ -585,6 +599,7 @@ extern "C" int otmb_transportmatrix_stream(otmb_ctx* c, const otmb_tm_params* pr
                     guard(co.values(c->nzval[m].as<double>() + prev[m], nzval[m] + prev[m], (size_t)(tot[m] - prev[m]), pageable[m]));
                 for (int m = 0; m < 5; ++m) prev[m] = tot[m];
                 ++issued;
+                up.allowed.store(std::min(S, issued + lead), std::memory_order_release);
                 progress = true;
                 mark("copy-out issued");
             }
@@ -597,6 +612,8 @@ extern "C" int otmb_transportmatrix_stream(otmb_ctx* c, const otmb_tm_params* pr
         }
         if (!progress) _mm_pause();
     }
+    if (rc != OTMB_OK) up.status.store(rc);   // releases an uploader that is waiting for its turn
+    up.allowed.store(S, std::memory_order_release);
     up.th.join();
     mark("loop end");
     if (rc == OTMB_OK && up.status.load() != OTMB_OK) rc = otmb_fail(c, OTMB_ERR_CUDA, "upload of the face fluxes failed");
