@@ -212,7 +212,8 @@ int otmb_fused_build(otmb_ctx* ctx, const otmb_tm_params* prm, int mask, bool tw
 // own; 1 = first launch of a chained build (running entry totals start at zero), 2 = continues the chain: the
 // launch's entries follow those of the launches before it (slab-pipelined builds, stream.cu)
 int otmb_fused_v4_build(otmb_ctx* ctx, const otmb_tm_params* prm, int mask, i64 col0 = 0, i64 ncols = -1, int chain = 0);
-int otmb_v4_publish(otmb_ctx* ctx);   // enqueue the completion record of the last k_fused_v4 launch
+// enqueue the completion record of the last k_fused_v4 launch (totals_out: device copy of the five running nnz, or null)
+int otmb_v4_publish(otmb_ctx* ctx, u64* totals_out = nullptr);
 int otmb_wait_v4(otmb_ctx* ctx, u64 serial, bool block);   // 0 = done (flags in h_flags), -1 = not yet (block == false)
 int otmb_check_build_flags(otmb_ctx* ctx, int ops);
 int otmb_drop_zeros(otmb_ctx* ctx, int m, int base);

@@ -31,6 +31,28 @@ __global__ void __launch_bounds__(256) k_narrow(const i64* __restrict__ in, int*
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (int)in[i];
 }
 
+// The slab-pipelined call narrows on the COMPUTE stream, right behind the assembly of a slab, so that the copy-out stream
+// carries nothing but copies: the entry ranges are read from the device (the running totals before / after the slab),
+// the narrowed arrays keep the global positions.  blockIdx.y: 0-4 colptr of matrix m, 5-9 rowval of matrix m.
+struct NarrowSlab {
+    const i64* colptr[5];
+    const i64* rowval[5];
+    int* nar_colptr[5];
+    int* nar_rowval[5];
+    i64 col0, ncp;          // colptr entries [col0, col0 + ncp)
+    const u64* before;      // 5 totals before the slab (device)
+    const u64* after;       // 5 totals after it
+};
+__global__ void __launch_bounds__(256) k_narrow_slab(const __grid_constant__ NarrowSlab S) {
+    const int m = blockIdx.y % 5;
+    const bool rows = blockIdx.y >= 5;
+    const i64 lo = rows ? (i64)S.before[m] : S.col0, hi = rows ? (i64)S.after[m] : S.col0 + S.ncp;
+    const i64* __restrict__ in = rows ? S.rowval[m] : S.colptr[m];
+    int* __restrict__ out = rows ? S.nar_rowval[m] : S.nar_colptr[m];
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 i = lo + (i64)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride) out[i] = (int)in[i];
+}
+
 // host threads that widen Int32 -> Int64 or copy bytes; run() returns when the whole range is done
 struct HostPool {
     std::vector<std::thread> th;
@@ -262,6 +284,12 @@ struct CopyOut {
         narrow_off += n;
         return staged(nar, host, n * 4, 0, 8);
     }
+    // indices that were narrowed already (k_narrow_slab): `nar` is the Int32 device array, same positions as `host`
+    int narrowed(const int* nar, int64_t* host, size_t n) {
+        if (n == 0 || !host) return OTMB_OK;
+        return staged(nar, host, n * 4, 0, 8);
+    }
+    bool has_stage_room(size_t bytes) const { return narrow_ok && stage_off + bytes + 64 <= f->stage_cap; }
     int values(const double* dev, double* host, size_t n, bool pageable) {
         if (n == 0 || !host) return OTMB_OK;
         if (!pageable || !narrow_ok || stage_off + n * 8 + 64 > f->stage_cap) {
@@ -470,6 +498,19 @@ extern "C" int otmb_transportmatrix_stream(otmb_ctx* c, const otmb_tm_params* pr
     }
     CopyOut co(c, f, f->s_dn);
     OT_TRY(co.prepare(fits, nidx, stage));
+    // narrowed index arrays at global positions: per matrix N+1 colptr + `bound` rowval entries; slab totals [S+1][5]
+    int* nar_cp[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    int* nar_rv[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (co.narrow_ok) {
+        size_t off = 0;
+        for (int m = 0; m < 5; ++m) {
+            nar_cp[m] = f->narrow.as<int>() + off, off += (size_t)N + 1;
+            nar_rv[m] = f->narrow.as<int>() + off, off += (size_t)std::min<i64>(capacity[m], N * cap_per_col[m]);
+        }
+    }
+    CU_TRY(c, c->comm_buf.ensure((size_t)(S + 1) * 5 * 8));
+    u64* slab_tot = c->comm_buf.as<u64>();
+    CU_TRY(c, cudaMemsetAsync(slab_tot, 0, 40, c->stream));
 
     // ---- device buffers of the whole matrix set (as for a single launch)
     for (int q = 0; q < 6; ++q) CU_TRY(c, c->phi[q].ensure((size_t)c->M * 8));
@@ -555,10 +596,22 @@ extern "C" int otmb_transportmatrix_stream(otmb_ctx* c, const otmb_tm_params* pr
                 cudaMemsetAsync(c->run_nnz.p, 0, 40, c->stream);
             }
             if (ncols > 0) {
-                if (!guard(otmb_v4_publish(c))) break;
+                if (!guard(otmb_v4_publish(c, slab_tot + 5 * (s + 1)))) break;
                 serial[s] = c->v4_serial;
             } else {
                 serial[s] = 0;   // nothing launched: nothing to wait for
+                cudaMemcpyAsync(slab_tot + 5 * (s + 1), slab_tot + 5 * s, 40, cudaMemcpyDeviceToDevice, c->stream);
+            }
+            if (co.narrow_ok) {   // narrow this slab's indices here, on the compute stream (ranges read from the device)
+                NarrowSlab ns;
+                for (int m = 0; m < 5; ++m) {
+                    ns.colptr[m] = c->colptr[m].as<i64>(), ns.rowval[m] = c->rowval[m].as<i64>();
+                    ns.nar_colptr[m] = nar_cp[m], ns.nar_rowval[m] = nar_rv[m];
+                }
+                ns.col0 = col0, ns.ncp = ncols + (s == S - 1 ? 1 : 0);
+                ns.before = slab_tot + 5 * s, ns.after = slab_tot + 5 * (s + 1);
+                k_narrow_slab<<<dim3((unsigned)c->sm_count, 10), 256, 0, c->stream>>>(ns);
+                LAUNCHED(c);
             }
             cudaEventRecord(ev_k[s], c->stream);
             ++launched;
@@ -591,9 +644,15 @@ extern "C" int otmb_transportmatrix_stream(otmb_ctx* c, const otmb_tm_params* pr
                 if (rc != OTMB_OK) break;
                 cudaStreamWaitEvent(f->s_dn, ev_k[s], 0);
                 for (int m = 0; m < 5; ++m) {
-                    const size_t ncp = (size_t)ncols + (s == S - 1 ? 1 : 0);
-                    if (!guard(co.indices(c->colptr[m].as<i64>() + col0, colptr[m] + col0, ncp))) break;
-                    if (!guard(co.indices(c->rowval[m].as<i64>() + prev[m], rowval[m] + prev[m], (size_t)(tot[m] - prev[m])))) break;
+                    const size_t ncp = (size_t)ncols + (s == S - 1 ? 1 : 0), nrv = (size_t)(tot[m] - prev[m]);
+                    if (co.has_stage_room((ncp + nrv) * 4 + 64)) {   // narrowed on the compute stream already
+                        if (!guard(co.narrowed(nar_cp[m] + col0, colptr[m] + col0, ncp))) break;
+                        if (!guard(co.narrowed(nar_rv[m] + prev[m], rowval[m] + prev[m], nrv))) break;
+                    } else {                                            // 8-byte copies as they are
+                        co.narrow_ok = false;
+                        if (!guard(co.indices(c->colptr[m].as<i64>() + col0, colptr[m] + col0, ncp))) break;
+                        if (!guard(co.indices(c->rowval[m].as<i64>() + prev[m], rowval[m] + prev[m], nrv))) break;
+                    }
                 }
                 for (int m = 0; m < 5 && rc == OTMB_OK; ++m)
                     guard(co.values(c->nzval[m].as<double>() + prev[m], nzval[m] + prev[m], (size_t)(tot[m] - prev[m]), pageable[m]));

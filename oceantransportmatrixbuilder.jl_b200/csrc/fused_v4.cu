@@ -799,11 +799,14 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
 // place: copy the flag block and the five nnz into the host-mapped record of this launch, re-zero the device block
 // for the next launch, then store the launch's serial number — the word the host polls (transport.cu, otmb_wait_v4)
 // instead of issuing a copy and a stream synchronise per build.
-__global__ void __launch_bounds__(32) k_publish(DevFlags* __restrict__ flags, otmb_ctx::HostDone* __restrict__ rec, u64 serial) {
+__global__ void __launch_bounds__(32) k_publish(DevFlags* __restrict__ flags, otmb_ctx::HostDone* __restrict__ rec, u64 serial,
+                                                u64* __restrict__ totals_out) {
     constexpr int NI = (int)(sizeof(DevFlags) / sizeof(int));
     static_assert(NI <= 32, "one warp copies the flag block");
     int* src = reinterpret_cast<int*>(flags);
     volatile int* dst = reinterpret_cast<volatile int*>(&rec->snap);
+    if (totals_out && threadIdx.x < 5) totals_out[threadIdx.x] = flags->nnz[threadIdx.x];   // (read before the block is zeroed:
+    __syncwarp();                                                                          //  the ints below alias nnz)
     if (threadIdx.x < NI) {
         dst[threadIdx.x] = src[threadIdx.x];
         src[threadIdx.x] = 0;
@@ -888,8 +891,9 @@ int launch_v4(otmb_ctx* c, V4Params& P) {
 
 }  // namespace
 
-int otmb_v4_publish(otmb_ctx* c) {
-    k_publish<<<1, 32, 0, c->stream>>>(c->flags.as<DevFlags>(), c->d_done + (c->v4_serial % otmb_ctx::DONE_RING), c->v4_serial);
+int otmb_v4_publish(otmb_ctx* c, u64* totals_out) {
+    k_publish<<<1, 32, 0, c->stream>>>(c->flags.as<DevFlags>(), c->d_done + (c->v4_serial % otmb_ctx::DONE_RING), c->v4_serial,
+                                       totals_out);
     LAUNCHED(c);
     CU_TRY(c, cudaGetLastError());
     return OTMB_OK;
