@@ -164,10 +164,13 @@ int otmb_comm_allgather_i64(otmb_ctx* ctx, const int64_t* mine, int32_t count, i
  *  - makeindices on the slab + all-gather of the owned counts: N of the whole ocean, this rank's first wet rank
  *    (already applied: no otmb_set_rank_offset needed) and its number of columns;
  *  - otmb_set_masstransport uploads the window of umo / vmo (local); otmb_sharded_facefluxes runs the continuity
- *    chain from the sea-floor rank (nranks-1) up to the surface rank (0): the carry plane is cut into `nchunks`
- *    column chunks (0 = default) which are sent / received with NCCL on the context's stream and PIPELINED — a rank
- *    starts on a chunk as soon as the rank below has sent it.  Outputs (may be NULL): owned cells of full-size
- *    arrays.  The all-fill assertion (:199-200) is evaluated over all ranks.  otmb_sharded_facefluxes_enqueue is
+ *    chain from the sea-floor rank (nranks-1) up to the surface rank (0), PIPELINED: a rank starts on a block of
+ *    columns as soon as the rank below has delivered it.  nchunks == 0 (default): the peer-memory form — each rank
+ *    exports an inbox with CUDA IPC, ONE k_faceflux launch per rank whose thread blocks wait for / raise per-block
+ *    flags in peer memory, the send being plain stores over NVLink from inside the kernel (per-block acks keep a
+ *    fast rank from overwriting values that have not been read); if IPC / P2P is unavailable, or nchunks > 0: the
+ *    carry plane is cut into nchunks column chunks (8 by default) sent / received with NCCL on the context's
+ *    stream.  Same bits either way.  Outputs (may be NULL): owned cells of full-size arrays.  The all-fill assertion (:199-200) is evaluated over all ranks.  otmb_sharded_facefluxes_enqueue is
  *    the device-resident chain alone (no flags, no copies, does not block);
  *  - assembly of this rank's columns + all-gather of the nnz: entries held by lower ranks (add to the local
  *    colptr) and of the whole matrix. */

@@ -143,7 +143,114 @@ __global__ void __launch_bounds__(256) k_checksum(const i64* __restrict__ colptr
 
 }  // namespace
 
+// inbox layout: P doubles (the carry plane), then per block of 128 columns one flag ("epoch e has landed", written by
+// the rank below) and one ack ("epoch e has been read", written by the rank above into the inbox of the rank it acks)
+static i64 inbox_blocks(i64 P) { return (P + 127) / 128; }
+static size_t inbox_bytes(i64 P) { return (size_t)P * 8 + (size_t)inbox_blocks(P) * 8 + 64; }
+
+// Peer-memory transport of the carry chain: every rank allocates an inbox and exports it (cudaIpcGetMemHandle), the 64-byte
+// handles are all-gathered, and every rank maps the inbox of the rank above it.  Any failure (no P2P, IPC refused)
+// leaves peer_state = -1 on EVERY rank (the outcome is all-gathered too) and the chain uses NCCL send / recv instead.
+static int peer_setup(otmb_ctx* c) {
+    if (c->peer_state != 0 && c->peer_P == c->P) return OTMB_OK;
+    const int R = c->comm_size, r = c->comm_rank;
+    for (void** q : {&c->peer_above, &c->peer_below})
+        if (*q) {
+            cudaIpcCloseMemHandle(*q);
+            *q = nullptr;
+        }
+    c->peer_state = -1;
+    c->peer_P = c->P;
+    int64_t mine[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    bool ok = c->peer_inbox.ensure(inbox_bytes(c->P)) == cudaSuccess &&
+              cudaMemsetAsync(c->peer_inbox.p, 0, inbox_bytes(c->P), c->stream) == cudaSuccess &&
+              cudaStreamSynchronize(c->stream) == cudaSuccess && cudaIpcGetMemHandle(&h, c->peer_inbox.p) == cudaSuccess;
+    if (ok) memcpy(mine, &h, 64);
+    mine[8] = ok ? 1 : 0;
+    cudaGetLastError();
+    std::vector<int64_t> all((size_t)R * 9);
+    OT_TRY(allgather_i64(c, mine, 9, all.data()));
+    bool everyone = true;
+    for (int q = 0; q < R; ++q) everyone = everyone && all[(size_t)q * 9 + 8] == 1;
+    int64_t opened = 1;
+    auto open_inbox = [&](int rank, void** out) {
+        cudaIpcMemHandle_t hh;
+        memcpy(&hh, &all[(size_t)rank * 9], 64);
+        if (cudaIpcOpenMemHandle(out, hh, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            *out = nullptr;
+            opened = 0;
+        }
+    };
+    if (everyone && r > 0) open_inbox(r - 1, &c->peer_above);        // carry + flags go up
+    if (everyone && r < R - 1) open_inbox(r + 1, &c->peer_below);    // acks go down
+    std::vector<int64_t> res((size_t)R);
+    OT_TRY(allgather_i64(c, &opened, 1, res.data()));
+    for (int q = 0; q < R; ++q) everyone = everyone && res[(size_t)q] == 1;
+    c->peer_state = everyone ? 1 : -1;
+    c->peer_epoch = 0;
+    return OTMB_OK;
+}
+
+// The continuity chain on the device, rank R-1 (sea floor) -> rank 0 (surface); everything is enqueued on the context's
+// stream, nothing blocks.  nchunks == 0: the peer-memory form when it is available — ONE k_faceflux launch per rank whose
+// blocks wait for / raise per-block flags in peer memory (the send is a plain store over NVLink from inside the kernel) —
+// else NCCL with 8 chunks; nchunks > 0: NCCL send / recv of that many column chunks, pipelined.
+static int enqueue_chain(otmb_ctx* c, int32_t nchunks) {
+    const int R = c->comm_size, r = c->comm_rank;
+    NcclApi* a = nullptr;
+    if (R > 1) {
+        OT_TRY(need_api(c, &a));
+        OT_TRY(otmb_need(c, c->comm != nullptr, "otmb_comm_init"));
+    }
+    const bool recv = r < R - 1, send = r > 0;   // rank R-1 owns the sea floor, rank 0 the surface
+    OT_TRY(otmb_faceflux_begin(c, c->uv_fill));
+    if (R > 1 && nchunks == 0) OT_TRY(peer_setup(c));
+    if (R > 1 && nchunks == 0 && c->peer_state == 1) {
+        PeerLink link;
+        link.epoch = ++c->peer_epoch;
+        double* d_in = nullptr;
+        double* d_out = nullptr;
+        const i64 nb = inbox_blocks(c->P);
+        unsigned* my_words = reinterpret_cast<unsigned*>(c->peer_inbox.as<double>() + c->P);
+        if (recv) {
+            d_in = c->peer_inbox.as<double>();
+            link.flag_in = my_words;                                                                     // raised by the rank below
+            link.ack_out = reinterpret_cast<unsigned*>(reinterpret_cast<double*>(c->peer_below) + c->P) + nb;   // its ack array
+        }
+        if (send) {
+            d_out = reinterpret_cast<double*>(c->peer_above);
+            link.flag_out = reinterpret_cast<unsigned*>(d_out + c->P);
+            link.ack_in = my_words + nb;                                                                 // written by the rank above
+        }
+        return otmb_faceflux_columns(c, c->uv_fill, 0, c->P, d_in, d_out, link);
+    }
+    if (recv) CU_TRY(c, c->carry[0].ensure((size_t)c->P * 8));
+    if (send) CU_TRY(c, c->carry[1].ensure((size_t)c->P * 8));
+    double* d_in = recv ? c->carry[0].as<double>() : nullptr;
+    double* d_out = send ? c->carry[1].as<double>() : nullptr;
+    // column chunks in units of whole thread blocks
+    if (nchunks < 1) nchunks = R > 1 ? 8 : 1;
+    const i64 blocks = (c->P + 127) / 128;
+    nchunks = (int)std::min<i64>(nchunks, blocks);
+    for (int q = 0; q < nchunks; ++q) {
+        const i64 p0 = std::min<i64>(c->P, blocks * q / nchunks * 128), p1 = std::min<i64>(c->P, blocks * (q + 1) / nchunks * 128);
+        if (recv) NCCL_TRY(c, a, a->Recv(d_in + p0, (size_t)(p1 - p0), ncclFloat64, r + 1, (ncclComm_t)c->comm, c->stream));
+        OT_TRY(otmb_faceflux_columns(c, c->uv_fill, p0, p1, d_in, d_out));
+        if (send) NCCL_TRY(c, a, a->Send(d_out + p0, (size_t)(p1 - p0), ncclFloat64, r - 1, (ncclComm_t)c->comm, c->stream));
+    }
+    return OTMB_OK;
+}
+
 void otmb_comm_release(otmb_ctx* c) {
+    for (void** q : {&c->peer_above, &c->peer_below})
+        if (*q) {
+            cudaIpcCloseMemHandle(*q);
+            *q = nullptr;
+        }
+    c->peer_state = 0;
     if (c->comm) {
         NcclApi* a = nccl_api();
         if (a->CommDestroy) a->CommDestroy((ncclComm_t)c->comm);
@@ -291,35 +398,19 @@ int otmb_sharded_facefluxes(otmb_ctx* c, int32_t nchunks, double* east, double* 
     OT_TRY(otmb_need(c, c->have_uv, "otmb_set_masstransport"));
     if (c->topo == OTMB_TOPO_UNKNOWN) return otmb_fail(c, OTMB_ERR_UNKNOWN_GRID, otmb_status_string(OTMB_ERR_UNKNOWN_GRID));
     CU_TRY(c, cudaSetDevice(c->device));
-    const int R = c->comm_size, r = c->comm_rank;
-    NcclApi* a = nullptr;
-    if (R > 1) {
-        OT_TRY(need_api(c, &a));
-        OT_TRY(otmb_need(c, c->comm != nullptr, "otmb_comm_init"));
-    }
-    const bool recv = r < R - 1, send = r > 0;   // rank R-1 owns the sea floor, rank 0 the surface
-    if (recv) CU_TRY(c, c->carry[0].ensure((size_t)c->P * 8));
-    if (send) CU_TRY(c, c->carry[1].ensure((size_t)c->P * 8));
-    double* d_in = recv ? c->carry[0].as<double>() : nullptr;
-    double* d_out = send ? c->carry[1].as<double>() : nullptr;
-    OT_TRY(otmb_faceflux_begin(c, c->uv_fill));
-    // column chunks in units of whole thread blocks
-    if (nchunks < 1) nchunks = R > 1 ? 8 : 1;
-    const i64 blocks = (c->P + 127) / 128;
-    nchunks = (int)std::min<i64>(nchunks, blocks);
-    for (int q = 0; q < nchunks; ++q) {
-        const i64 p0 = std::min<i64>(c->P, blocks * q / nchunks * 128), p1 = std::min<i64>(c->P, blocks * (q + 1) / nchunks * 128);
-        if (recv) NCCL_TRY(c, a, a->Recv(d_in + p0, (size_t)(p1 - p0), ncclFloat64, r + 1, (ncclComm_t)c->comm, c->stream));
-        OT_TRY(otmb_faceflux_columns(c, c->uv_fill, p0, p1, d_in, d_out));
-        if (send) NCCL_TRY(c, a, a->Send(d_out + p0, (size_t)(p1 - p0), ncclFloat64, r - 1, (ncclComm_t)c->comm, c->stream));
-    }
+    const int R = c->comm_size;
+    OT_TRY(enqueue_chain(c, nchunks));
     OT_TRY(otmb_fetch_flags(c));
     // the reference asserts on the WHOLE arrays (src/velocities.jl:199-200): combine the ranks' flags
-    std::vector<int64_t> all((size_t)R * 2);
-    const int64_t mine[2] = {c->h_flags->any_valid_u, c->h_flags->any_valid_v};
-    OT_TRY(allgather_i64(c, mine, 2, all.data()));
-    bool any_u = false, any_v = false;
-    for (int q = 0; q < R; ++q) any_u |= all[2 * q] != 0, any_v |= all[2 * q + 1] != 0;
+    std::vector<int64_t> all((size_t)R * 3);
+    const int64_t mine[3] = {c->h_flags->any_valid_u, c->h_flags->any_valid_v, c->h_flags->lookback_timeout};
+    OT_TRY(allgather_i64(c, mine, 3, all.data()));
+    bool any_u = false, any_v = false, timeout = false;
+    for (int q = 0; q < R; ++q) any_u |= all[3 * q] != 0, any_v |= all[3 * q + 1] != 0, timeout |= all[3 * q + 2] != 0;
+    if (timeout) {
+        c->have_phi = false;
+        return otmb_fail(c, OTMB_ERR_COMM, "face-flux carry chain: a rank never received the plane of the rank below it");
+    }
     if (!any_u || !any_v) {
         c->have_phi = false;
         return otmb_fail(c, OTMB_ERR_ALL_FILL, otmb_status_string(OTMB_ERR_ALL_FILL));
@@ -338,27 +429,7 @@ int otmb_sharded_facefluxes_enqueue(otmb_ctx* c, int32_t nchunks) {
     OT_TRY(otmb_need(c, c->have_indices, "otmb_makeindices"));
     OT_TRY(otmb_need(c, c->have_uv, "otmb_set_masstransport"));
     CU_TRY(c, cudaSetDevice(c->device));
-    const int R = c->comm_size, r = c->comm_rank;
-    NcclApi* a = nullptr;
-    if (R > 1) {
-        OT_TRY(need_api(c, &a));
-        OT_TRY(otmb_need(c, c->comm != nullptr, "otmb_comm_init"));
-    }
-    const bool recv = r < R - 1, send = r > 0;
-    if (recv) CU_TRY(c, c->carry[0].ensure((size_t)c->P * 8));
-    if (send) CU_TRY(c, c->carry[1].ensure((size_t)c->P * 8));
-    double* d_in = recv ? c->carry[0].as<double>() : nullptr;
-    double* d_out = send ? c->carry[1].as<double>() : nullptr;
-    OT_TRY(otmb_faceflux_begin(c, c->uv_fill));
-    if (nchunks < 1) nchunks = R > 1 ? 8 : 1;
-    const i64 blocks = (c->P + 127) / 128;
-    nchunks = (int)std::min<i64>(nchunks, blocks);
-    for (int q = 0; q < nchunks; ++q) {
-        const i64 p0 = std::min<i64>(c->P, blocks * q / nchunks * 128), p1 = std::min<i64>(c->P, blocks * (q + 1) / nchunks * 128);
-        if (recv) NCCL_TRY(c, a, a->Recv(d_in + p0, (size_t)(p1 - p0), ncclFloat64, r + 1, (ncclComm_t)c->comm, c->stream));
-        OT_TRY(otmb_faceflux_columns(c, c->uv_fill, p0, p1, d_in, d_out));
-        if (send) NCCL_TRY(c, a, a->Send(d_out + p0, (size_t)(p1 - p0), ncclFloat64, r - 1, (ncclComm_t)c->comm, c->stream));
-    }
+    OT_TRY(enqueue_chain(c, nchunks));
     c->have_phi = true;
     return OTMB_OK;
 }

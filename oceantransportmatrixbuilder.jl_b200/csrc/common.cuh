@@ -82,6 +82,14 @@ struct otmb_ctx {
     void* comm = nullptr;
     int comm_rank = 0, comm_size = 1;
     DevBuf comm_buf;          // small device staging for the integer all-gathers
+    // peer-memory carry chain (comm.cu): this rank's inbox (carry plane + per-block flags, exported with CUDA IPC) and
+    // the mapped inbox of the rank above; peer_state: 0 = not tried, 1 = ready, -1 = unavailable (NCCL chunks instead)
+    DevBuf peer_inbox;
+    void* peer_above = nullptr;
+    void* peer_below = nullptr;
+    int peer_state = 0;
+    i64 peer_P = 0;
+    unsigned peer_epoch = 0;
     bool have_uv = false;     // umo / vmo are resident in stage_a / stage_b (otmb_set_masstransport)
     double uv_fill = 0.0;
     int topo = OTMB_TOPO_UNKNOWN;
@@ -224,7 +232,19 @@ int otmb_dev_sparse(otmb_ctx* ctx, i64 len, const i64* dI, const i64* dJ, const 
 int otmb_dev_spadd(otmb_ctx* ctx, i64 n, int base, const i64* acp, const i64* arv, const double* anz, const i64* bcp,
                    const i64* brv, const double* bnz, DevBuf& colptr, DevBuf& rowval, DevBuf& nzval, i64* nnz);
 int otmb_faceflux_begin(otmb_ctx* ctx, double fill);
-int otmb_faceflux_columns(otmb_ctx* ctx, double fill, i64 p_begin, i64 p_end, const double* d_in, double* d_out);
+// peer-memory link of the face-flux carry chain: per-block flags (one per 128 columns) in this GPU's memory (written by
+// the rank below) and in the memory of the rank above (mapped with CUDA IPC), and the value that means "this launch"
+// ack_in (this GPU, written by the rank above) / ack_out (the rank below): "your plane of epoch e has been read" — the
+// sender may not overwrite a block of the inbox before the receiver has taken the previous epoch's values out of it
+struct PeerLink {
+    const unsigned* flag_in = nullptr;
+    unsigned* flag_out = nullptr;
+    const unsigned* ack_in = nullptr;
+    unsigned* ack_out = nullptr;
+    unsigned epoch = 0;
+};
+int otmb_faceflux_columns(otmb_ctx* ctx, double fill, i64 p_begin, i64 p_end, const double* d_in, double* d_out,
+                          PeerLink link = PeerLink());
 int otmb_faceflux_copy_out(otmb_ctx* ctx, double* const outs[6]);
 int otmb_upload_uv(otmb_ctx* ctx, const double* umo, const double* vmo, double fill);
 void otmb_comm_release(otmb_ctx* ctx);

@@ -275,6 +275,7 @@ int otmb_destroy(otmb_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     otmb_comm_release(c);
+    c->peer_inbox.release();
     c->comm_buf.release();
     c->run_nnz.release();
     DevBuf* bufs[] = {&c->v3D, &c->mask, &c->wcount, &c->wpre, &c->lwet, &c->rank3d, &c->area2D, &c->thk, &c->Z3D, &c->zt, &c->edge, &c->dnbr,

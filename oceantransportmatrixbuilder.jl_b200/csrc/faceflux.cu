@@ -23,11 +23,31 @@ __global__ void __launch_bounds__(128) k_faceflux(const double* __restrict__ umo
                                                   double* __restrict__ north, double* __restrict__ south,
                                                   double* __restrict__ top, double* __restrict__ bottom,
                                                   DevFlags* __restrict__ flags, int row0, int row1, int p_begin, int p_end,
-                                                  const double* __restrict__ carry_in, double* __restrict__ carry_out) {
+                                                  const double* __restrict__ carry_in, double* __restrict__ carry_out,
+                                                  PeerLink link) {
     // (all 3-D pointers are window-biased and indexed by the global linear cell index; the kernel covers the columns
     // [p_begin, p_end) of the plane — one chunk of the pipelined carry chain — and, per column, the owned levels)
     const int p = p_begin + blockIdx.x * blockDim.x + threadIdx.x;
     bool valid_u = false, valid_v = false;
+    // Peer-memory form of the carry chain (comm.cu): carry_in lives in THIS GPU's memory and is written by the rank below
+    // over NVLink, block by block; a block waits for the flag of its own 128 columns, so the ranks' kernels overlap
+    // column block by column block instead of exchanging whole planes.  The spin is bounded: a peer that never
+    // arrives becomes an error code (flags->lookback_timeout), not a hang.
+    double carry0 = 0.0, carry_last = 0.0;
+    if (link.flag_in) {
+        if (threadIdx.x == 0) {
+            unsigned v, spins = 0;
+            do {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(link.flag_in + blockIdx.x) : "memory");
+            } while (v != link.epoch && ++spins < (1u << 25));
+            if (v != link.epoch) atomicOr(&flags->lookback_timeout, 1);
+        }
+        __syncthreads();
+        if (p < p_end) carry0 = __ldcv(carry_in + p);   // (the peer wrote it behind this SM's back: read around L1)
+        __syncthreads();                                // every value of the block is in a register: the inbox may be reused
+        if (threadIdx.x == 0)
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(link.ack_out + blockIdx.x), "r"(link.epoch) : "memory");
+    }
     if (p < p_end) {
         const int i = p % g.nx, j = p / g.nx;
         // owned levels of this column: the grid rows R = j + ny*k inside [row0, row1)
@@ -38,7 +58,7 @@ __global__ void __launch_bounds__(128) k_faceflux(const double* __restrict__ umo
         // north neighbour of this column, and of the column to the south (always regular: j-1 < ny-1)
         const int pN = j < g.ny - 1 ? p + g.nx : (g.topo == OTMB_TOPO_TRIPOLAR ? (g.nx - 1 - i) + g.nx * (g.ny - 1) : -1);
         // phi_top of the level below: 0 under the sea floor, or the plane handed up by the slab below
-        double carry = carry_in ? carry_in[p] : 0.0;
+        double carry = carry_in ? (link.flag_in ? carry0 : carry_in[p]) : 0.0;
         const bool owns = k_begin < k_end;
         if (owns && carry_in && k_end < g.nz) top[(size_t)k_end * g.P + p] = carry;   // halo cell below: its top flux
         for (int k0 = k_end - 1; k0 >= k_begin; k0 -= UNROLL) {
@@ -83,13 +103,29 @@ __global__ void __launch_bounds__(128) k_faceflux(const double* __restrict__ umo
                 carry = t;
             }
         }
-        if (carry_out) carry_out[p] = carry;   // phi_top of the column's first owned level (a column that owns nothing passes it on)
+        carry_last = carry;
+        if (carry_out && !link.flag_out) carry_out[p] = carry;   // phi_top of the column's first owned level (a column that owns nothing passes it on)
         if (owns && k_begin > 0) bottom[(size_t)(k_begin - 1) * g.P + p] = carry;   // halo cell above: its bottom flux
     }
     const unsigned bu = __ballot_sync(0xffffffffu, valid_u), bv = __ballot_sync(0xffffffffu, valid_v);
     if ((threadIdx.x & 31) == 0) {
         if (bu) atomicOr(&flags->any_valid_u, 1);
         if (bv) atomicOr(&flags->any_valid_v, 1);
+    }
+    if (link.flag_out) {   // carry_out is the inbox of the rank above (mapped peer memory)
+        if (threadIdx.x == 0) {   // ... which must have taken the previous epoch's values of this block out of it
+            unsigned v, spins = 0;
+            do {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(link.ack_in + blockIdx.x) : "memory");
+            } while ((int)(v - (link.epoch - 1u)) < 0 && ++spins < (1u << 25));
+            if ((int)(v - (link.epoch - 1u)) < 0) atomicOr(&flags->lookback_timeout, 1);
+        }
+        __syncthreads();
+        if (p < p_end) carry_out[p] = carry_last;   // a plain store over NVLink
+        __threadfence_system();                    // visible before the flag
+        __syncthreads();
+        if (threadIdx.x == 0)
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(link.flag_out + blockIdx.x), "r"(link.epoch) : "memory");
     }
 }
 
@@ -135,7 +171,7 @@ int otmb_faceflux_begin(otmb_ctx* c, double fill) {
     return OTMB_OK;
 }
 // the columns [p_begin, p_end) of the plane; d_in / d_out are device planes of nx*ny doubles (or null)
-int otmb_faceflux_columns(otmb_ctx* c, double fill, i64 p_begin, i64 p_end, const double* d_in, double* d_out) {
+int otmb_faceflux_columns(otmb_ctx* c, double fill, i64 p_begin, i64 p_end, const double* d_in, double* d_out, PeerLink link) {
     if (p_end <= p_begin) return OTMB_OK;
     GridDims g{(int)c->nx, (int)c->ny, (int)c->nz, c->topo, (int)c->P, (int)c->M};
     // Five levels of loads in flight per column.  Ten were measured slower even on the 1-degree grid, where there are
@@ -149,7 +185,7 @@ int otmb_faceflux_columns(otmb_ctx* c, double fill, i64 p_begin, i64 p_end, cons
         c->win<double>(c->stage_a), c->win<double>(c->stage_b), c->mask_win(), g, fill,
         c->win<double>(c->phi[OTMB_FACE_EAST]), c->win<double>(c->phi[OTMB_FACE_WEST]), c->win<double>(c->phi[OTMB_FACE_NORTH]),
         c->win<double>(c->phi[OTMB_FACE_SOUTH]), c->win<double>(c->phi[OTMB_FACE_TOP]), c->win<double>(c->phi[OTMB_FACE_BOTTOM]),
-        c->flags.as<DevFlags>(), (int)(c->L_own0 / c->nx), (int)(c->L_own1 / c->nx), (int)p_begin, (int)p_end, d_in, d_out);
+        c->flags.as<DevFlags>(), (int)(c->L_own0 / c->nx), (int)(c->L_own1 / c->nx), (int)p_begin, (int)p_end, d_in, d_out, link);
     LAUNCHED(c);
     CU_TRY(c, cudaGetLastError());
     return OTMB_OK;
