@@ -257,6 +257,17 @@ def sharded_record(args, rank, local_rank, world, dist):
     launches = ctx.launches() - launches0
     pipe_ms = timed(month, args.steps)
     flux_ms = timed(fluxes, args.steps)
+    tr = C.c_int32(0)
+    ctx.check(lib.otmb_comm_chain_transport(ctx.h, C.byref(tr)))
+    transport = {1: "peer memory: CUDA-IPC inboxes, ONE fused k_faceflux launch per rank, per-block flags + acks, stores over NVLink",
+                 -1: "NCCL send/recv of 8 column chunks on the library stream", 0: "none (one rank)"}[tr.value if world > 1 else 0]
+    nccl_ms = None
+    if world > 1 and args.chunks == 0:      # the same chain over NCCL send / recv, for comparison
+        def fluxes_nccl():
+            ns.facefluxes_enqueue(8)
+        for _ in range(3):
+            fluxes_nccl()
+        nccl_ms = timed(fluxes_nccl, args.steps)
     kernel_ms = []
     for _ in range(args.steps):
         asm()
@@ -266,7 +277,8 @@ def sharded_record(args, rank, local_rank, world, dist):
     P = nx * ny
     own_cells = (ns.slabs[rank][1] - ns.slabs[rank][0]) * nx
     b_rank = 8 * 7 * own_cells + 8 * 10 * P + sum(8 * (slab.n_owned + 1) + 16 * nnz[m] for m in range(5))
-    rows = gather([int(asm_ms * 1e6), int(pipe_ms * 1e6), int(flux_ms * 1e6), int(k_ms * 1e6), launches, slab.n_owned, b_rank] + list(nnz))
+    rows = gather([int(asm_ms * 1e6), int(pipe_ms * 1e6), int(flux_ms * 1e6), int(k_ms * 1e6), launches, slab.n_owned, b_rank] + list(nnz)
+                  + [int((nccl_ms or 0.0) * 1e6)])
 
     # the same matrix from ONE context on rank 0's GPU (at world == 1 that is the run above)
     same, cs_one, one_ms = None, None, None
@@ -301,9 +313,10 @@ def sharded_record(args, rank, local_rank, world, dist):
         "assembly": {"ms": amax, "value": nnz_tot[0] / (amax / 1e3), "ms_per_rank": [r[0] / 1e6 for r in rows],
                      "timed": "K x otmb_transportmatrix_build on every rank's slab; inputs resident; max over ranks"},
         "pipeline": {"ms": pmax, "value": nnz_tot[0] / (pmax / 1e3), "ms_per_rank": [r[1] / 1e6 for r in rows],
-                     "facefluxes_chain_ms": fmax, "chunks": args.chunks or (8 if world > 1 else 1),
-                     "timed": "K x [facefluxes continuity chain (NCCL send/recv of the chunked carry plane on the library stream) "
-                              "+ assembly]; umo/vmo resident; max over ranks"},
+                     "facefluxes_chain_ms": fmax, "chain_transport": transport,
+                     "facefluxes_chain_nccl_chunks_ms": (max(r[12] for r in rows) / 1e6) if nccl_ms is not None else None,
+                     "timed": "K x [facefluxes continuity chain across the ranks (bottom-up, pipelined per block of columns) + assembly]; "
+                              "umo/vmo resident; max over ranks"},
         "roofline_slowest_rank": {"rank": slow, "kernel_ms": kslow, "algorithmic_bytes": rows[slow][6],
                                   "achieved": rows[slow][6] / (kslow / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                                   "frac": rows[slow][6] / (kslow / 1e3) / 1e9 / peak, "peak_source": peak_src},

@@ -159,6 +159,9 @@ int otmb_comm_unique_id(uint8_t id[OTMB_COMM_ID_BYTES]);
 int otmb_comm_init(otmb_ctx* ctx, int32_t nranks, int32_t rank, const uint8_t id[OTMB_COMM_ID_BYTES]);
 int otmb_comm_free(otmb_ctx* ctx);
 int otmb_comm_allgather_i64(otmb_ctx* ctx, const int64_t* mine, int32_t count, int64_t* all /* nranks*count */);
+/* transport of the default face-flux carry chain on this context: 1 = peer memory (CUDA IPC, fused kernel),
+ * -1 = NCCL send / recv, 0 = no chain has run yet (or one rank) */
+int otmb_comm_chain_transport(otmb_ctx* ctx, int32_t* transport);
 /* collective steps (every rank calls them; a failure on ANY rank is returned on EVERY rank, so nobody is left
  * waiting in a collective for a peer that has raised):
  *  - makeindices on the slab + all-gather of the owned counts: N of the whole ocean, this rank's first wet rank

@@ -25,7 +25,7 @@ EXPORTS = [
     "otmb_dyad_derivative", "otmb_bolus_gm_velocity", "otmb_timer_start", "otmb_timer_stop", "otmb_l2_flush",
     "otmb_launch_count", "otmb_last_build_ms", "otmb_synchronize", "otmb_set_slab", "otmb_slab_counts",
     "otmb_set_rank_offset", "otmb_facefluxes_slab", "otmb_velocity2fluxes", "otmb_fluxes2velocity", "otmb_bgrid_to_cgrid", "otmb_lump_and_spray_build", "otmb_lump_and_spray_fetch", "otmb_spmv",
-    "otmb_plan_slabs", "otmb_set_slab_rows", "otmb_comm_unique_id", "otmb_comm_init", "otmb_comm_free", "otmb_comm_allgather_i64",
+    "otmb_plan_slabs", "otmb_set_slab_rows", "otmb_comm_unique_id", "otmb_comm_init", "otmb_comm_free", "otmb_comm_allgather_i64", "otmb_comm_chain_transport",
     "otmb_sharded_makeindices", "otmb_set_masstransport", "otmb_sharded_facefluxes", "otmb_sharded_facefluxes_enqueue",
     "otmb_sharded_transportmatrix_build", "otmb_result_checksum",
     "otmb_facefluxes_gm", "otmb_transportmatrix_stream",
@@ -103,6 +103,7 @@ def load():
         "otmb_comm_init": ([vp, i32, i32, vp], C.c_int),
         "otmb_comm_free": ([vp], C.c_int),
         "otmb_comm_allgather_i64": ([vp, pi64, i32, pi64], C.c_int),
+        "otmb_comm_chain_transport": ([vp, C.POINTER(i32)], C.c_int),
         "otmb_sharded_makeindices": ([vp, vp, pi64, pi64, pi64], C.c_int),
         "otmb_set_masstransport": ([vp, vp, vp, dbl], C.c_int),
         "otmb_sharded_facefluxes": ([vp, i32] + [vp] * 6, C.c_int),

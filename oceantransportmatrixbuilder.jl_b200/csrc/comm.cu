@@ -350,6 +350,14 @@ int otmb_comm_free(otmb_ctx* c) {
     return OTMB_OK;
 }
 
+// which transport the default (nchunks == 0) carry chain uses on this context: 0 = not decided yet (no chain has run),
+// 1 = peer memory (CUDA IPC inboxes, fused kernel), -1 = NCCL send / recv of column chunks
+int otmb_comm_chain_transport(otmb_ctx* c, int32_t* transport) {
+    if (!c || !transport) return OTMB_ERR_BADARG;
+    *transport = c->comm_size > 1 ? c->peer_state : 0;
+    return OTMB_OK;
+}
+
 int otmb_comm_allgather_i64(otmb_ctx* c, const int64_t* mine, int32_t count, int64_t* all) {
     if (!c || !mine || !all || count < 1) return OTMB_ERR_BADARG;
     CU_TRY(c, cudaSetDevice(c->device));
