@@ -231,6 +231,11 @@ int otmb_transportmatrix_stream(otmb_ctx* ctx, const otmb_tm_params* params, con
                                 const double* mlotst, const double* rho3d, int32_t nslabs, const int64_t capacity[5],
                                 int64_t* const colptr[5], int64_t* const rowval[5], double* const nzval[5],
                                 int64_t nnz_out[5]);
+/* the resident result matrices (bit m of mask = OTMB_MAT_m, 0 = all five) straight to a binary file, through pinned
+ * staging, without host SparseMatrixCSC objects in between (the 12-month batch).  Layout, little
+ * endian: "OTMBCSC1"; Int64 N, index_base, nmat; per matrix Int64 id, Int64 nnz; then per matrix colptr (N+1 Int64),
+ * rowval (nnz Int64), nzval (nnz Float64). */
+int otmb_transportmatrix_dump(otmb_ctx* ctx, int mask, const char* path);
 /* host half of that pipeline alone (no GPU needed): sign-extend n Int32 indices into Int64 on `threads` pool
  * threads (0 = the calling thread). */
 int otmb_host_widen(const int32_t* src, int64_t* dst, int64_t n, int32_t threads);
@@ -294,6 +299,14 @@ int otmb_lump_and_spray_build(otmb_ctx* ctx, int64_t di, int64_t dj, int64_t dk,
 int otmb_lump_and_spray_fetch(otmb_ctx* ctx, int64_t* lump_colptr /* N+1 */, int64_t* lump_rowval /* N */,
                               double* lump_nzval /* N */, int64_t* spray_colptr /* N_c+1 */, int64_t* spray_rowval /* N */,
                               double* spray_nzval /* N */, double* vol_c /* N_c */);
+
+/* T_c = LUMP * T * SPRAY (test/local_full.jl:161, the coarse operator of the reference's downstream solve) on the
+ * device: LUMP / SPRAY of the last otmb_lump_and_spray_build, T = the RESIDENT result matrix `which` (OTMB_MAT_*) of the
+ * last build.  LUMP has one entry per column and SPRAY column J holds ones at the members of component J, so this is a
+ * gather per coarse column (one thread each), accumulated in the order of SparseArrays' product (LUMP * T first, then
+ * * SPRAY): bit-identical, structural zeros kept.  Two-phase; indices in the lump build's index base. */
+int otmb_coarsen_build(otmb_ctx* ctx, int which, int64_t* n_coarse, int64_t* nnz);
+int otmb_coarsen_fetch(otmb_ctx* ctx, int64_t* colptr /* N_c+1 */, int64_t* rowval, double* nzval);
 
 /* y = X x (transpose = 0) or y = Xᵀ x (transpose != 0) on the RESIDENT result matrix `which` (OTMB_MAT_*) of the
  * last build: the products behind the reference's conservation checks τdiv = ‖1‖/‖T 1‖, τvol = ‖v‖/‖Tᵀ v‖

@@ -9,7 +9,7 @@ from .api import (  # noqa: F401
     bolus_GM_velocity, default_context, facefluxes, facefluxesfrommasstransport, getgridtopology,
     globalverticaldyadderivative, globalverticalfacetriadderivative, makegridmetrics, makeindices,
     spadd, sparse, transportmatrix, vertexpermutation, velocity2fluxes, fluxes2velocity, facefluxesfromvelocities,
-    getarakawagrid, interpolateontodefaultCgrid, lump_and_spray, resident_matvec, facefluxes_GM,
+    getarakawagrid, interpolateontodefaultCgrid, lump_and_spray, resident_matvec, facefluxes_GM, coarsen, dump_resident, load_dump,
 )
 from . import synthetic  # noqa: F401
 

@@ -28,7 +28,7 @@ EXPORTS = [
     "otmb_plan_slabs", "otmb_set_slab_rows", "otmb_comm_unique_id", "otmb_comm_init", "otmb_comm_free", "otmb_comm_allgather_i64", "otmb_comm_chain_transport",
     "otmb_sharded_makeindices", "otmb_set_masstransport", "otmb_sharded_facefluxes", "otmb_sharded_facefluxes_enqueue",
     "otmb_sharded_transportmatrix_build", "otmb_result_checksum",
-    "otmb_facefluxes_gm", "otmb_transportmatrix_stream",
+    "otmb_facefluxes_gm", "otmb_transportmatrix_stream", "otmb_coarsen_build", "otmb_coarsen_fetch", "otmb_transportmatrix_dump",
 ]
 
 
@@ -95,6 +95,9 @@ def load():
         "otmb_spmv": ([vp, C.c_int, C.c_int, vp, vp], C.c_int),
         "otmb_set_slab": ([vp, i64, i64], C.c_int),
         "otmb_set_slab_rows": ([vp, i64, i64], C.c_int),
+        "otmb_coarsen_build": ([vp, C.c_int, pi64, pi64], C.c_int),
+        "otmb_coarsen_fetch": ([vp, vp, vp, vp], C.c_int),
+        "otmb_transportmatrix_dump": ([vp, C.c_int, C.c_char_p], C.c_int),
         "otmb_transportmatrix_stream": ([vp, C.POINTER(TMParams), C.POINTER(vp), vp, vp, i32, pi64, vp, vp, vp, pi64], C.c_int),
         "otmb_facefluxes_gm": ([vp, vp, vp, dbl, vp, dbl, dbl, dbl, i32] + [vp] * 8, C.c_int),
         "otmb_result_checksum": ([vp, C.c_int, i64, i64, C.POINTER(C.c_uint64)], C.c_int),

@@ -562,6 +562,41 @@ def lump_and_spray(wet3D, vol, T, mask=None, *, di=2, dj=2, dk=1, ctx=None):
     return LUMP, SPRAY, vol_c
 
 
+def coarsen(name="T", *, ctx=None):
+    """T_c = LUMP * T * SPRAY (test/local_full.jl:161) on the device, with the LUMP / SPRAY of the last `lump_and_spray`
+    call and the RESIDENT matrix `name` of the last `transportmatrix` call on this context — the coarse operator of the
+    reference's downstream solve, without moving T.  Returns a scipy CSC (N_c x N_c)."""
+    ctx = ctx or default_context()
+    Nc, nnz = C.c_int64(), C.c_int64()
+    ctx.check(ctx.lib.otmb_coarsen_build(ctx.h, _L.MAT[name], C.byref(Nc), C.byref(nnz)))
+    cp, rv, nz = np.empty(Nc.value + 1, np.int64), np.empty(nnz.value, np.int64), np.empty(nnz.value, np.float64)
+    ctx.check(ctx.lib.otmb_coarsen_fetch(ctx.h, _ptr(cp), _ptr(rv), _ptr(nz)))
+    return _csc(Nc.value, cp, rv, nz)
+
+
+def dump_resident(path, names=MATRICES, *, ctx=None):
+    """Write the resident result matrices of the last transportmatrix call to `path` (otmb_transportmatrix_dump: device ->
+    pinned staging -> file, no host matrices in between)."""
+    ctx = ctx or default_context()
+    mask = sum(1 << _L.MAT[n] for n in names)
+    ctx.check(ctx.lib.otmb_transportmatrix_dump(ctx.h, mask, str(path).encode()))
+
+
+def load_dump(path):
+    """Read a file written by `dump_resident` / otmb_transportmatrix_dump: dict name -> scipy CSC (0-based)."""
+    with open(path, "rb") as f:
+        assert f.read(8) == b"OTMBCSC1", "not an OTMBCSC1 file"
+        N, base, nmat = np.fromfile(f, "<i8", 3)
+        recs = np.fromfile(f, "<i8", 2 * nmat).reshape(nmat, 2)
+        out = {}
+        for mid, nnz in recs:
+            cp = np.fromfile(f, "<i8", N + 1) - base
+            rv = np.fromfile(f, "<i8", nnz) - base
+            nz = np.fromfile(f, "<f8", nnz)
+            out[MATRICES[mid]] = _csc(int(N), cp, rv, nz)
+    return out
+
+
 # ---- products with the resident matrices (no host copy of the matrix needed) ------------------------------
 def resident_matvec(name, x, *, transpose=False, ctx=None):
     """y = X @ x (or X.T @ x) with X the resident matrix `name` ("T", "Tadv", "TκH", "TκVML", "TκVdeep") of the last

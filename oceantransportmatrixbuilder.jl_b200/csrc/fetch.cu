@@ -714,3 +714,80 @@ extern "C" int otmb_transportmatrix_stream(otmb_ctx* c, const otmb_tm_params* pr
         for (int m = 0; m < 5; ++m) nnz_out[m] = c->nnz[m];
     return OTMB_OK;
 }
+
+// =======================================================================================================================
+// otmb_transportmatrix_dump — the resident result matrices straight to a binary file (the 12-month
+// batch keeps T on the device and writes it out without ever building host SparseMatrixCSC objects).  The arrays go
+// through two pinned 16 MB slots: while one is being written to the file the next chunk crosses the link.
+// File layout (little endian): 8 bytes magic "OTMBCSC1"; Int64 N, index_base, nmat; then per matrix Int64 id (OTMB_MAT_*),
+// Int64 nnz; then per matrix colptr (N+1 Int64), rowval (nnz Int64), nzval (nnz Float64) — the SparseMatrixCSC fields.
+// =======================================================================================================================
+extern "C" int otmb_transportmatrix_dump(otmb_ctx* c, int mask, const char* path) {
+    if (!c || !path || mask < 0 || mask > 31) return OTMB_ERR_BADARG;
+    if (mask == 0) mask = 31;
+    for (int m = 0; m < 5; ++m)
+        if (mask >> m & 1) OT_TRY(otmb_need(c, c->have_mat[m], "otmb_transportmatrix_build"));
+    CU_TRY(c, cudaSetDevice(c->device));
+    FetchState* f = nullptr;
+    OT_TRY(fetch_state(c, &f));
+    const size_t SLOT = CHUNK_BYTES;
+    if (f->stage_cap < 2 * SLOT) {
+        if (f->stage) cudaFreeHost(f->stage);
+        f->stage = nullptr, f->stage_cap = 0;
+        CU_TRY(c, cudaMallocHost((void**)&f->stage, 2 * SLOT));
+        f->stage_cap = 2 * SLOT;
+    }
+    while (f->ev.size() < 2) {
+        cudaEvent_t e;
+        CU_TRY(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        f->ev.push_back(e);
+    }
+    FILE* fp = fopen(path, "wb");
+    if (!fp) return otmb_fail(c, OTMB_ERR_BADARG, std::string("cannot open ") + path);
+    bool io_ok = true;
+    auto put = [&](const void* p, size_t n) { io_ok = io_ok && fwrite(p, 1, n, fp) == n; };
+    int64_t nmat = 0;
+    for (int m = 0; m < 5; ++m) nmat += mask >> m & 1;
+    const int64_t head[3] = {c->ncols, c->out_base, nmat};
+    put("OTMBCSC1", 8);
+    put(head, sizeof(head));
+    for (int m = 0; m < 5; ++m)
+        if (mask >> m & 1) {
+            const int64_t rec[2] = {m, c->nnz[m]};
+            put(rec, sizeof(rec));
+        }
+    // every array as a sequence of chunks through the two slots
+    struct Piece {
+        const char* dev;
+        size_t bytes;
+    };
+    std::vector<Piece> pieces;
+    for (int m = 0; m < 5; ++m)
+        if (mask >> m & 1) {
+            pieces.push_back({(const char*)c->colptr[m].p, (size_t)(c->ncols + 1) * 8});
+            pieces.push_back({(const char*)c->rowval[m].p, (size_t)c->nnz[m] * 8});
+            pieces.push_back({(const char*)c->nzval[m].p, (size_t)c->nnz[m] * 8});
+        }
+    std::vector<Piece> chunks;
+    for (const Piece& p : pieces)
+        for (size_t lo = 0; lo < p.bytes; lo += SLOT) chunks.push_back({p.dev + lo, std::min(SLOT, p.bytes - lo)});
+    int rc = OTMB_OK;
+    for (size_t q = 0; q <= chunks.size() && rc == OTMB_OK; ++q) {
+        if (q < chunks.size()) {   // chunk q into slot q & 1 (its previous content was written out two steps ago)
+            if (cudaMemcpyAsync(f->stage + (q & 1) * SLOT, chunks[q].dev, chunks[q].bytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                cudaEventRecord(f->ev[q & 1], c->stream) != cudaSuccess)
+                rc = otmb_fail(c, OTMB_ERR_CUDA, "copy-out for the dump failed");
+        }
+        if (q > 0 && rc == OTMB_OK) {   // ... while chunk q-1 goes to the file
+            if (cudaEventSynchronize(f->ev[(q - 1) & 1]) != cudaSuccess)
+                rc = otmb_fail(c, OTMB_ERR_CUDA, "copy-out for the dump failed");
+            else
+                put(f->stage + ((q - 1) & 1) * SLOT, chunks[q - 1].bytes);
+        }
+    }
+    cudaStreamSynchronize(c->stream);
+    io_ok = (fclose(fp) == 0) && io_ok;
+    if (rc != OTMB_OK) return rc;
+    if (!io_ok) return otmb_fail(c, OTMB_ERR_BADARG, std::string("write error on ") + path);
+    return OTMB_OK;
+}

@@ -121,6 +121,88 @@ __global__ void __launch_bounds__(128) k_lump_fill(LumpParams P, int nboxes, con
 
 __global__ void k_set_last(i64* p, i64 idx, i64 v) { p[idx] = v; }
 
+// ---- T_c = LUMP * T * SPRAY (/root/reference/test/local_full.jl:161: the step right behind lump_and_spray in every
+// downstream use).  Not a general SpGEMM: LUMP has ONE entry per column (the cell's box component I(k), weight w_k =
+// (1/vol_c) * 1 * vol) and SPRAY column J holds ones at the members of component J, so
+//     T_c[I, J] = sum over members j of J, ascending ( X[I, j] * 1.0 ),   X[I, j] = sum over rows k of T[:, j] with I(k) = I,
+//                                                                                  ascending ( w_k * T[k, j] )
+// which is exactly the order in which SparseArrays' Gustavson product (LUMP * T first, then * SPRAY) accumulates: the
+// first product of an entry is stored, later ones are added left to right.  One thread per coarse column J gathers
+// its entries into a small sorted list (a box of <= 32 cells with <= 7 entries per column touches few components);
+// PASS 0 counts, PASS 1 fills behind an exclusive scan of the counts.  Structural zeros are kept (the product does
+// not drop them).
+constexpr int TC_MAX = 96;   // distinct coarse rows one coarse column can hold before the kernel gives up
+struct TripleParams {
+    const i64 *t_colptr, *t_rowval;
+    const double* t_nzval;
+    int t_base;
+    const i64* lump_rowval;      // I(k), 0-based
+    const double* lump_nzval;    // w_k
+    const i64 *spray_colptr, *spray_rowval;   // members of component J, ascending, 0-based
+    i64 Nc;
+};
+template <int PASS>
+__global__ void __launch_bounds__(128) k_triple(TripleParams P, uint32_t* __restrict__ count, const i64* __restrict__ start, int base,
+                                                i64* __restrict__ out_colptr, i64* __restrict__ out_rowval,
+                                                double* __restrict__ out_nzval, int* __restrict__ overflow) {
+    const i64 J = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (J > P.Nc) return;
+    if (J == P.Nc) {
+        if (PASS == 0) count[J] = 0; else out_colptr[J] = start[J] + base;
+        return;
+    }
+    int rows[TC_MAX];
+    double vals[TC_MAX];
+    int n = 0;
+    bool over = false;
+    for (i64 e = P.spray_colptr[J]; e < P.spray_colptr[J + 1]; ++e) {
+        const i64 j = P.spray_rowval[e];
+        // X[:, j]: the coarse rows this fine column touches, each accumulated over T's rows in ascending order
+        int xr[8];
+        double xv[8];
+        int xn = 0;
+        for (i64 t = P.t_colptr[j] - P.t_base; t < P.t_colptr[j + 1] - P.t_base; ++t) {
+            const i64 k = P.t_rowval[t] - P.t_base;
+            const int I = (int)P.lump_rowval[k];
+            const double prod = P.lump_nzval[k] * P.t_nzval[t];
+            int q = 0;
+            while (q < xn && xr[q] != I) ++q;
+            if (q == xn) {
+                if (xn < 8) xr[xn] = I, xv[xn] = prod, ++xn;      // a column of T holds at most 7 entries
+            } else {
+                xv[q] = xv[q] + prod;
+            }
+        }
+        // T_c[:, J] += X[:, j] * 1.0
+        for (int q = 0; q < xn; ++q) {
+            const double term = xv[q] * 1.0;
+            int w = 0;
+            while (w < n && rows[w] != xr[q]) ++w;
+            if (w == n) {
+                if (n < TC_MAX) rows[n] = xr[q], vals[n] = term, ++n; else over = true;
+            } else {
+                vals[w] = vals[w] + term;
+            }
+        }
+    }
+    if (over) atomicOr(overflow, 1);
+    if (PASS == 0) {
+        count[J] = (uint32_t)n;
+        return;
+    }
+    // rows ascending inside the column, like every SparseMatrixCSC
+    for (int a = 1; a < n; ++a) {
+        const int r = rows[a];
+        const double v = vals[a];
+        int b = a - 1;
+        while (b >= 0 && rows[b] > r) rows[b + 1] = rows[b], vals[b + 1] = vals[b], --b;
+        rows[b + 1] = r, vals[b + 1] = v;
+    }
+    const i64 o = start[J];
+    out_colptr[J] = o + base;
+    for (int q = 0; q < n; ++q) out_rowval[o + q] = rows[q] + base, out_nzval[o + q] = vals[q];
+}
+
 }  // namespace
 
 extern "C" {
@@ -231,5 +313,57 @@ int otmb_lump_and_spray_fetch(otmb_ctx* c, int64_t* lump_colptr, int64_t* lump_r
     }
     return OTMB_OK;
 }
+
+// T_c = LUMP * T * SPRAY with the LUMP / SPRAY of the last otmb_lump_and_spray_build and the RESIDENT matrix `which`
+// (OTMB_MAT_*) of the last transportmatrix build: the coarse operator of the reference's downstream solve
+// (test/local_full.jl:161), built on the device, bit-identical to SparseArrays' product.  Two-phase like the other
+// sparse results: *n_coarse, *nnz, then otmb_coarsen_fetch (colptr N_c+1, rowval, nzval; index base of the lump build).
+int otmb_coarsen_build(otmb_ctx* c, int which, int64_t* n_coarse, int64_t* nnz) {
+    if (!c || which < 0 || which > 4) return OTMB_ERR_BADARG;
+    OT_TRY(otmb_need(c, c->have_lump, "otmb_lump_and_spray_build"));
+    OT_TRY(otmb_need(c, c->have_mat[which], "otmb_transportmatrix_build"));
+    CU_TRY(c, cudaSetDevice(c->device));
+    const i64 Nc = c->lump_nc;
+    TripleParams P;
+    P.t_colptr = c->colptr[which].as<i64>();
+    P.t_rowval = c->rowval[which].as<i64>();
+    P.t_nzval = c->nzval[which].as<double>();
+    P.t_base = c->out_base;
+    P.lump_rowval = c->lump[1].as<i64>();
+    P.lump_nzval = c->lump[2].as<double>();
+    P.spray_colptr = c->lump[3].as<i64>();
+    P.spray_rowval = c->lump[4].as<i64>();
+    P.Nc = Nc;
+    DevBuf* b = c->coo;   // scratch: 7 counts, 8 starts, 9 overflow flag
+    CU_TRY(c, b[7].ensure((size_t)(Nc + 2) * 4));
+    CU_TRY(c, b[8].ensure((size_t)(Nc + 2) * 8));
+    CU_TRY(c, b[9].ensure(8));
+    CU_TRY(c, cudaMemsetAsync(b[9].p, 0, 8, c->stream));
+    OT_TRY(otmb_reset_flags(c));
+    const unsigned grid = grid_for(Nc + 1, 128);
+    k_triple<0><<<grid, 128, 0, c->stream>>>(P, b[7].as<uint32_t>(), nullptr, 0, nullptr, nullptr, nullptr, b[9].as<int>());
+    LAUNCHED(c);
+    OT_TRY(otmb_scan_u32_to_i64(c, b[7].as<uint32_t>(), b[8].as<i64>(), Nc + 1, &c->flags.as<DevFlags>()->nnz[0]));
+    OT_TRY(otmb_fetch_flags(c));
+    int over = 0;
+    CU_TRY(c, cudaMemcpy(&over, b[9].p, 4, cudaMemcpyDeviceToHost));
+    if (over) return otmb_fail(c, OTMB_ERR_TOO_LARGE, "LUMP*T*SPRAY: a coarse column touches more than 96 coarse rows");
+    const i64 total = (i64)c->h_flags->nnz[0];
+    CU_TRY(c, c->sp_colptr.ensure((size_t)(Nc + 1) * 8));
+    CU_TRY(c, c->sp_rowval.ensure((size_t)(total + 1) * 8));
+    CU_TRY(c, c->sp_nzval.ensure((size_t)(total + 1) * 8));
+    k_triple<1><<<grid, 128, 0, c->stream>>>(P, nullptr, b[8].as<i64>(), c->lump_base, c->sp_colptr.as<i64>(), c->sp_rowval.as<i64>(),
+                                             c->sp_nzval.as<double>(), b[9].as<int>());
+    LAUNCHED(c);
+    CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    c->sp_n = Nc;
+    c->sp_nnz = total;
+    if (n_coarse) *n_coarse = Nc;
+    if (nnz) *nnz = total;
+    return OTMB_OK;
+}
+
+int otmb_coarsen_fetch(otmb_ctx* c, int64_t* colptr, int64_t* rowval, double* nzval) { return otmb_sparse_fetch(c, colptr, rowval, nzval); }
 
 }  // extern "C"

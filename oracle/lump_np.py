@@ -101,3 +101,32 @@ def lump_and_spray(wet3D, vol, T, mask=None, di=2, dj=2, dk=1):
     SPRAY.sort_indices()
     SPRAY.data[:] = 1.0
     return L2, SPRAY, vol_c
+
+
+def spmatmul(A, B):
+    """C = A * B as SparseArrays computes it (Gustavson, stdlib `spmatmul`; restated from its published algorithm, parity
+    unpinned): for each column j of B, for each stored B[k, j] in ascending k, for each stored A[i, k] in ascending i:
+    the first product for row i is stored, later ones are added, in that order; rows of the result column ascending;
+    no zero dropping.  A, B: scipy CSC with sorted indices.  Pure-Python loops: small cases only."""
+    import scipy.sparse as sp
+    A, B = sp.csc_matrix(A), sp.csc_matrix(B)
+    indptr, indices, data = [0], [], []
+    for j in range(B.shape[1]):
+        acc = {}
+        for t in range(B.indptr[j], B.indptr[j + 1]):
+            k, b = B.indices[t], B.data[t]
+            for s in range(A.indptr[k], A.indptr[k + 1]):
+                i, p = A.indices[s], A.data[s] * b
+                acc[i] = p if i not in acc else acc[i] + p
+        for i in sorted(acc):
+            indices.append(i)
+            data.append(acc[i])
+        indptr.append(len(indices))
+    C = sp.csc_matrix((A.shape[0], B.shape[1]), dtype=np.float64)
+    C.data, C.indices, C.indptr = np.array(data, np.float64), np.array(indices, np.int64), np.array(indptr, np.int64)
+    return C
+
+
+def coarsen(LUMP, T, SPRAY):
+    """T_c = LUMP * T * SPRAY, left to right like Julia parses it (/root/reference/test/local_full.jl:161)."""
+    return spmatmul(spmatmul(LUMP, T), SPRAY)

@@ -578,3 +578,20 @@ def test_stream_call_zero_dropping_errors_and_capacity():
     # and the context is still usable
     ok = A._transportmatrix_stream(c, o["ix"]["N"], phi, oc.mlotst, 1035.0, 500.0, 0.1, 1e-5, True)
     assert_csc_equal(ok.T, o["tm"]["T"], "after the failures")
+
+
+def test_binary_dump_of_resident_matrices(tmp_path):
+    """otmb_transportmatrix_dump: the resident matrices to a file and back, bit for bit (C2-sized arrays span several
+    16 MB staging chunks; C1t fits one)."""
+    for cfg in ("C1t", "C2"):
+        oc = synthetic.make_config(cfg, seed=1)
+        g = gpu_pipeline(oc)
+        path = tmp_path / f"{cfg}.otmbcsc"
+        otmb_b200.dump_resident(path)
+        back = otmb_b200.load_dump(path)
+        for name in A.MATRICES:
+            a, b = getattr(g["tm"], name), back[name]
+            assert a.shape == b.shape and np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices), name
+            assert np.array_equal(bits(a.data), bits(b.data)), name
+        otmb_b200.dump_resident(path, ("T",))
+        assert list(otmb_b200.load_dump(path)) == ["T"]

@@ -93,3 +93,43 @@ def test_gpu_lump_errors():
     Tasym = sp.csc_matrix(sp.triu(T))                                            # SimpleGraph would throw
     with pytest.raises(A.OTMBError):
         otmb_b200.lump_and_spray(wet, vol, Tasym)
+
+
+# ------------------------------------------------------------------------------------------ T_c = LUMP * T * SPRAY
+def test_spmatmul_restatement_against_scipy_and_by_hand():
+    """The Gustavson restatement (accumulation order of SparseArrays' product) agrees with scipy's product to rounding
+    and keeps structural zeros; a 2x2 example by hand."""
+    A_ = sp.csc_matrix(np.array([[1.0, 2.0], [0.0, 3.0]]))
+    B_ = sp.csc_matrix(np.array([[4.0, 0.0], [5.0, 6.0]]))
+    Cm = lump_np.spmatmul(A_, B_)
+    assert np.array_equal(Cm.toarray(), np.array([[14.0, 12.0], [15.0, 18.0]]))
+    Z = lump_np.spmatmul(sp.csc_matrix(np.array([[1.0, -1.0]])), sp.csc_matrix(np.array([[2.0], [2.0]])))
+    assert Z.nnz == 1 and Z.data[0] == 0.0                                     # 2 - 2: the zero is stored
+    wet, vol, T = _case((12, 10, 6), "tripolar", 0)
+    L, S, _ = lump_np.lump_and_spray(wet, vol, T)
+    Tc = lump_np.coarsen(L, T, S)
+    ref = sp.csc_matrix(L @ T @ S)
+    ref.sort_indices()
+    assert Tc.shape == ref.shape and np.array_equal(Tc.indptr, ref.indptr) and np.array_equal(Tc.indices, ref.indices)
+    np.testing.assert_allclose(Tc.data, ref.data, rtol=1e-13, atol=1e-25)
+    # volume conservation carries over to the coarse operator: v_cᵀ T_c = (vᵀ T) SPRAY
+    _, _, vc = lump_np.lump_and_spray(wet, vol, T)
+    np.testing.assert_allclose(Tc.T @ vc, S.T @ (T.T @ vol), rtol=0, atol=1e-9 * np.abs(Tc.diagonal() * vc).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("d", [(2, 2, 1), (3, 2, 2), (4, 4, 2)])
+@pytest.mark.parametrize("name", ["T", "TκH"])
+def test_gpu_coarse_operator_bit_exact(d, name):
+    """T_c = LUMP * T * SPRAY on the device (resident T, resident LUMP / SPRAY) against the restated SparseArrays product."""
+    from _util import gpu_pipeline
+    oc = synthetic.make_ocean(37, 11, 7, "tripolar", seed=6, land_frac=0.25)
+    g = gpu_pipeline(oc)
+    wet = g["ix"].wet3D
+    vol = g["gm"].v3D.ravel(order="F")[wet.ravel(order="F")]
+    X = getattr(g["tm"], name)
+    LUMP, SPRAY, vol_c = otmb_b200.lump_and_spray(wet, vol, g["tm"].T, di=d[0], dj=d[1], dk=d[2])
+    got = otmb_b200.coarsen(name)
+    want = lump_np.coarsen(LUMP, sp.csc_matrix(X), SPRAY)
+    assert got.shape == want.shape and np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
+    assert np.array_equal(bits(got.data), bits(want.data))
