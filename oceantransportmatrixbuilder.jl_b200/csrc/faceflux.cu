@@ -8,6 +8,7 @@
 // Threads are consecutive in i, so every load/store of a level is a coalesced row segment;
 // the west/south operands are the east/north values of the i-1 / j-1 columns re-read through
 // L1 (same or adjacent cache lines).  The wet tests use the packed bit mask.
+#include <cstddef>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -129,6 +130,126 @@ __global__ void __launch_bounds__(128) k_faceflux(const double* __restrict__ umo
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The same computation with the inputs staged by the bulk-copy engine (TMA, `cp.async.bulk`): used for a whole-grid launch
+// (no slab, no carry planes).  There are only nx*ny threads (108 000 at 1 degree, a third of the GPU's thread slots) and
+// the register-only way to keep more loads in flight — a deeper unroll — measured slower (profiles/README.md).  Here one
+// elected thread per block keeps FT_STAGES levels of the block's input rows in flight into shared memory — per level three
+// contiguous segments: umo[p0-2 .. p0+128) (own east flux + the west neighbour's), vmo[p0 .. p0+128), vmo[p0-nx ..
+// p0-nx+128) (the south neighbour's north flux) — each completing on the slot's mbarrier; the 128 threads take their
+// operands from the slot, hand it back for the level FT_STAGES further up, and compute / store as before.  The queue to
+// DRAM stays full while the threads compute, independent of the thread count.  Needs nx and nx*ny even (16-byte source
+// alignment of every segment); other grids take the plain kernel.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int FT_TI = 128, FT_STAGES = 8;
+struct FtSlot {
+    double u[FT_TI + 2];
+    double vn[FT_TI];
+    double vs[FT_TI];
+};
+static_assert(sizeof(FtSlot) % 16 == 0 && offsetof(FtSlot, vn) % 16 == 0 && offsetof(FtSlot, vs) % 16 == 0, "16-byte aligned segments");
+
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}" ::"r"(
+            smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(FT_TI) k_faceflux_tile(const double* __restrict__ umo, const double* __restrict__ vmo,
+                                                         const u64* __restrict__ mask, GridDims g, double fill,
+                                                         double* __restrict__ east, double* __restrict__ west,
+                                                         double* __restrict__ north, double* __restrict__ south,
+                                                         double* __restrict__ top, double* __restrict__ bottom,
+                                                         DevFlags* __restrict__ flags) {
+    __shared__ __align__(128) FtSlot slot[FT_STAGES];
+    __shared__ __align__(8) unsigned long long full[FT_STAGES];
+    const int tid = threadIdx.x, p0 = blockIdx.x * FT_TI, p = p0 + tid;
+    const int pend = min(p0 + FT_TI, g.P);
+    // the three segments of a level, in columns of the plane (all even: p0, nx and P are)
+    const int ua = max(p0 - 2, 0), un = pend - ua;
+    const int vn_n = pend - p0;
+    const int vs_lo = max(p0 - g.nx, 0), vs_n = max(pend - g.nx - vs_lo, 0);
+    const unsigned bytes = (unsigned)(un + vn_n + vs_n) * 8u;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < FT_STAGES; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&full[s])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](const int k) {   // one thread: arm the slot's barrier with the byte count, then the three copies
+        FtSlot& S = slot[k % FT_STAGES];
+        unsigned long long* bar = &full[k % FT_STAGES];
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+        const size_t off = (size_t)k * g.P;
+        bulk_load(S.u, umo + off + ua, (unsigned)un * 8u, bar);
+        bulk_load(S.vn, vmo + off + p0, (unsigned)vn_n * 8u, bar);
+        if (vs_n > 0) bulk_load(S.vs, vmo + off + vs_lo, (unsigned)vs_n * 8u, bar);
+    };
+    if (tid == 0)
+        for (int q = 0; q < FT_STAGES; ++q)
+            if (g.nz - 1 - q >= 0) issue(g.nz - 1 - q);
+    const bool in = p < g.P;
+    const int pc = in ? p : g.P - 1;   // threads past the plane follow the last column and store nothing
+    const int i = pc % g.nx, j = pc / g.nx;
+    const int pE = i < g.nx - 1 ? pc + 1 : pc - (g.nx - 1);
+    const int pW = i > 0 ? pc - 1 : pc + (g.nx - 1);
+    const int pS = j > 0 ? pc - g.nx : -1;
+    const int pN = j < g.ny - 1 ? pc + g.nx : (g.topo == OTMB_TOPO_TRIPOLAR ? (g.nx - 1 - i) + g.nx * (g.ny - 1) : -1);
+    bool valid_u = false, valid_v = false;
+    double carry = 0.0;   // phi_top of the level below: 0 under the sea floor
+    for (int k = g.nz - 1; k >= 0; --k) {
+        const int s = k % FT_STAGES;
+        bar_wait(&full[s], (unsigned)(((g.nz - 1 - k) / FT_STAGES) & 1));
+        const FtSlot& S = slot[s];
+        const int off = k * g.P;
+        // operands out of the slot (the west neighbour of i = 0 sits at the other end of the row: a plain load)
+        const double ue_raw = S.u[pc - ua];
+        const double uw_raw = i > 0 ? S.u[pc - 1 - ua] : __ldg(umo + off + pW);
+        const double vn_raw = S.vn[pc - p0];
+        const double vs_raw = pS >= 0 ? S.vs[pS - vs_lo] : 0.0;
+        __syncthreads();                                   // every thread holds its operands: the slot is free
+        if (tid == 0 && k - FT_STAGES >= 0) issue(k - FT_STAGES);
+        const int L = off + pc;
+        const bool wc = wet_at(mask, L);
+        const bool wE = wet_at(mask, off + pE);
+        const bool wW = wet_at(mask, off + pW);
+        const bool wN = pN >= 0 && wet_at(mask, off + pN);
+        const bool wS = pS >= 0 && wet_at(mask, off + pS);
+        // nofluxboundaries!: zero at dry cells and towards dry/absent east / north neighbours
+        const double ue = (wc && wE) ? ue_raw : 0.0;
+        const double vn = (wc && wN) ? vn_raw : 0.0;
+        const double uw = (wW && wc) ? uw_raw : 0.0;
+        const double vs = (wS && wc) ? vs_raw : 0.0;   // north nbr of (i,j-1) is (i,j)
+        valid_u |= in && !(isnan(ue) || ue == fill);
+        valid_v |= in && !(isnan(vn) || vn == fill);
+        const double e = clean(ue, fill), n = clean(vn, fill), w = clean(uw, fill), so = clean(vs, fill);
+        const double b = carry;
+        const double t = (((b + w) + so) - e) - n;
+        if (in) {
+            __stcs(east + L, e);
+            __stcs(west + L, w);
+            __stcs(north + L, n);
+            __stcs(south + L, so);
+            __stcs(bottom + L, b);
+            __stcs(top + L, t);
+        }
+        carry = t;
+    }
+    const unsigned bu = __ballot_sync(0xffffffffu, valid_u), bv = __ballot_sync(0xffffffffu, valid_v);
+    if ((tid & 31) == 0) {
+        if (bu) atomicOr(&flags->any_valid_u, 1);
+        if (bv) atomicOr(&flags->any_valid_v, 1);
+    }
+}
+
 // A slab cut inside a level: the assembly of the first / last owned grid row reads the north-face flux of the row
 // before it and the south-face flux of the row after it (its south / north neighbours, same level, owned by the
 // adjacent rank).  Both are pure functions of the inputs (vmo + mask, src/velocities.jl:169-174, :213-221), which the
@@ -174,6 +295,21 @@ int otmb_faceflux_begin(otmb_ctx* c, double fill) {
 int otmb_faceflux_columns(otmb_ctx* c, double fill, i64 p_begin, i64 p_end, const double* d_in, double* d_out, PeerLink link) {
     if (p_end <= p_begin) return OTMB_OK;
     GridDims g{(int)c->nx, (int)c->ny, (int)c->nz, c->topo, (int)c->P, (int)c->M};
+    // whole grid, no carry planes, segments 16-byte aligned: inputs staged by the bulk-copy engine (k_faceflux_tile)
+    bool tile = !c->sharded && p_begin == 0 && p_end == c->P && !d_in && !d_out && !link.flag_in && !link.flag_out && c->nx % 2 == 0 &&
+                c->P % 2 == 0 && c->nx >= 2;
+#ifdef OTMB_AB
+    if (getenv("OTMB_FACEFLUX_PLAIN")) tile = false;
+#endif
+    if (tile) {
+        k_faceflux_tile<<<grid_for(c->P, FT_TI), FT_TI, 0, c->stream>>>(
+            c->stage_a.as<double>(), c->stage_b.as<double>(), c->mask.as<u64>(), g, fill, c->phi[OTMB_FACE_EAST].as<double>(),
+            c->phi[OTMB_FACE_WEST].as<double>(), c->phi[OTMB_FACE_NORTH].as<double>(), c->phi[OTMB_FACE_SOUTH].as<double>(),
+            c->phi[OTMB_FACE_TOP].as<double>(), c->phi[OTMB_FACE_BOTTOM].as<double>(), c->flags.as<DevFlags>());
+        LAUNCHED(c);
+        CU_TRY(c, cudaGetLastError());
+        return OTMB_OK;
+    }
     // Five levels of loads in flight per column.  Ten were measured slower even on the 1-degree grid, where there are
     // only 108 000 columns (74 us vs 121 us, profiles/README.md): the batch then no longer fits the registers.
     int unroll = 5;

@@ -16,8 +16,10 @@ oc = synthetic.make_config(cfg, seed=0)
 f = fields(oc)
 ctx = A.Context(0)
 for rep in range(3):
-    for unroll in ("5", "10"):
-        os.environ["OTMB_FACEFLUX_UNROLL"] = unroll          # read by measurement builds only (-DOTMB_AB)
+    for plain in (False, True):
+        os.environ.pop("OTMB_FACEFLUX_PLAIN", None)          # read by measurement builds only (-DOTMB_AB):
+        if plain:                                            # the plain kernel instead of the bulk-copy tile kernel
+            os.environ["OTMB_FACEFLUX_PLAIN"] = "1"
         gm = A.makegridmetrics(areacello=f["areacello"], volcello=f["volcello"], lon=f["lon"], lat=f["lat"], lev=f["lev"],
                                lon_vertices=f["lon_vertices"], lat_vertices=f["lat_vertices"], ctx=ctx)
         A.facefluxesfrommasstransport(umo=f["umo"], vmo=f["vmo"], gridmetrics=gm, indices=None, ctx=ctx)
