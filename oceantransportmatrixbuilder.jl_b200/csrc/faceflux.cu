@@ -131,8 +131,7 @@ __global__ void __launch_bounds__(128) k_faceflux(const double* __restrict__ umo
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// The same computation with the inputs staged by the bulk-copy engine (TMA, `cp.async.bulk`): used for a whole-grid launch
-// (no slab, no carry planes).  There are only nx*ny threads (108 000 at 1 degree, a third of the GPU's thread slots) and
+// The same computation with the inputs staged by the bulk-copy engine (TMA, `cp.async.bulk`).  There are only nx*ny threads (108 000 at 1 degree, a third of the GPU's thread slots) and
 // the register-only way to keep more loads in flight — a deeper unroll — measured slower (profiles/README.md).  Here one
 // elected thread per block keeps FT_STAGES levels of the block's input rows in flight into shared memory — per level three
 // contiguous segments: umo[p0-2 .. p0+128) (own east flux + the west neighbour's), vmo[p0 .. p0+128), vmo[p0-nx ..
@@ -168,11 +167,15 @@ __global__ void __launch_bounds__(FT_TI) k_faceflux_tile(const double* __restric
                                                          double* __restrict__ east, double* __restrict__ west,
                                                          double* __restrict__ north, double* __restrict__ south,
                                                          double* __restrict__ top, double* __restrict__ bottom,
-                                                         DevFlags* __restrict__ flags) {
+                                                         DevFlags* __restrict__ flags, int row0, int row1, int p_begin, int p_end,
+                                                         const double* __restrict__ carry_in, double* __restrict__ carry_out,
+                                                         PeerLink link) {
+    // (same arguments and semantics as k_faceflux: window-biased 3-D pointers, columns [p_begin, p_end), owned rows
+    // [row0, row1), carry planes / peer link of a slab chain; p_begin is a multiple of FT_TI)
     __shared__ __align__(128) FtSlot slot[FT_STAGES];
     __shared__ __align__(8) unsigned long long full[FT_STAGES];
-    const int tid = threadIdx.x, p0 = blockIdx.x * FT_TI, p = p0 + tid;
-    const int pend = min(p0 + FT_TI, g.P);
+    const int tid = threadIdx.x, p0 = p_begin + blockIdx.x * FT_TI, p = p0 + tid;
+    const int pend = min(p0 + FT_TI, p_end);
     // the three segments of a level, in columns of the plane (all even: p0, nx and P are)
     const int ua = max(p0 - 2, 0), un = pend - ua;
     const int vn_n = pend - p0;
@@ -184,9 +187,13 @@ __global__ void __launch_bounds__(FT_TI) k_faceflux_tile(const double* __restric
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // levels the block visits: from the deepest owned level of its first column (smallest j) up to the first owned level
+    // of its last column — the owned ranges of the columns of a block differ by at most the rows it spans
+    const int kmax = (row1 - p0 / g.nx + g.ny - 1) / g.ny, kmin = (row0 - (pend - 1) / g.nx + g.ny - 1) / g.ny;
     auto issue = [&](const int k) {   // one thread: arm the slot's barrier with the byte count, then the three copies
-        FtSlot& S = slot[k % FT_STAGES];
-        unsigned long long* bar = &full[k % FT_STAGES];
+        const int s = (kmax - 1 - k) % FT_STAGES;
+        FtSlot& S = slot[s];
+        unsigned long long* bar = &full[s];
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
         const size_t off = (size_t)k * g.P;
         bulk_load(S.u, umo + off + ua, (unsigned)un * 8u, bar);
@@ -195,28 +202,50 @@ __global__ void __launch_bounds__(FT_TI) k_faceflux_tile(const double* __restric
     };
     if (tid == 0)
         for (int q = 0; q < FT_STAGES; ++q)
-            if (g.nz - 1 - q >= 0) issue(g.nz - 1 - q);
-    const bool in = p < g.P;
-    const int pc = in ? p : g.P - 1;   // threads past the plane follow the last column and store nothing
+            if (kmax - 1 - q >= kmin) issue(kmax - 1 - q);
+    const bool in = p < pend;
+    const int pc = in ? p : pend - 1;   // threads past the end follow the last column and store nothing
     const int i = pc % g.nx, j = pc / g.nx;
+    const int k_begin = (row0 - j + g.ny - 1) / g.ny, k_end = (row1 - j + g.ny - 1) / g.ny;   // this column's owned levels
+    const bool owns = in && k_begin < k_end;
     const int pE = i < g.nx - 1 ? pc + 1 : pc - (g.nx - 1);
     const int pW = i > 0 ? pc - 1 : pc + (g.nx - 1);
     const int pS = j > 0 ? pc - g.nx : -1;
     const int pN = j < g.ny - 1 ? pc + g.nx : (g.topo == OTMB_TOPO_TRIPOLAR ? (g.nx - 1 - i) + g.nx * (g.ny - 1) : -1);
     bool valid_u = false, valid_v = false;
-    double carry = 0.0;   // phi_top of the level below: 0 under the sea floor
-    for (int k = g.nz - 1; k >= 0; --k) {
-        const int s = k % FT_STAGES;
-        bar_wait(&full[s], (unsigned)(((g.nz - 1 - k) / FT_STAGES) & 1));
+    // phi_top of the level below: 0 under the sea floor, or the plane handed up by the slab below (see k_faceflux)
+    double carry = 0.0;
+    if (link.flag_in) {
+        if (tid == 0) {
+            unsigned v, spins = 0;
+            do {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(link.flag_in + blockIdx.x) : "memory");
+            } while (v != link.epoch && ++spins < (1u << 25));
+            if (v != link.epoch) atomicOr(&flags->lookback_timeout, 1);
+        }
+        __syncthreads();
+        if (in) carry = __ldcv(carry_in + p);
+        __syncthreads();
+        if (tid == 0)
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(link.ack_out + blockIdx.x), "r"(link.epoch) : "memory");
+    } else if (carry_in && in) {
+        carry = carry_in[p];
+    }
+    if (owns && carry_in && k_end < g.nz) top[(size_t)k_end * g.P + p] = carry;   // halo cell below: its top flux
+    for (int k = kmax - 1; k >= kmin; --k) {
+        const int q = kmax - 1 - k, s = q % FT_STAGES;
+        bar_wait(&full[s], (unsigned)((q / FT_STAGES) & 1));
         const FtSlot& S = slot[s];
         const int off = k * g.P;
         // operands out of the slot (the west neighbour of i = 0 sits at the other end of the row: a plain load)
+        const bool act = owns && k >= k_begin && k < k_end;
         const double ue_raw = S.u[pc - ua];
-        const double uw_raw = i > 0 ? S.u[pc - 1 - ua] : __ldg(umo + off + pW);
+        const double uw_raw = i > 0 ? S.u[pc - 1 - ua] : (act ? __ldg(umo + off + pW) : 0.0);
         const double vn_raw = S.vn[pc - p0];
         const double vs_raw = pS >= 0 ? S.vs[pS - vs_lo] : 0.0;
         __syncthreads();                                   // every thread holds its operands: the slot is free
-        if (tid == 0 && k - FT_STAGES >= 0) issue(k - FT_STAGES);
+        if (tid == 0 && k - FT_STAGES >= kmin) issue(k - FT_STAGES);
+        if (!act) continue;
         const int L = off + pc;
         const bool wc = wet_at(mask, L);
         const bool wE = wet_at(mask, off + pE);
@@ -228,25 +257,40 @@ __global__ void __launch_bounds__(FT_TI) k_faceflux_tile(const double* __restric
         const double vn = (wc && wN) ? vn_raw : 0.0;
         const double uw = (wW && wc) ? uw_raw : 0.0;
         const double vs = (wS && wc) ? vs_raw : 0.0;   // north nbr of (i,j-1) is (i,j)
-        valid_u |= in && !(isnan(ue) || ue == fill);
-        valid_v |= in && !(isnan(vn) || vn == fill);
+        valid_u |= !(isnan(ue) || ue == fill);
+        valid_v |= !(isnan(vn) || vn == fill);
         const double e = clean(ue, fill), n = clean(vn, fill), w = clean(uw, fill), so = clean(vs, fill);
         const double b = carry;
         const double t = (((b + w) + so) - e) - n;
-        if (in) {
-            __stcs(east + L, e);
-            __stcs(west + L, w);
-            __stcs(north + L, n);
-            __stcs(south + L, so);
-            __stcs(bottom + L, b);
-            __stcs(top + L, t);
-        }
+        __stcs(east + L, e);
+        __stcs(west + L, w);
+        __stcs(north + L, n);
+        __stcs(south + L, so);
+        __stcs(bottom + L, b);
+        __stcs(top + L, t);
         carry = t;
     }
+    if (in && carry_out && !link.flag_out) carry_out[p] = carry;   // phi_top of the column's first owned level (passed on if it owns nothing)
+    if (owns && k_begin > 0) bottom[(size_t)(k_begin - 1) * g.P + p] = carry;   // halo cell above: its bottom flux
     const unsigned bu = __ballot_sync(0xffffffffu, valid_u), bv = __ballot_sync(0xffffffffu, valid_v);
     if ((tid & 31) == 0) {
         if (bu) atomicOr(&flags->any_valid_u, 1);
         if (bv) atomicOr(&flags->any_valid_v, 1);
+    }
+    if (link.flag_out) {   // carry_out is the inbox of the rank above (mapped peer memory), see k_faceflux
+        if (tid == 0) {
+            unsigned v, spins = 0;
+            do {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(link.ack_in + blockIdx.x) : "memory");
+            } while ((int)(v - (link.epoch - 1u)) < 0 && ++spins < (1u << 25));
+            if ((int)(v - (link.epoch - 1u)) < 0) atomicOr(&flags->lookback_timeout, 1);
+        }
+        __syncthreads();
+        if (in) carry_out[p] = carry;
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0)
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(link.flag_out + blockIdx.x), "r"(link.epoch) : "memory");
     }
 }
 
@@ -295,17 +339,17 @@ int otmb_faceflux_begin(otmb_ctx* c, double fill) {
 int otmb_faceflux_columns(otmb_ctx* c, double fill, i64 p_begin, i64 p_end, const double* d_in, double* d_out, PeerLink link) {
     if (p_end <= p_begin) return OTMB_OK;
     GridDims g{(int)c->nx, (int)c->ny, (int)c->nz, c->topo, (int)c->P, (int)c->M};
-    // whole grid, no carry planes, segments 16-byte aligned: inputs staged by the bulk-copy engine (k_faceflux_tile)
-    bool tile = !c->sharded && p_begin == 0 && p_end == c->P && !d_in && !d_out && !link.flag_in && !link.flag_out && c->nx % 2 == 0 &&
-                c->P % 2 == 0 && c->nx >= 2;
+    // segments 16-byte aligned (nx and nx*ny even): inputs staged by the bulk-copy engine (k_faceflux_tile)
+    bool tile = c->nx % 2 == 0 && c->P % 2 == 0 && c->nx >= 2 && p_begin % FT_TI == 0;
 #ifdef OTMB_AB
     if (getenv("OTMB_FACEFLUX_PLAIN")) tile = false;
 #endif
     if (tile) {
-        k_faceflux_tile<<<grid_for(c->P, FT_TI), FT_TI, 0, c->stream>>>(
-            c->stage_a.as<double>(), c->stage_b.as<double>(), c->mask.as<u64>(), g, fill, c->phi[OTMB_FACE_EAST].as<double>(),
-            c->phi[OTMB_FACE_WEST].as<double>(), c->phi[OTMB_FACE_NORTH].as<double>(), c->phi[OTMB_FACE_SOUTH].as<double>(),
-            c->phi[OTMB_FACE_TOP].as<double>(), c->phi[OTMB_FACE_BOTTOM].as<double>(), c->flags.as<DevFlags>());
+        k_faceflux_tile<<<grid_for(p_end - p_begin, FT_TI), FT_TI, 0, c->stream>>>(
+            c->win<double>(c->stage_a), c->win<double>(c->stage_b), c->mask_win(), g, fill, c->win<double>(c->phi[OTMB_FACE_EAST]),
+            c->win<double>(c->phi[OTMB_FACE_WEST]), c->win<double>(c->phi[OTMB_FACE_NORTH]), c->win<double>(c->phi[OTMB_FACE_SOUTH]),
+            c->win<double>(c->phi[OTMB_FACE_TOP]), c->win<double>(c->phi[OTMB_FACE_BOTTOM]), c->flags.as<DevFlags>(),
+            (int)(c->L_own0 / c->nx), (int)(c->L_own1 / c->nx), (int)p_begin, (int)p_end, d_in, d_out, link);
         LAUNCHED(c);
         CU_TRY(c, cudaGetLastError());
         return OTMB_OK;
