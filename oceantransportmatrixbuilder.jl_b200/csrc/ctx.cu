@@ -6,6 +6,8 @@
 // the per-word popcounts.  wet index of cell L = wpre[L/64] + popc(mask[L/64] & lowbits(L%64)):
 // 12 bytes per 64 cells instead of the reference's 9 bytes per cell Lwet3D array, small
 // enough to live in L1/L2 for every neighbour query of the assembly kernels.
+#include <cooperative_groups.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -34,100 +36,112 @@ __global__ void __launch_bounds__(256) k_fill_lwet32(const u64* __restrict__ mas
     if (wet) lwet[r] = (int)L;
 }
 
-// makeindices in ONE pass (src/matrixbuilding.jl:10-24): wet mask (ballots -> the BitArray chunks), wet count per chunk,
-// exclusive scan over the whole grid (decoupled look-back over the blocks, one counter) and — when the wet-rank offset is
-// already known (FILL: unsharded contexts) — Lwet3D (`rank3d`, -1 = dry) and the compacted wet list, all from the one read
-// of v3D.  A block owns MI_WORDS chunks of 64 cells (8 warps x MI_WPW chunks); blocks publish in index order.
+// makeindices in ONE launch (src/matrixbuilding.jl:10-24), two phases around a grid-wide barrier (cooperative launch,
+// every block resident).  A block owns a contiguous range of 64-cell chunks.
+//   phase 1: the one read of v3D — `isnan` -> ballots = the BitArray chunks, written out; the block's wet count
+//   grid.sync()
+//   phase 2: exclusive prefix of the block counts (a few thousand values, summed by every block for itself), then the
+//            block walks its range again FROM THE MASK (1 bit per cell, L2-resident) 32 chunks at a time: per-chunk
+//            prefix, and — when the wet-rank offset is already known (FILL: unsharded contexts) — Lwet3D (`rank3d`,
+//            -1 = dry) and the compacted wet list.
+// No serial dependency between blocks (a decoupled look-back over 38 000 small blocks ran at 43 % of the HBM roofline on
+// the 0.25-degree grid: every block waits for the prefix to travel down the chain), and no second read of v3D.
 // Algorithmic bytes: read 8 per cell; write 1/8 + 1/16 per cell, and with FILL 4 per cell + 4 per wet cell.
-#ifndef OTMB_MI_WPW
-#define OTMB_MI_WPW 4
-#endif
-constexpr int MI_WPW = OTMB_MI_WPW, MI_WARPS = 8, MI_WORDS = MI_WPW * MI_WARPS;
+constexpr int MI_WPW = 4, MI_WARPS = 8, MI_WORDS = MI_WPW * MI_WARPS;
 template <bool FILL>
 __global__ void __launch_bounds__(32 * MI_WARPS) k_makeindices(const double* __restrict__ v3D, i64 L0, i64 L1, i64 word0, i64 word1,
                                                                u64* __restrict__ mask, uint32_t* __restrict__ wpre,
                                                                int* __restrict__ rank3d, int* __restrict__ lwet, int rank_offset,
-                                                               u64* __restrict__ desc, u64* __restrict__ total) {
-    constexpr u64 AGG = 1ull << 62, PRE = 2ull << 62, VAL = (1ull << 62) - 1;
+                                                               unsigned* __restrict__ block_tot, u64* __restrict__ total) {
     __shared__ unsigned s_wtot[MI_WARPS];
     __shared__ unsigned s_base;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const i64 wfirst = word0 + (i64)blockIdx.x * MI_WORDS + wid * MI_WPW;
-    unsigned lo[MI_WPW], hi[MI_WPW], cnt[MI_WPW];
+    // this block's chunks: rounds of MI_WORDS chunks (8 warps x 4), the same split in both phases
+    const i64 nwords = word1 - word0;
+    const i64 rounds_all = (nwords + MI_WORDS - 1) / MI_WORDS;
+    const i64 r0 = rounds_all * blockIdx.x / gridDim.x, r1 = rounds_all * (blockIdx.x + 1) / gridDim.x;
     const double dry = __longlong_as_double(0x7ff8000000000000ll);
-    double va[MI_WPW], vb[MI_WPW];
+    // ---------------- phase 1: mask + block count
+    unsigned mine = 0;
+    for (i64 r = r0; r < r1; ++r) {
+        const i64 wfirst = word0 + r * MI_WORDS + wid * MI_WPW;
+        double va[MI_WPW], vb[MI_WPW];
 #pragma unroll
-    for (int q = 0; q < MI_WPW; ++q) {   // all eight loads of a lane in flight at once
-        const i64 a = (wfirst + q) * 64 + lane, b = a + 32;
-        va[q] = (wfirst + q < word1 && a >= L0 && a < L1) ? __ldg(v3D + a) : dry;
-        vb[q] = (wfirst + q < word1 && b >= L0 && b < L1) ? __ldg(v3D + b) : dry;
-    }
-    unsigned wsum = 0;
-#pragma unroll
-    for (int q = 0; q < MI_WPW; ++q) {
-        lo[q] = __ballot_sync(0xffffffffu, !isnan(va[q]));
-        hi[q] = __ballot_sync(0xffffffffu, !isnan(vb[q]));
-        cnt[q] = __popc(lo[q]) + __popc(hi[q]);
-        wsum += cnt[q];
-    }
-    if (lane == 0) s_wtot[wid] = wsum;
-    __syncthreads();
-    if (wid == 0) {   // block total -> publish -> look back over the lower blocks, 32 at a time
-        unsigned tot = 0;
-#pragma unroll
-        for (int q = 0; q < MI_WARPS; ++q) tot += s_wtot[q];
-        const int b = blockIdx.x;
-        if (lane == 0) {
-            const u64 d = (b == 0 ? PRE : AGG) | (u64)tot;
-            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(desc + b), "l"(d) : "memory");
+        for (int q = 0; q < MI_WPW; ++q) {   // all eight loads of a lane in flight at once
+            const i64 a = (wfirst + q) * 64 + lane, b = a + 32;
+            va[q] = (wfirst + q < word1 && a >= L0 && a < L1) ? __ldcs(v3D + a) : dry;
+            vb[q] = (wfirst + q < word1 && b >= L0 && b < L1) ? __ldcs(v3D + b) : dry;
         }
-        u64 excl = 0;
-        int look = b - 1;
-        while (look >= 0) {
-            const int t = look - lane;
-            u64 v = PRE;   // before the first block: prefix 0
-            if (t >= 0) do {
-                    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(desc + t) : "memory");
-                } while ((v >> 62) == 0);
-            const unsigned pm = __ballot_sync(0xffffffffu, (v >> 62) == 2);
-            const int first = pm ? __ffs(pm) - 1 : 32;
-            u64 part = lane <= first ? (v & VAL) : 0ull;   // aggregates up to and including the first inclusive prefix
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-            excl += part;
-            if (pm) break;
-            look -= 32;
-        }
-        if (lane == 0) {
-            if (b > 0) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(desc + b), "l"(PRE | (excl + tot)) : "memory");
-            s_base = (unsigned)excl;
-            if (b == (int)gridDim.x - 1) *total = excl + tot;
-        }
-    }
-    __syncthreads();
-    unsigned pre = s_base;
-#pragma unroll
-    for (int q = 0; q < MI_WARPS; ++q) pre += q < wid ? s_wtot[q] : 0u;
-#pragma unroll
-    for (int q = 0; q < MI_WPW; ++q) {
-        const i64 w = wfirst + q;
-        if (w < word1) {
-            if (lane == 0) {
-                mask[w] = (u64)lo[q] | ((u64)hi[q] << 32);
-                wpre[w] = pre;
-            }
-            if (FILL) {
-                const i64 a = w * 64 + lane, b = a + 32;
-                const unsigned below = (1u << lane) - 1u;
-                const int ra = (int)(pre + __popc(lo[q] & below)), rb = (int)(pre + __popc(lo[q]) + __popc(hi[q] & below));
-                const bool wa = lo[q] >> lane & 1u, wb = hi[q] >> lane & 1u;
-                if (a >= L0 && a < L1) rank3d[a] = wa ? ra + rank_offset : -1;
-                if (b >= L0 && b < L1) rank3d[b] = wb ? rb + rank_offset : -1;
-                if (wa) lwet[ra] = (int)a;
-                if (wb) lwet[rb] = (int)b;
+        for (int q = 0; q < MI_WPW; ++q) {
+            const unsigned lo = __ballot_sync(0xffffffffu, !isnan(va[q])), hi = __ballot_sync(0xffffffffu, !isnan(vb[q]));
+            if (wfirst + q < word1) {
+                if (lane == 0) mask[wfirst + q] = (u64)lo | ((u64)hi << 32);
+                mine += __popc(lo) + __popc(hi);
             }
         }
-        pre += cnt[q];
+    }
+    if (lane == 0) s_wtot[wid] = mine;   // (every lane of a warp holds the same count)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+#pragma unroll
+        for (int q = 0; q < MI_WARPS; ++q) t += s_wtot[q];
+        block_tot[blockIdx.x] = t;
+    }
+    __threadfence();
+    cooperative_groups::this_grid().sync();
+    // ---------------- phase 2: prefix of the block counts, then the block's chunks again from the mask
+    unsigned part = 0;
+    for (int b = threadIdx.x; b < (int)blockIdx.x; b += blockDim.x) part += __ldcg(block_tot + b);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    __syncthreads();   // s_wtot is reused
+    if (lane == 0) s_wtot[wid] = part;
+    __syncthreads();
+    unsigned base = 0;
+#pragma unroll
+    for (int q = 0; q < MI_WARPS; ++q) base += s_wtot[q];
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *total = (u64)base + __ldcg(block_tot + blockIdx.x);
+    for (i64 r = r0; r < r1; ++r) {
+        const i64 wfirst = word0 + r * MI_WORDS + wid * MI_WPW;
+        u64 word[MI_WPW];
+        unsigned cnt[MI_WPW], wsum = 0;
+#pragma unroll
+        for (int q = 0; q < MI_WPW; ++q) {
+            word[q] = wfirst + q < word1 ? __ldcg(mask + wfirst + q) : 0ull;
+            cnt[q] = __popcll(word[q]);
+            wsum += cnt[q];
+        }
+        __syncthreads();
+        if (lane == 0) s_wtot[wid] = wsum;
+        __syncthreads();
+        unsigned pre = base, round_tot = 0;
+#pragma unroll
+        for (int q = 0; q < MI_WARPS; ++q) {
+            pre += q < wid ? s_wtot[q] : 0u;
+            round_tot += s_wtot[q];
+        }
+#pragma unroll
+        for (int q = 0; q < MI_WPW; ++q) {
+            const i64 w = wfirst + q;
+            if (w < word1) {
+                if (lane == 0) wpre[w] = pre;
+                if (FILL) {
+                    const unsigned lo = (unsigned)word[q], hi = (unsigned)(word[q] >> 32);
+                    const i64 a = w * 64 + lane, b = a + 32;
+                    const unsigned below = (1u << lane) - 1u;
+                    const int ra = (int)(pre + __popc(lo & below)), rb = (int)(pre + __popc(lo) + __popc(hi & below));
+                    const bool wa = lo >> lane & 1u, wb = hi >> lane & 1u;
+                    if (a >= L0 && a < L1) rank3d[a] = wa ? ra + rank_offset : -1;
+                    if (b >= L0 && b < L1) rank3d[b] = wb ? rb + rank_offset : -1;
+                    if (wa) lwet[ra] = (int)a;
+                    if (wb) lwet[rb] = (int)b;
+                }
+            }
+            pre += cnt[q];
+        }
+        base += round_tot;
     }
 }
 
@@ -404,10 +418,7 @@ int otmb_makeindices(otmb_ctx* c, const double* v3D, int64_t* N) {
     c->nwords = word1 - word0;
     CU_TRY(c, c->mask.ensure((size_t)(c->nwords + 1) * 8));
     CU_TRY(c, c->wpre.ensure((size_t)(c->nwords + 1) * 4));
-    // one pass: mask, per-chunk prefix, and (unsharded: the rank offset is 0) Lwet3D + the wet list
-    const int blocks = (int)((c->nwords + MI_WORDS - 1) / MI_WORDS);
-    CU_TRY(c, c->scan_tmp.ensure((size_t)(blocks + 1) * 8));
-    CU_TRY(c, cudaMemsetAsync(c->scan_tmp.p, 0, (size_t)(blocks + 1) * 8, c->stream));
+    // one cooperative launch: mask, per-chunk prefix, and (unsharded: the rank offset is 0) Lwet3D + the wet list
     OT_TRY(otmb_reset_flags(c));
     c->h_up = 0;
     c->w0 = 0;
@@ -415,13 +426,25 @@ int otmb_makeindices(otmb_ctx* c, const double* v3D, int64_t* N) {
         // the wet list cannot be longer than the window; N is only known afterwards
         CU_TRY(c, c->lwet.ensure((c->win_cells() + 1) * 4));
         CU_TRY(c, c->rank3d.ensure((c->win_cells() + 1) * 4));
-        k_makeindices<true><<<blocks, 32 * MI_WARPS, 0, c->stream>>>(c->win<double>(c->v3D), c->L_win0, c->L_win1, word0, word1, c->mask_win(),
-                                                                      c->wpre_win(), c->win<int>(c->rank3d), c->lwet.as<int>(), 0,
-                                                                      c->scan_tmp.as<u64>(), &c->flags.as<DevFlags>()->nnz[0]);
-    } else {
-        k_makeindices<false><<<blocks, 32 * MI_WARPS, 0, c->stream>>>(c->win<double>(c->v3D), c->L_win0, c->L_win1, word0, word1, c->mask_win(),
-                                                                       c->wpre_win(), nullptr, nullptr, 0, c->scan_tmp.as<u64>(),
-                                                                       &c->flags.as<DevFlags>()->nnz[0]);
+    }
+    {
+        void* kern = c->sharded ? (void*)k_makeindices<false> : (void*)k_makeindices<true>;
+        int per_sm = 0;
+        CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * MI_WARPS, 0));
+        const i64 rounds = (c->nwords + MI_WORDS - 1) / MI_WORDS;
+        const int blocks = (int)std::max<i64>(1, std::min<i64>(rounds, (i64)std::max(per_sm, 1) * c->sm_count));
+        CU_TRY(c, c->scan_tmp.ensure((size_t)(blocks + 1) * 4));
+        const double* v = c->win<double>(c->v3D);
+        i64 L0 = c->L_win0, L1 = c->L_win1, w0 = word0, w1 = word1;
+        u64* m = c->mask_win();
+        uint32_t* wp = c->wpre_win();
+        int* r3 = c->sharded ? nullptr : c->win<int>(c->rank3d);
+        int* lw = c->sharded ? nullptr : c->lwet.as<int>();
+        int off = 0;
+        unsigned* bt = c->scan_tmp.as<unsigned>();
+        u64* tot = &c->flags.as<DevFlags>()->nnz[0];
+        void* args[] = {&v, &L0, &L1, &w0, &w1, &m, &wp, &r3, &lw, &off, &bt, &tot};
+        CU_TRY(c, cudaLaunchCooperativeKernel(kern, dim3((unsigned)blocks), dim3(32 * MI_WARPS), args, 0, c->stream));
     }
     LAUNCHED(c);
     CU_TRY(c, cudaGetLastError());
