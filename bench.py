@@ -252,6 +252,7 @@ def sharded_record(args, rank, local_rank, world, dist):
 
     for _ in range(max(args.warmup, 3)):
         month()
+    ctx.check(lib.otmb_set_build_timing(ctx.h, 0))      # a build = two launches (kernel + completion record), no event pair
     launches0 = ctx.launches()
     asm_ms = timed(asm, args.steps)
     launches = ctx.launches() - launches0
@@ -268,6 +269,7 @@ def sharded_record(args, rank, local_rank, world, dist):
         for _ in range(3):
             fluxes_nccl()
         nccl_ms = timed(fluxes_nccl, args.steps)
+    ctx.check(lib.otmb_set_build_timing(ctx.h, 1))
     kernel_ms = []
     for _ in range(args.steps):
         asm()
@@ -429,6 +431,7 @@ def main():
     time.sleep(0.25)
     barrier()
     launches0 = ctx.launches()
+    ctx.check(lib.otmb_set_build_timing(ctx.h, 0))      # no per-build event pair in the loop `value` is quoted on
     t0 = time.perf_counter()
     ctx.check(lib.otmb_timer_start(ctx.h))
     for _ in range(args.steps):
@@ -437,6 +440,7 @@ def main():
     ctx.check(lib.otmb_timer_stop(ctx.h, C.byref(ms)))
     barrier()
     t1 = time.perf_counter()
+    ctx.check(lib.otmb_set_build_timing(ctx.h, 1))
     launches = ctx.launches() - launches0
     total_ms = float(ms.value)
     nnz_list = [int(x) for x in nnz]

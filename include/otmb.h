@@ -328,6 +328,9 @@ int otmb_timer_stop(otmb_ctx* ctx, float* milliseconds);
 int otmb_l2_flush(otmb_ctx* ctx);
 int otmb_launch_count(otmb_ctx* ctx, int64_t* launches);   /* kernels launched by this ctx so far */
 int otmb_last_build_ms(otmb_ctx* ctx, float* milliseconds); /* device time of the last transportmatrix_build */
+/* whether otmb_transportmatrix_build brackets its kernels with a CUDA event pair for otmb_last_build_ms (default on;
+ * off saves two driver calls per build — a build is then exactly two launches, the kernel and its completion record) */
+int otmb_set_build_timing(otmb_ctx* ctx, int32_t on);
 int otmb_synchronize(otmb_ctx* ctx);
 
 #ifdef __cplusplus

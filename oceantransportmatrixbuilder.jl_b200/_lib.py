@@ -23,7 +23,7 @@ EXPORTS = [
     "otmb_set_rho3d", "otmb_transportmatrix_build", "otmb_transportmatrix_fetch", "otmb_transportmatrix_fetch_all", "otmb_host_widen", "otmb_set_operator",
     "otmb_sparse_build", "otmb_sparse_fetch", "otmb_spadd_build", "otmb_spadd_fetch", "otmb_triad_derivative",
     "otmb_dyad_derivative", "otmb_bolus_gm_velocity", "otmb_timer_start", "otmb_timer_stop", "otmb_l2_flush",
-    "otmb_launch_count", "otmb_last_build_ms", "otmb_synchronize", "otmb_set_slab", "otmb_slab_counts",
+    "otmb_launch_count", "otmb_last_build_ms", "otmb_set_build_timing", "otmb_synchronize", "otmb_set_slab", "otmb_slab_counts",
     "otmb_set_rank_offset", "otmb_facefluxes_slab", "otmb_velocity2fluxes", "otmb_fluxes2velocity", "otmb_bgrid_to_cgrid", "otmb_lump_and_spray_build", "otmb_lump_and_spray_fetch", "otmb_spmv",
     "otmb_plan_slabs", "otmb_set_slab_rows", "otmb_comm_unique_id", "otmb_comm_init", "otmb_comm_free", "otmb_comm_allgather_i64", "otmb_comm_chain_transport",
     "otmb_sharded_makeindices", "otmb_set_masstransport", "otmb_sharded_facefluxes", "otmb_sharded_facefluxes_enqueue",
@@ -86,6 +86,7 @@ def load():
         "otmb_l2_flush": ([vp], C.c_int),
         "otmb_launch_count": ([vp, pi64], C.c_int),
         "otmb_last_build_ms": ([vp, C.POINTER(C.c_float)], C.c_int),
+        "otmb_set_build_timing": ([vp, i32], C.c_int),
         "otmb_synchronize": ([vp], C.c_int),
         "otmb_velocity2fluxes": ([vp, vp, vp, vp, dbl, vp, vp], C.c_int),
         "otmb_fluxes2velocity": ([vp, vp, vp, vp, dbl, vp, vp], C.c_int),

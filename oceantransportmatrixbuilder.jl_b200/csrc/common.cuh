@@ -149,6 +149,7 @@ struct otmb_ctx {
     i64 launches = 0;
     float last_build_ms = 0.f;
     bool build_ms_valid = false;  // ev_b0 / ev_b1 bracket a finished build whose duration has not been read yet
+    bool time_builds = true;      // record that event pair around every build (otmb_set_build_timing)
 };
 
 inline int otmb_fail(otmb_ctx* c, int code, const std::string& msg) {

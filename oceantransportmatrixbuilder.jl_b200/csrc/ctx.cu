@@ -586,6 +586,12 @@ int otmb_launch_count(otmb_ctx* c, int64_t* launches) {
     *launches = c->launches;
     return OTMB_OK;
 }
+int otmb_set_build_timing(otmb_ctx* c, int32_t on) {
+    if (!c) return OTMB_ERR_BADARG;
+    c->time_builds = on != 0;
+    if (!c->time_builds) c->build_ms_valid = false;
+    return OTMB_OK;
+}
 int otmb_last_build_ms(otmb_ctx* c, float* ms) {
     if (!c || !ms) return OTMB_ERR_BADARG;
     if (c->build_ms_valid) {

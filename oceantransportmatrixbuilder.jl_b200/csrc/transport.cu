@@ -104,7 +104,8 @@ int otmb_transportmatrix_build(otmb_ctx* c, const otmb_tm_params* prm, int64_t n
     const bool v4 = c->ncols != 0 && ops != 0 && prm->path == OTMB_PATH_FUSED;
     if (!(v4 && c->flags_clean)) OT_TRY(otmb_reset_flags(c));   // k_fused_v4 leaves the flag block zeroed
     c->build_ms_valid = false;
-    CU_TRY(c, cudaEventRecord(c->ev_b0, c->stream));
+    const bool timed = c->time_builds;
+    if (timed) CU_TRY(c, cudaEventRecord(c->ev_b0, c->stream));
     int st = OTMB_OK;
     if (c->ncols == 0) {
         // empty ocean: five empty matrices
@@ -130,7 +131,7 @@ int otmb_transportmatrix_build(otmb_ctx* c, const otmb_tm_params* prm, int64_t n
         const int build = ops | (all4 ? 1 : 0);
         st = v4 ? otmb_fused_v4_build(c, prm, build) : otmb_fused_build(c, prm, build, true);
         if (st != OTMB_OK) return st;
-        CU_TRY(c, cudaEventRecord(c->ev_b1, c->stream));
+        if (timed) CU_TRY(c, cudaEventRecord(c->ev_b1, c->stream));
         if (v4) {
             OT_TRY(otmb_v4_publish(c));
             OT_TRY(otmb_wait_v4(c, c->v4_serial, true));
@@ -146,7 +147,7 @@ int otmb_transportmatrix_build(otmb_ctx* c, const otmb_tm_params* prm, int64_t n
         if ((build & 1) && c->h_flags->zero_dropped) {
             // sparse + does not store results equal to zero (:147): rare, handled by a compaction pass
             OT_TRY(otmb_drop_zeros(c, 0, prm->index_base));
-            CU_TRY(c, cudaEventRecord(c->ev_b1, c->stream));
+            if (timed) CU_TRY(c, cudaEventRecord(c->ev_b1, c->stream));
         }
         if (!all4) {
             for (int m = 1; m <= 4; ++m) c->have_mat[m] = true;
@@ -154,9 +155,9 @@ int otmb_transportmatrix_build(otmb_ctx* c, const otmb_tm_params* prm, int64_t n
         }
     }
     const bool fast = v4 && all4 && !c->h_flags->zero_dropped;   // one kernel, completion already observed
-    if (!(c->ncols != 0 && ops != 0 && prm->path != OTMB_PATH_COO && all4)) CU_TRY(c, cudaEventRecord(c->ev_b1, c->stream));
+    if (timed && !(c->ncols != 0 && ops != 0 && prm->path != OTMB_PATH_COO && all4)) CU_TRY(c, cudaEventRecord(c->ev_b1, c->stream));
     if (!fast) CU_TRY(c, cudaStreamSynchronize(c->stream));
-    c->build_ms_valid = true;   // elapsed time is read on demand (otmb_last_build_ms): no event wait per build
+    c->build_ms_valid = timed;   // elapsed time is read on demand (otmb_last_build_ms): no event wait per build
     if (nnz_out)
         for (int m = 0; m < 5; ++m) nnz_out[m] = c->nnz[m];
     return OTMB_OK;
