@@ -86,6 +86,7 @@ struct V4Params {
     // a slab context holds a WINDOW of the 3-D arrays (common.cuh): idle threads of the last tile read the cell Lsafe
     // (the window's first owned cell, i = 0) instead of cell 0, and the two-levels-ahead prefetch stops at Lmax
     int Lsafe, ksafe, psafe, Lmax;
+    int lwet_ahead;      // columns ahead whose wet-list entries a tile prefetches into L2 (0 = off)
     i64* colptr[5];
     i64* rowval[5];
     double* nzval[5];
@@ -148,6 +149,9 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int tile = blockIdx.x;
+    // the completion record (k_publish, launched with programmatic stream serialisation) may be scheduled as soon as
+    // every tile has started; it waits for this grid to complete before it reads anything
+    asm volatile("griddepcontrol.launch_dependents;");
     // timeline instrumentation (debug instantiation): SM clock stamps of one tile's phases
     long long* const tl = TLINE ? P.timeline + (size_t)tile * 64 : nullptr;
     // (a clock read right behind BAR.SYNC.DEFER_BLOCKING issues before the barrier resolves: stamps behind a barrier
@@ -299,6 +303,9 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
     if (valid) {
         int Lc[7], r[7];
         L = __ldg(P.lwet + w);
+        // the wet list of the tile that will take this slot a few waves from now: one L2 prefetch per thread, so that
+        // the tile's very first load (everything else depends on it) is an L2 hit instead of a DRAM round trip
+        if (P.lwet_ahead > 0 && w + P.lwet_ahead < P.ncols) prefetch_l2(P.lwet + w + P.lwet_ahead);
         k = (int)fdiv((unsigned)L, P.divP);
         p2 = L - k * PP;
         const int j = (int)fdiv((unsigned)p2, P.divNx);
@@ -803,6 +810,9 @@ __global__ void __launch_bounds__(32) k_publish(DevFlags* __restrict__ flags, ot
                                                 u64* __restrict__ totals_out) {
     constexpr int NI = (int)(sizeof(DevFlags) / sizeof(int));
     static_assert(NI <= 32, "one warp copies the flag block");
+    // launched with programmatic stream serialisation: it may be scheduled while the assembly kernel still runs (its
+    // launch latency is hidden) and waits HERE until that kernel has completed and its writes are visible
+    cudaGridDependencySynchronize();
     int* src = reinterpret_cast<int*>(flags);
     volatile int* dst = reinterpret_cast<volatile int*>(&rec->snap);
     if (totals_out && threadIdx.x < 5) totals_out[threadIdx.x] = flags->nnz[threadIdx.x];   // (read before the block is zeroed:
@@ -892,8 +902,17 @@ int launch_v4(otmb_ctx* c, V4Params& P) {
 }  // namespace
 
 int otmb_v4_publish(otmb_ctx* c, u64* totals_out) {
-    k_publish<<<1, 32, 0, c->stream>>>(c->flags.as<DevFlags>(), c->d_done + (c->v4_serial % otmb_ctx::DONE_RING), c->v4_serial,
-                                       totals_out);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1);
+    cfg.blockDim = dim3(32);
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CU_TRY(c, cudaLaunchKernelEx(&cfg, k_publish, c->flags.as<DevFlags>(), c->d_done + (c->v4_serial % otmb_ctx::DONE_RING),
+                                 (u64)c->v4_serial, totals_out));
     LAUNCHED(c);
     CU_TRY(c, cudaGetLastError());
     return OTMB_OK;
@@ -949,6 +968,10 @@ int otmb_fused_v4_build(otmb_ctx* c, const otmb_tm_params* prm, int build, i64 c
     P.Lmax = (int)(c->L_win1 - 1);
     P.w0 = (int)(c->w0 + col0);
     P.ncols = (int)ncols;
+    P.lwet_ahead = 0;
+#ifdef OTMB_AB
+    if (const char* e = getenv("OTMB_V4_LWET_AHEAD")) P.lwet_ahead = atoi(e) * 352;   // in tiles
+#endif
     P.flags = c->flags.as<DevFlags>();
     const int cap_per_col[5] = {7, 7, 5, 3, 3};
     for (int m = 0; m < 5; ++m) {
