@@ -968,7 +968,9 @@ int otmb_fused_v4_build(otmb_ctx* c, const otmb_tm_params* prm, int build, i64 c
     P.Lmax = (int)(c->L_win1 - 1);
     P.w0 = (int)(c->w0 + col0);
     P.ncols = (int)ncols;
-    P.lwet_ahead = 0;
+    // one wave of tiles ahead (two blocks per SM): measured 0.3765 vs 0.3815 ms per launch on C2, 148 / 296 tiles alike,
+    // 600 and more no gain (profiles/README.md)
+    P.lwet_ahead = c->sm_count * 2 * 352;
 #ifdef OTMB_AB
     if (const char* e = getenv("OTMB_V4_LWET_AHEAD")) P.lwet_ahead = atoi(e) * 352;   // in tiles
 #endif
