@@ -313,7 +313,7 @@ def test_transportmatrix_c2_full_size():
 
 
 # ------------------------------------------------------------------------------------------ K10
-@pytest.mark.parametrize("cfg", ["C1t"])
+@pytest.mark.parametrize("cfg", ["C1t", "C2"])
 def test_redigm_matches_oracle(cfg):
     oc = synthetic.make_config(cfg, seed=4)
     o = oracle_pipeline(oc)
@@ -328,8 +328,11 @@ def test_redigm_matches_oracle(cfg):
     assert np.array_equal(bits(got), bits(want))
     u, v = A.bolus_GM_velocity(oc.rho3d, gm, None)
     uo, vo = O.bolus_gm(oc.rho3d, oc.lon, oc.lat, o["gm"]["Z3D"], o["v3D"], oc.topology)
-    np.testing.assert_allclose(u, uo, rtol=1e-10, atol=1e-300, equal_nan=True)
-    np.testing.assert_allclose(v, vo, rtol=1e-10, atol=1e-300, equal_nan=True)
+    # north-star tolerance 1e-12, plus 1e-12 of the field's scale: where the taper 1 + tanh(..) cancels to ~0 the value is
+    # negligible but its last bits are the tanh implementation's (CUDA's vs glibc's; Julia's own is a third one)
+    for got, want in ((u, uo), (v, vo)):
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12 * np.nanmax(np.abs(want)), equal_nan=True)
 
 
 def test_triad_on_bipolar_top_row_throws_like_reference():
