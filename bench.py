@@ -124,7 +124,8 @@ def config_of(args, shape, topology, N, nnz_list, world):
                         "five CSC matrices (T, Tadv, TkH, TkVML, TkVdeep)",
             "N_wet": int(N), "nnz": dict(zip(("T", "Tadv", "TκH", "TκVML", "TκVdeep"), [int(x) for x in nnz_list])),
             "parallelism": f"batch: one matrix per GPU x{world}, no collective",
-            "l2": f"no flush: per-step working set {(b_in + b_out) / 1e6:.0f} MB > 126 MB L2"}
+            "l2": f"no flush: per-step working set {(b_in + b_out) / 1e6:.0f} MB " +
+                  ("> 126 MB L2" if b_in + b_out > 126e6 else "< 126 MB L2: NOT a valid timing workload (parity-size case)")}
 
 
 def hbm_peak():

@@ -174,3 +174,35 @@ def test_c_driver_resolves_the_abi_and_fails_loudly_without_a_gpu(tmp_path):
 def test_c_driver_on_gpu(tmp_path):
     r = _abi_driver(tmp_path)
     assert r.returncode == 0 and "ABI-DRIVER: OK" in r.stdout, r.stdout + r.stderr
+
+
+def _bench(*args, timeout=600):
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), *args], capture_output=True, text=True, timeout=timeout)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, "bench.py must print exactly ONE JSON line on stdout"
+    import json
+    return json.loads(lines[0])
+
+
+def test_bench_reference_arm_line():
+    """`bench.py --impl reference`: the oracle port timed on host cores (no Julia in the image), one JSON line with the
+    contract's keys; run here on the test-suite-sized grid."""
+    d = _bench("--impl", "reference", "--workload", "C1", "--steps", "1", "--warmup", "0")
+    assert d["impl"] == "reference" and d["unit"] == "nnz(T)/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("C1 90x45x20") and d["config"]["N_wet"] > 0 and d["gpu_launches"] == 0
+
+
+@pytest.mark.gpu
+def test_bench_cuda_arm_line_and_same_config_as_reference_arm():
+    d = _bench("--workload", "C1", "--steps", "3", "--warmup", "3", "--mode", "batch")
+    r = _bench("--impl", "reference", "--workload", "C1", "--steps", "1", "--warmup", "0")
+    assert d["config"] == r["config"], "both arms must describe the same configuration"
+    assert d["metric"] == r["metric"] and d["unit"] == r["unit"] and d["dtype"] == "f64" and d["vs_baseline"] is None
+    rf = d["roofline"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12
+    assert rf["frac_step"] <= rf["frac"] * 1.05 and rf["traffic"] is None
+    assert d["gpu_launches"] >= 3 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
