@@ -67,6 +67,8 @@ class ClockSampler:
         self.rows, self.proc, self.device = [], None, device
 
     def start(self):
+        if int(os.environ.get("RANK", "0")) != 0:
+            return      # one sampler per box: eight nvidia-smi loops querying the driver would perturb eight ranks' launches
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
