@@ -134,12 +134,10 @@ struct Smem {
     u64 lexcl[TILE];               // in-warp exclusive offsets of the column, five 12-bit fields
     u64 warp[TILE / 32];           // entries of each warp, five 12-bit fields
     u64 excl[5];
-    int arrived;                   // column warps whose counts are in `warp` (early look-back: polled by the scan warp)
 };
 
 // ---------------------------------------------------------------------------------------
-template <bool RHO3D, bool UP, int TILE, int MINB, int KHB = 2, bool VAH = true, bool VC0 = true, bool TLINE = false, bool XSM = true,
-          bool ELB = true>
+template <bool RHO3D, bool UP, int TILE, int MINB, int KHB = 2, bool VAH = true, bool VC0 = true, bool TLINE = false, bool XSM = true>
 // __grid_constant__: P is indexed dynamically and its address is taken by the generic branch
 __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_constant__ V4Params P) {
     constexpr int NW = TILE / 32;   // column warps; warp NW is the scan warp
@@ -175,99 +173,9 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
         tl[6] = smid;
     }
 
-    if (ELB) {   // early look-back: the scan warp polls `arrived` instead of waiting at barrier 1
-        if (tid == 0) S.arrived = 0;
-        __syncthreads();
-    }
     // ================= the scan warp: decoupled look-back for all five counters =================
     // It owns no columns, so the column warps never wait for a warp that still has values to compute:
     // by the time they reach the second barrier the offsets have long been resolved.
-    if (wid == NW && ELB) {
-        // EARLY look-back.  The prefix of the lower tiles does not depend on this tile's own counts, so the scan warp starts
-        // walking back at once, while the column warps are still in phase 0, instead of first waiting for their counts:
-        // the offsets are then ready about when the tile's own aggregate is, not 3.8 us later, and the column warps do
-        // not wait at their release barrier (it was 8 % of a warp's life).  The tile's aggregate is published the moment
-        // the last column warp has arrived (`arrived`, polled between two look-back polls — never later than before).
-        const unsigned tagA = (1u << 20) | P.epoch, tagP = (2u << 20) | P.epoch;   // the descriptor's top 22 bits
-        const u64 first = (tile == 0 && P.start != nullptr && lane < 5) ? P.start[lane] : 0ull;
-        auto ready = [&](const u64 v) {
-            const unsigned hi = (unsigned)(v >> ST_SHIFT);
-            return hi == tagA || hi == tagP;
-        };
-        u64 excl[5] = {0, 0, 0, 0, 0}, wv[5];
-        unsigned pending = tile > 0 ? 31u : 0u, agg_m = 0, spins = 0;
-        int look = tile - 1;
-        bool have_agg = false;
-#pragma unroll
-        for (int m = 0; m < 5; ++m) wv[m] = (look - lane) >= 0 ? 0ull : ((u64)tagP << ST_SHIFT);   // before the first tile: prefix 0
-        while (pending || !have_agg) {
-            if (!have_agg && *reinterpret_cast<volatile int*>(&S.arrived) == NW) {   // (uniform: one word, one instruction)
-                __threadfence_block();
-                const u64 pk = lane < NW ? *reinterpret_cast<volatile u64*>(&S.warp[lane]) : 0ull;
-#pragma unroll
-                for (int m = 0; m < 5; ++m) {
-                    const unsigned tot = __reduce_add_sync(0xffffffffu, (unsigned)((pk >> (12 * m)) & 0xfffull));
-                    if (lane == m) agg_m = tot;
-                }
-                if (lane < 5) st_vol(P.tile_state + (size_t)tile * 8 + lane, ((u64)(tile == 0 ? tagP : tagA) << ST_SHIFT) | (first + (u64)agg_m));
-                have_agg = true;
-            }
-            if (pending) {
-                bool again = false;
-#pragma unroll
-                for (int m = 0; m < 5; ++m)
-                    if ((pending >> m & 1) && !ready(wv[m])) {
-                        wv[m] = ld_vol(P.tile_state + (size_t)(look - lane) * 8 + m);
-                        again |= !ready(wv[m]);
-                    }
-                if (!__any_sync(0xffffffffu, again)) {   // the whole window is published: take it
-#pragma unroll
-                    for (int m = 0; m < 5; ++m) {
-                        if (!(pending >> m & 1)) continue;
-                        const u64 val = wv[m] & ST_MASK;
-                        const unsigned pm = __ballot_sync(0xffffffffu, (unsigned)(wv[m] >> ST_SHIFT) == tagP);
-                        if (pm) {
-                            const int f1 = __ffs(pm) - 1;
-                            excl[m] += (u64)__reduce_add_sync(0xffffffffu, lane < f1 ? (unsigned)val : 0u) + __shfl_sync(0xffffffffu, val, f1);
-                            pending &= ~(1u << m);
-                        } else {
-                            excl[m] += (u64)__reduce_add_sync(0xffffffffu, (unsigned)val);
-                        }
-                    }
-                    look -= 32;
-#pragma unroll
-                    for (int m = 0; m < 5; ++m) wv[m] = (look - lane) >= 0 ? 0ull : ((u64)tagP << ST_SHIFT);
-                } else if (!have_agg) {
-                    __nanosleep(200);   // the lower tiles are in phase 0 like this one: do not hammer their descriptor lines
-                }
-            } else if (!have_agg) {
-                __nanosleep(100);
-            }
-            if (++spins > (1u << 24)) {   // see the bound in the late variant below
-                if (lane == 0) atomicOr(&P.flags->lookback_timeout, 1);
-                if (lane < NW) S.warp[lane] = 0ull;
-                break;
-            }
-        }
-        const u64 mine = first + (lane == 0 ? excl[0] : lane == 1 ? excl[1] : lane == 2 ? excl[2] : lane == 3 ? excl[3] : excl[4]);
-        if (lane < 5) {
-            const u64 agg = agg_m;
-            if (tile > 0) st_vol(P.tile_state + (size_t)tile * 8 + lane, ((u64)tagP << ST_SHIFT) | (mine + agg));
-            S.excl[lane] = mine;
-            if (tile == P.ntiles - 1) {
-                P.flags->nnz[lane] = mine + agg;
-                if (P.run_out) P.run_out[lane] = mine + agg;
-                if (P.build >> lane & 1) P.colptr[lane][P.ncols] = (i64)(mine + agg) + P.base;
-            }
-        }
-        __threadfence_block();
-#pragma unroll
-        for (int gq = 0; gq < NBG; ++gq) {
-            const int members = (gq + 1) * BG <= NW ? BG : NW - gq * BG;
-            asm volatile("bar.arrive %0, %1;" ::"r"(2 + gq), "r"(32 * members + 32) : "memory");
-        }
-        return;
-    }
     if (wid == NW) {
         // producer / consumer named barriers: the column warps only ARRIVE at barrier 1 (no wait) once their
         // counts are in S.warp; the scan warp only arrives at barrier 2 once the offsets are in S.excl
@@ -541,11 +449,7 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
     }
     if (lane == 31) S.warp[wid] = incl;
     __threadfence_block();
-    if (ELB) {
-        if (lane == 0) atomicAdd(&S.arrived, 1);                     // counts published; nobody waits here
-    } else {
-        asm volatile("bar.arrive 1, %0;" ::"r"(TILE + 32) : "memory");   // counts published; nobody waits here
-    }
+    asm volatile("bar.arrive 1, %0;" ::"r"(TILE + 32) : "memory");   // counts published; nobody waits here
     stamp(8 + 4 * wid);
     // kept in shared memory, not in registers: they are needed again only at the five flushes, and as
     // registers they were spilled to local memory (ncu: 25 % of the long-scoreboard stalls were their reloads)
@@ -931,8 +835,7 @@ FastDiv make_fastdiv(unsigned d) {
     return f;
 }
 
-template <bool RHO3D, bool UP, int TILE, int MINB, int KHB = 2, bool VAH = true, bool VC0 = true, bool TLINE = false, bool XSM = true,
-          bool ELB = true>
+template <bool RHO3D, bool UP, int TILE, int MINB, int KHB = 2, bool VAH = true, bool VC0 = true, bool TLINE = false, bool XSM = true>
 int launch_v4(otmb_ctx* c, V4Params& P) {
     const int ntiles = (int)(((i64)P.ncols + TILE - 1) / TILE);
     P.ntiles = ntiles;
@@ -956,7 +859,7 @@ int launch_v4(otmb_ctx* c, V4Params& P) {
     }
     P.timeline = tline.as<long long>();
     const size_t smem = sizeof(Smem<TILE>);
-    auto kern = k_fused_v4<RHO3D, UP, TILE, MINB, KHB, VAH, VC0, TLINE, XSM, ELB>;
+    auto kern = k_fused_v4<RHO3D, UP, TILE, MINB, KHB, VAH, VC0, TLINE, XSM>;
     // function attributes once per instantiation and device
     static std::atomic<unsigned long long> configured{0};
     if (!(configured.load(std::memory_order_acquire) >> (c->device & 63) & 1ull)) {
@@ -1091,13 +994,12 @@ int otmb_fused_v4_build(otmb_ctx* c, const otmb_tm_params* prm, int build, i64 c
     if (c->have_rho3d) return up ? launch_v4<true, true, 352, 2>(c, P) : launch_v4<true, false, 352, 2>(c, P);
     if (!up) return launch_v4<false, false, 352, 2>(c, P);
 #ifdef OTMB_AB   // measurement builds only (nvcc -DOTMB_AB): launch geometries / schedules for A/B runs, per-tile phase stamps
-    if (getenv("OTMB_V4_TIMELINE")) return launch_v4<false, true, 352, 2, 2, true, true, true, true, false>(c, P);
+    if (getenv("OTMB_V4_TIMELINE")) return launch_v4<false, true, 352, 2, 2, true, true, true>(c, P);
     switch (getenv("OTMB_V4_VARIANT") ? atoi(getenv("OTMB_V4_VARIANT")) : 0) {
         case 1: return launch_v4<false, true, 352, 2, 2, true, true, false, false>(c, P);   // Tadv re-loads the neighbours' fluxes
         case 2: return launch_v4<false, true, 416, 2>(c, P);   // 72 registers
         case 3: return launch_v4<false, true, 352, 2, 1>(c, P);   // TκH loads direction by direction
         case 4: return launch_v4<false, true, 352, 2, 2, false, false>(c, P);   // vertical inputs and own volume loaded where they are used
-        case 5: return launch_v4<false, true, 352, 2, 2, true, true, false, true, false>(c, P);   // late look-back (round 1's)
         default: break;
     }
 #endif
