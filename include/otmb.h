@@ -74,9 +74,14 @@ int otmb_create(otmb_ctx** ctx, int device);
 int otmb_destroy(otmb_ctx* ctx);
 const char* otmb_last_error(const otmb_ctx* ctx);
 
-/* pinned host memory for full-rate PCIe transfers (optional) */
+/* Page-locked host memory: what makes the copies run at the rate of the link (a copy into pageable arrays runs at a
+ * fraction of it).  Pinning costs ~100 ms per GB, so freed blocks go to a process-wide pool (up to 8 GB) and are handed
+ * out again to requests they fit: a shim that wraps results in garbage-collected arrays (Julia: unsafe_wrap + a
+ * finalizer calling otmb_host_free) pays for the pinning once, not every month.  otmb_host_trim releases the pool.
+ * Thread-safe; otmb_host_free rejects pointers that did not come from otmb_host_alloc. */
 int otmb_host_alloc(void** ptr, int64_t bytes);
 int otmb_host_free(void* ptr);
+int otmb_host_trim(void);
 
 /* grid shape + topology tag.  Replaces the AbstractGridTopology structs,
  * src/gridtopology.jl:1-16; the tag comes from getgridtopology (:33-53), which stays on the host. */

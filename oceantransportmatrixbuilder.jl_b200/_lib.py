@@ -18,7 +18,7 @@ MAT = {"T": 0, "Tadv": 1, "TκH": 2, "TκVML": 3, "TκVdeep": 4}
 
 EXPORTS = [
     "otmb_version", "otmb_device_count", "otmb_status_string", "otmb_create", "otmb_destroy", "otmb_last_error",
-    "otmb_host_alloc", "otmb_host_free", "otmb_set_grid", "otmb_makeindices", "otmb_get_indices",
+    "otmb_host_alloc", "otmb_host_free", "otmb_host_trim", "otmb_set_grid", "otmb_makeindices", "otmb_get_indices",
     "otmb_gridmetrics", "otmb_set_gridmetrics", "otmb_facefluxes", "otmb_set_facefluxes", "otmb_set_mlotst",
     "otmb_set_rho3d", "otmb_transportmatrix_build", "otmb_transportmatrix_fetch", "otmb_transportmatrix_fetch_all", "otmb_host_widen", "otmb_set_operator",
     "otmb_sparse_build", "otmb_sparse_fetch", "otmb_spadd_build", "otmb_spadd_fetch", "otmb_triad_derivative",
@@ -60,6 +60,7 @@ def load():
         "otmb_last_error": ([vp], C.c_char_p),
         "otmb_host_alloc": ([C.POINTER(vp), i64], C.c_int),
         "otmb_host_free": ([vp], C.c_int),
+        "otmb_host_trim": ([], C.c_int),
         "otmb_set_grid": ([vp, i64, i64, i64, C.c_int], C.c_int),
         "otmb_makeindices": ([vp, vp, pi64], C.c_int),
         "otmb_get_indices": ([vp, vp, vp, vp], C.c_int),

@@ -9,6 +9,9 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
 
 #include "common.cuh"
 
@@ -324,19 +327,86 @@ int otmb_destroy(otmb_ctx* c) {
 
 const char* otmb_last_error(const otmb_ctx* c) { return c ? c->err.c_str() : "null context"; }
 
+// Page-locked host memory with a process-wide pool.  Pinning a gigabyte costs on the order of 100 ms, and a host shim
+// that wraps results in garbage-collected arrays (the Julia shim: unsafe_wrap + finalizer) allocates the same sizes month
+// after month: freed blocks are kept (up to POOL_MAX bytes) and handed out again to requests they fit within 1.5x.
+namespace {
+struct HostPoolState {
+    std::mutex mu;
+    std::vector<std::pair<size_t, void*>> free_blocks;     // (capacity, pointer)
+    std::unordered_map<void*, size_t> live;                // capacity of every block handed out
+    size_t pooled = 0;
+    static constexpr size_t POOL_MAX = (size_t)8 << 30;
+};
+HostPoolState& host_pool() {
+    static HostPoolState* p = new HostPoolState();   // never destroyed: finalizers may run after static destructors
+    return *p;
+}
+}  // namespace
+
 int otmb_host_alloc(void** ptr, int64_t bytes) {
     if (!ptr || bytes < 0) return OTMB_ERR_BADARG;
-    if (cudaMallocHost(ptr, (size_t)(bytes > 0 ? bytes : 8)) != cudaSuccess) {
+    const size_t need = (size_t)(bytes > 0 ? bytes : 8);
+    HostPoolState& hp = host_pool();
+    {
+        std::lock_guard<std::mutex> lk(hp.mu);
+        int best = -1;
+        for (int q = 0; q < (int)hp.free_blocks.size(); ++q) {
+            const size_t cap = hp.free_blocks[q].first;
+            if (cap >= need && cap <= need + need / 2 + ((size_t)1 << 20) && (best < 0 || cap < hp.free_blocks[best].first)) best = q;
+        }
+        if (best >= 0) {
+            *ptr = hp.free_blocks[best].second;
+            hp.live[*ptr] = hp.free_blocks[best].first;
+            hp.pooled -= hp.free_blocks[best].first;
+            hp.free_blocks.erase(hp.free_blocks.begin() + best);
+            return OTMB_OK;
+        }
+    }
+    if (cudaMallocHost(ptr, need) != cudaSuccess) {
+        cudaGetLastError();
+        otmb_host_trim();   // give the pooled blocks back and try once more
+        if (cudaMallocHost(ptr, need) != cudaSuccess) {
+            cudaGetLastError();
+            *ptr = nullptr;
+            return OTMB_ERR_CUDA;
+        }
+    }
+    std::lock_guard<std::mutex> lk(hp.mu);
+    hp.live[*ptr] = need;
+    return OTMB_OK;
+}
+int otmb_host_free(void* ptr) {
+    if (!ptr) return OTMB_OK;
+    HostPoolState& hp = host_pool();
+    {
+        std::lock_guard<std::mutex> lk(hp.mu);
+        auto it = hp.live.find(ptr);
+        if (it == hp.live.end()) return OTMB_ERR_BADARG;   // not a block of otmb_host_alloc (or freed twice)
+        const size_t cap = it->second;
+        hp.live.erase(it);
+        if (hp.pooled + cap <= HostPoolState::POOL_MAX) {
+            hp.free_blocks.emplace_back(cap, ptr);
+            hp.pooled += cap;
+            return OTMB_OK;
+        }
+    }
+    if (cudaFreeHost(ptr) != cudaSuccess) {
         cudaGetLastError();
         return OTMB_ERR_CUDA;
     }
     return OTMB_OK;
 }
-int otmb_host_free(void* ptr) {
-    if (ptr && cudaFreeHost(ptr) != cudaSuccess) {
-        cudaGetLastError();
-        return OTMB_ERR_CUDA;
+int otmb_host_trim(void) {
+    HostPoolState& hp = host_pool();
+    std::vector<std::pair<size_t, void*>> blocks;
+    {
+        std::lock_guard<std::mutex> lk(hp.mu);
+        blocks.swap(hp.free_blocks);
+        hp.pooled = 0;
     }
+    for (auto& b : blocks)
+        if (cudaFreeHost(b.second) != cudaSuccess) cudaGetLastError();
     return OTMB_OK;
 }
 

@@ -598,3 +598,22 @@ def test_binary_dump_of_resident_matrices(tmp_path):
             assert np.array_equal(bits(a.data), bits(b.data)), name
         otmb_b200.dump_resident(path, ("T",))
         assert list(otmb_b200.load_dump(path)) == ["T"]
+
+
+def test_pinned_host_pool_reuses_blocks():
+    """otmb_host_alloc / otmb_host_free: freed blocks are handed out again to requests they fit (pinning a gigabyte costs
+    ~100 ms; the Julia shim frees result arrays from finalizers and allocates the same sizes every month)."""
+    import ctypes as C
+    lib = otmb_b200._lib.load()
+    lib.otmb_host_trim()
+    p, q = C.c_void_p(), C.c_void_p()
+    assert lib.otmb_host_alloc(C.byref(p), 64 << 20) == 0 and p.value
+    assert lib.otmb_host_free(p) == 0
+    assert lib.otmb_host_alloc(C.byref(q), 60 << 20) == 0 and q.value == p.value       # fits within 1.5x: the same block
+    r = C.c_void_p()
+    assert lib.otmb_host_alloc(C.byref(r), 1 << 20) == 0 and r.value != q.value         # too small a request for a 64 MB block
+    assert lib.otmb_host_free(q) == 0 and lib.otmb_host_free(r) == 0
+    assert lib.otmb_host_free(q) == otmb_b200._lib.ERR_BADARG                              # freed twice
+    buf = (C.c_char * 64)()
+    assert lib.otmb_host_free(C.cast(buf, C.c_void_p)) == otmb_b200._lib.ERR_BADARG       # not ours
+    assert lib.otmb_host_trim() == 0
