@@ -148,7 +148,10 @@ struct HostPool {
     }
 };
 
-constexpr size_t CHUNK_BYTES = (size_t)16 << 20;       // bytes per staged D2H copy / host step
+#ifndef OTMB_CHUNK_MB
+#define OTMB_CHUNK_MB 16
+#endif
+constexpr size_t CHUNK_BYTES = (size_t)OTMB_CHUNK_MB << 20;   // bytes per staged D2H copy / host step
 constexpr size_t STAGE_CAP = (size_t)3 << 30;          // bytes of pinned staging at most; beyond: direct copies
 
 struct FetchState {
@@ -473,9 +476,13 @@ extern "C" int otmb_transportmatrix_stream(otmb_ctx* c, const otmb_tm_params* pr
     const std::vector<long long>& cum = c->level_cum;
     int S = nslabs > 0 ? nslabs : 8;
     S = (int)std::min<i64>(std::min<i64>(S, c->nz), otmb_ctx::DONE_RING / 2);
+    // default plan: the first two slabs are small, so that the copy-out — the long pole — starts after 0.5 ms of upload
+    // instead of 1.2 ms (a slab is assembled once it and the slab behind it have been uploaded)
+    static const double ramp[8] = {0.04, 0.12, 0.25, 0.40, 0.55, 0.70, 0.85, 1.0};
+    const bool ramped = nslabs <= 0 && S == 8;
     std::vector<int> cut(1, 0);
     for (int s = 1; s < S; ++s) {
-        const long double target = (long double)N * s / S;
+        const long double target = ramped ? (long double)N * ramp[s - 1] : (long double)N * s / S;
         int best = cut.back() + 1;
         for (int k = best; k <= (int)c->nz - (S - s); ++k)
             if (fabsl((long double)cum[k] - target) < fabsl((long double)cum[best] - target)) best = k;

@@ -336,6 +336,28 @@ function lump_and_spray(wet3D, vol, T::SparseMatrixCSC{Float64, Int64}, mask = t
     return SparseMatrixCSC(Nc[], N, lcp, lrv, lnz), SparseMatrixCSC(N, Nc[], scp, srv, snz), vol_c
 end
 
+"""
+    coarsen(which = :T)
+
+`T_c = LUMP * T * SPRAY` (test/local_full.jl:161) on the device: LUMP / SPRAY of the last `lump_and_spray` call (default
+mask), T = the RESIDENT matrix `which` of the last `transportmatrix` call.  Bit-identical to the SparseArrays product.
+"""
+function coarsen(which::Symbol = :T)
+    c = ctx(); Nc = Ref{Int64}(0); nz = Ref{Int64}(0)
+    m = findfirst(==(which), (:T, :Tadv, :TκH, :TκVML, :TκVdeep)) - 1
+    check(c, ccall((:otmb_coarsen_build, LIBOTMB), Cint, (PV, Cint, Ref{Int64}, Ref{Int64}), c.h, m, Nc, nz))
+    cp = Vector{Int64}(undef, Nc[] + 1); rv = Vector{Int64}(undef, nz[]); nv = Vector{Float64}(undef, nz[])
+    check(c, ccall((:otmb_coarsen_fetch, LIBOTMB), Cint, (PV, PI, PI, PF), c.h, cp, rv, nv))
+    return SparseMatrixCSC{Float64, Int64}(Nc[], Nc[], cp, rv, nv)
+end
+
+"write the RESIDENT result matrices of the last transportmatrix call to `path` (layout: include/otmb.h, \"OTMBCSC1\")"
+function dump_resident(path::AbstractString; which = (:T, :Tadv, :TκH, :TκVML, :TκVdeep))
+    c = ctx()
+    mask = sum(1 << (findfirst(==(w), (:T, :Tadv, :TκH, :TκVML, :TκVdeep)) - 1) for w in which)
+    check(c, ccall((:otmb_transportmatrix_dump, LIBOTMB), Cint, (PV, Cint, Cstring), c.h, mask, path))
+end
+
 # ------------------------------------------------------------------------------------------------------------------
 # ONE matrix sharded over the GPUs of a box (include/otmb.h, "ONE matrix sharded across the GPUs"): one Julia process
 # per GPU (e.g. under mpiexec), the exchanges run inside the library over NCCL.  The host program only has to hand every

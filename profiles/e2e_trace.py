@@ -35,8 +35,8 @@ nnz = (C.c_int64 * 5)()
 for nslabs in [int(x) for x in (sys.argv[1:] or ["8"])]:
     os.environ.pop("OTMB_STREAM_TRACE", None)
     ts = []
-    for it in range(6):
-        if it == 5:
+    for it in range(8):
+        if it == 7 and os.environ.get("TRACE"):
             os.environ["OTMB_STREAM_TRACE"] = "1"
         t = time.perf_counter()
         ctx.check(lib.otmb_transportmatrix_stream(ctx.h, C.byref(prm), ptrs, A._ptr(ml), None, nslabs, (C.c_int64 * 5)(*caps), *out_ptrs, nnz))
