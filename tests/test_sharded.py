@@ -322,3 +322,24 @@ def test_c4_quarter_degree_sharded_matches_streamed_oracle():
             assert np.array_equal(cp - cp[0] + 1, w.colptr), f"{gname} colptr, columns {lo}:{hi}"
             assert np.array_equal(np.concatenate(rvs) + 1, w.rowval), f"{gname} rowval, columns {lo}:{hi}"
             assert np.array_equal(np.concatenate(nzs).view(np.int64), w.nzval.view(np.int64)), f"{gname} nzval, columns {lo}:{hi}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(12))
+def test_fuzz_row_slabs_bit_exact(seed):
+    """Random small grids cut into a random number of row slabs (cuts inside levels; slabs thinner than a level; windows
+    that reach the first / last level): the concatenated matrices equal the oracle's bit for bit."""
+    rng = np.random.default_rng(2000 + seed)
+    nx, ny, nz = int(rng.integers(2, 13)), int(rng.integers(2, 9)), int(rng.integers(1, 7))
+    topo = "tripolar" if rng.random() < 0.6 else "bipolar"
+    oc = synthetic.make_ocean(nx, ny, nz, topo, seed=100 + seed, land_frac=float(rng.uniform(0.0, 0.4)), dirty=bool(rng.random() < 0.3))
+    R = int(rng.integers(2, min(9, ny * nz) + 1))
+    upwind = bool(rng.random() < 0.6)
+    rho = 1035.0 if rng.random() < 0.5 else oc.rho3d
+    o = oracle_pipeline(oc, rho=rho, upwind=upwind)
+    gm = oracle_gridmetrics(oc)
+    fn = lambda ex: sharded.transportmatrix_sharded(exchange=ex, gridmetrics=gm, mlotst=oc.mlotst, ρ=rho, umo=oc.umo, vmo=oc.vmo,
+                                                    FillValue=oc.fill, upwind=upwind)
+    full, segs, info = sharded.run_threaded(R, fn)[0]
+    for gname, oname in NAMES.items():
+        assert_csc_equal(getattr(full, gname), o["tm"][oname], f"seed {seed} {(nx, ny, nz, topo)} R={R} {oname}", exact=True)
