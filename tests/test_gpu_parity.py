@@ -657,3 +657,32 @@ def test_fuzz_small_grids_bit_exact(seed):
     g = gpu_pipeline(oc, rho=rho, upwind=upwind)                                   # resident ϕ: build + fetch, own geometry
     for oname, gname in NAMES.items():
         assert_csc_equal(getattr(g["tm"], gname), o["tm"][oname], f"seed {seed} {(nx, ny, nz, topo)} build {oname}", exact=False, rtol=1e-12)
+
+
+def test_prebuilt_operator_is_validated():
+    """A wrong-shaped pre-built operator is a DimensionMismatch in the reference's sum (src/matrixbuilding.jl:147); here
+    otmb_set_operator checks the caller's CSC before anything reaches the device: colptr length / ends / monotonicity, row
+    range, ascending rows."""
+    import ctypes as C
+    oc = synthetic.make_config("C1t", seed=5)
+    g = gpu_pipeline(oc)
+    c = A._ctx_of(g["gm"].v3D)
+    N = g["ix"].N
+    good = g["tm"].TκH
+    cp, rv, nz = good.indptr.astype(np.int64), good.indices.astype(np.int64), good.data.astype(np.float64)
+
+    def set_op(cp, rv, nz, nnz=None):
+        return c.lib.otmb_set_operator(c.h, 2, len(rv) if nnz is None else nnz, A._ptr(cp), A._ptr(rv), A._ptr(nz), 0)
+
+    assert set_op(cp, rv, nz) == 0
+    bad = cp.copy(); bad[-1] -= 1
+    assert set_op(bad, rv, nz) == otmb_b200._lib.ERR_BADARG and b"DimensionMismatch" in c.lib.otmb_last_error(c.h)
+    bad = cp.copy(); bad[5], bad[6] = bad[6], bad[5] - 1                       # not monotone
+    assert set_op(bad, rv, nz) == otmb_b200._lib.ERR_BADARG
+    bad = rv.copy(); bad[3] = N                                                # row out of range
+    assert set_op(cp, bad, nz) == otmb_b200._lib.ERR_BADARG
+    bad = rv.copy(); a = cp[10]; bad[a], bad[a + 1] = bad[a + 1], bad[a]       # rows not ascending inside a column
+    assert set_op(cp, bad, nz) == otmb_b200._lib.ERR_BADARG
+    # the context is still usable and the good operator gives the reference's sum
+    tm = otmb_b200.transportmatrix(ϕ=g["phi"], mlotst=oc.mlotst, gridmetrics=g["gm"], indices=g["ix"], ρ=1035.0, TκH=good)
+    assert np.array_equal(tm.T.indptr, g["tm"].T.indptr) and np.array_equal(bits(tm.T.data), bits(g["tm"].T.data))
