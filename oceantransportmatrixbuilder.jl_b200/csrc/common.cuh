@@ -132,6 +132,8 @@ struct otmb_ctx {
     DevBuf sp_colptr, sp_rowval, sp_nzval;  // results of otmb_sparse_build / otmb_spadd_build
     i64 sp_n = 0, sp_nnz = 0;
     DevBuf add_tmp[6];
+    DevBuf held[5][3];   // caller-supplied operators set aside while a build checks them against a full rebuild
+    DevBuf held_diff;    // one int: the comparison's verdict
     DevBuf tp[5][3];     // transposes of the result matrices (CSC of Xᵀ, 0-based), built on demand by otmb_spmv
     i64 tp_serial[5] = {-1, -1, -1, -1, -1};
     i64 build_serial = 0; // bumped by every transportmatrix build / set_operator
@@ -215,6 +217,7 @@ int otmb_scan_u32_to_i64(otmb_ctx* ctx, const uint32_t* in, i64* out, i64 n, u64
 
 // internal entry points across translation units
 int otmb_need(otmb_ctx* ctx, bool cond, const char* what);
+int otmb_h2d(otmb_ctx* ctx, void* dst, const void* src, size_t bytes, cudaStream_t st);   // fetch.cu: pageable sources are staged by the host pool
 int otmb_upload3d(otmb_ctx* ctx, DevBuf& buf, const double* host);   // whole (nx,ny,nz) array, or only the slab window
 int otmb_fused_build(otmb_ctx* ctx, const otmb_tm_params* prm, int mask, bool two_pass);
 // columns [col0, col0 + ncols) of the context's owned columns (ncols < 0: all of them).  chain: 0 = a build of its

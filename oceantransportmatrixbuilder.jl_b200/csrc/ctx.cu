@@ -156,7 +156,7 @@ __global__ void k_l2_flush(uint4* __restrict__ buf, i64 n) {
 
 int upload(otmb_ctx* ctx, DevBuf& buf, const void* host, size_t bytes) {
     CU_TRY(ctx, buf.ensure(bytes));
-    CU_TRY(ctx, cudaMemcpyAsync(buf.p, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    OT_TRY(otmb_h2d(ctx, buf.p, host, bytes, ctx->stream));
     return OTMB_OK;
 }
 
@@ -165,7 +165,7 @@ int upload(otmb_ctx* ctx, DevBuf& buf, const void* host, size_t bytes) {
 // `host` is the caller's FULL (nx,ny,nz) array; the device buffer holds the context's window only (win<T>())
 int otmb_upload3d(otmb_ctx* c, DevBuf& buf, const double* host) {
     CU_TRY(c, buf.ensure(c->win_cells() * 8));
-    CU_TRY(c, cudaMemcpyAsync(buf.p, host + c->L_win0, c->win_cells() * 8, cudaMemcpyHostToDevice, c->stream));
+    OT_TRY(otmb_h2d(c, buf.p, host + c->L_win0, c->win_cells() * 8, c->stream));
     return OTMB_OK;
 }
 
@@ -307,6 +307,9 @@ int otmb_destroy(otmb_ctx* c) {
     c->spmv_x.release();
     c->spmv_y.release();
     for (int q = 0; q < 6; ++q) c->add_tmp[q].release();
+    for (int m = 0; m < 5; ++m)
+        for (int q = 0; q < 3; ++q) c->held[m][q].release();
+    c->held_diff.release();
     for (int q = 0; q < 12; ++q) c->coo[q].release();
     for (int q = 0; q < 5; ++q) {
         c->colptr[q].release();

@@ -162,6 +162,8 @@ struct FetchState {
     HostPool* pool = nullptr;
     bool few_threads = false;
     cudaStream_t s_up = nullptr, s_dn = nullptr;   // transfer streams of the slab-pipelined call (stream.cu)
+    char* up_stage = nullptr;                      // pinned: UP_BUFS pieces of a pageable upload in flight (otmb_h2d)
+    cudaEvent_t up_ev[3] = {};
     cudaEvent_t ev_slab[2 * otmb_ctx::DONE_RING + 1] = {};   // [s] slab uploaded, [RING + s] slab assembled, [2 RING] call start
 };
 
@@ -178,6 +180,9 @@ int fetch_state(otmb_ctx* c, FetchState** out) {
             if (f->s_up) cudaStreamDestroy(f->s_up);
             if (f->s_dn) cudaStreamDestroy(f->s_dn);
             if (f->stage) cudaFreeHost(f->stage);
+            if (f->up_stage) cudaFreeHost(f->up_stage);
+            for (cudaEvent_t e : f->up_ev)
+                if (e) cudaEventDestroy(e);
             f->narrow.release();
             delete f;
         };
@@ -203,6 +208,44 @@ bool is_pageable(const void* p) {
     }
     return at.type == cudaMemoryTypeUnregistered;
 }
+
+}  // namespace
+
+// Host array -> device on stream `st`.  A page-locked source goes straight to the copy engine.  A pageable one the driver
+// would stage through its own bounce buffer with one thread (measured: 290 MB of pre-built operators in 64 ms, 4.5 GB/s);
+// here the pool's threads copy 16 MB pieces into three page-locked buffers while the earlier pieces are on the link.
+// As with any copy from pageable memory the source has been read in full when this returns.
+int otmb_h2d(otmb_ctx* c, void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    constexpr int UP_BUFS = 3;
+    FetchState* f = nullptr;
+    if (bytes >= ((size_t)4 << 20) && is_pageable(src) && !getenv("OTMB_UPLOAD_DIRECT")) OT_TRY(fetch_state(c, &f));
+    if (f && !f->few_threads && !f->up_stage) {
+        if (cudaMallocHost((void**)&f->up_stage, UP_BUFS * CHUNK_BYTES) != cudaSuccess) {
+            cudaGetLastError();
+            f->up_stage = nullptr;
+        } else
+            for (auto& e : f->up_ev) CU_TRY(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    if (!f || f->few_threads || !f->up_stage) {
+        CU_TRY(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+        return OTMB_OK;
+    }
+    int piece = 0;
+    for (size_t lo = 0; lo < bytes; lo += CHUNK_BYTES, ++piece) {
+        const size_t cnt = std::min(CHUNK_BYTES, bytes - lo);
+        const int b = piece % UP_BUFS;
+        char* stage = f->up_stage + (size_t)b * CHUNK_BYTES;
+        if (piece >= UP_BUFS) CU_TRY(c, cudaEventSynchronize(f->up_ev[b]));
+        f->pool->run(1, (const char*)src + lo, stage, cnt);
+        CU_TRY(c, cudaMemcpyAsync((char*)dst + lo, stage, cnt, cudaMemcpyHostToDevice, st));
+        CU_TRY(c, cudaEventRecord(f->up_ev[b], st));
+    }
+    // the buffers are reused by the next call: wait until the link has taken the last pieces
+    for (int b = 0; b < std::min(piece, UP_BUFS); ++b) CU_TRY(c, cudaEventSynchronize(f->up_ev[b]));
+    return OTMB_OK;
+}
+
+namespace {
 
 // One copy-out in flight: device arrays -> caller arrays, on stream `st`.
 //   indices : narrowed to Int32 on the device, copied into pinned staging in 16 MB chunks (an event per chunk), widened

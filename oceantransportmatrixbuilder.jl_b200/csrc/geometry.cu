@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(128) k_geom2d(const double* __restrict__ lon, 
 
 int upload(otmb_ctx* ctx, DevBuf& buf, const void* host, size_t bytes) {
     CU_TRY(ctx, buf.ensure(bytes));
-    CU_TRY(ctx, cudaMemcpyAsync(buf.p, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    OT_TRY(otmb_h2d(ctx, buf.p, host, bytes, ctx->stream));
     return OTMB_OK;
 }
 

@@ -61,7 +61,7 @@ extern "C" int otmb_facefluxes_gm(otmb_ctx* c, const double* umo, const double* 
     const size_t M8 = (size_t)c->M * 8;
     DevBuf *b = c->coo;   // scratch of the COO path, idle here: ρ, Sᵢ, Sⱼ, u*, v*, ϕᵢ*, ϕⱼ*
     for (int q = 0; q < 7; ++q) CU_TRY(c, b[q].ensure(M8));
-    CU_TRY(c, cudaMemcpyAsync(b[0].p, rho3d, M8, cudaMemcpyHostToDevice, c->stream));
+    OT_TRY(otmb_h2d(c, b[0].p, rho3d, M8, c->stream));
     OT_TRY(otmb_upload_uv(c, umo, vmo, fill));
     OT_TRY(otmb_reset_flags(c));
     OT_TRY(otmb_bolus_gm_dev(c, b[0].as<double>(), kGM, maxslope, b[1].as<double>(), b[2].as<double>(), b[3].as<double>(),

@@ -227,8 +227,8 @@ int otmb_lump_and_spray_build(otmb_ctx* c, int64_t di, int64_t dj, int64_t dk, c
         const i64 tn = t_colptr[N] - t_index_base;
         CU_TRY(c, c->add_tmp[0].ensure((size_t)(N + 1) * 8));
         CU_TRY(c, c->add_tmp[1].ensure((size_t)(tn + 1) * 8));
-        CU_TRY(c, cudaMemcpyAsync(c->add_tmp[0].p, t_colptr, (size_t)(N + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-        if (tn > 0) CU_TRY(c, cudaMemcpyAsync(c->add_tmp[1].p, t_rowval, (size_t)tn * 8, cudaMemcpyHostToDevice, c->stream));
+        OT_TRY(otmb_h2d(c, c->add_tmp[0].p, t_colptr, (size_t)(N + 1) * 8, c->stream));
+        if (tn > 0) OT_TRY(otmb_h2d(c, c->add_tmp[1].p, t_rowval, (size_t)tn * 8, c->stream));
         P.t_colptr = c->add_tmp[0].as<i64>();
         P.t_rowval = c->add_tmp[1].as<i64>();
         P.t_base = t_index_base;
@@ -244,7 +244,7 @@ int otmb_lump_and_spray_build(otmb_ctx* c, int64_t di, int64_t dj, int64_t dk, c
     CU_TRY(c, b[2].ensure((size_t)(nboxes + 1) * 4));
     CU_TRY(c, b[3].ensure((size_t)(N + 1) * 4));
     CU_TRY(c, b[5].ensure(8));
-    CU_TRY(c, cudaMemcpyAsync(b[0].p, vol, (size_t)N * 8, cudaMemcpyHostToDevice, c->stream));
+    OT_TRY(otmb_h2d(c, b[0].p, vol, (size_t)N * 8, c->stream));
     CU_TRY(c, cudaMemsetAsync(b[5].p, 0, 8, c->stream));
     OT_TRY(otmb_reset_flags(c));
     const unsigned grid = grid_for(nboxes, 128);

@@ -140,7 +140,7 @@ int otmb_triad_derivative(otmb_ctx* c, const double* chi, int dir, double* out) 
     const size_t M8 = (size_t)c->M * 8;
     CU_TRY(c, c->stage_a.ensure(M8));
     CU_TRY(c, c->stage_b.ensure(M8));
-    CU_TRY(c, cudaMemcpyAsync(c->stage_a.p, chi, M8, cudaMemcpyHostToDevice, c->stream));
+    OT_TRY(otmb_h2d(c, c->stage_a.p, chi, M8, c->stream));
     OT_TRY(otmb_reset_flags(c));
     OT_TRY(triad_dev(c, c->stage_a.as<double>(), dir, c->stage_b.as<double>()));
     OT_TRY(otmb_fetch_flags(c));
@@ -158,7 +158,7 @@ int otmb_dyad_derivative(otmb_ctx* c, const double* chi, double* out) {
     const size_t M8 = (size_t)c->M * 8;
     CU_TRY(c, c->stage_a.ensure(M8));
     CU_TRY(c, c->stage_b.ensure(M8));
-    CU_TRY(c, cudaMemcpyAsync(c->stage_a.p, chi, M8, cudaMemcpyHostToDevice, c->stream));
+    OT_TRY(otmb_h2d(c, c->stage_a.p, chi, M8, c->stream));
     OT_TRY(dyad_dev(c, c->stage_a.as<double>(), c->stage_b.as<double>()));
     CU_TRY(c, cudaMemcpyAsync(out, c->stage_b.p, M8, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
@@ -176,7 +176,7 @@ int otmb_bolus_gm_velocity(otmb_ctx* c, const double* rho, double kGM, double ma
     CU_TRY(c, sj.ensure(M8));
     CU_TRY(c, du.ensure(M8));
     CU_TRY(c, dv.ensure(M8));
-    CU_TRY(c, cudaMemcpyAsync(dr.p, rho, M8, cudaMemcpyHostToDevice, c->stream));
+    OT_TRY(otmb_h2d(c, dr.p, rho, M8, c->stream));
     OT_TRY(otmb_reset_flags(c));
     OT_TRY(triad_dev(c, dr.as<double>(), 0, si.as<double>()));
     OT_TRY(triad_dev(c, dr.as<double>(), 1, sj.as<double>()));

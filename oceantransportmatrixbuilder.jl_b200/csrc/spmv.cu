@@ -42,7 +42,7 @@ extern "C" int otmb_spmv(otmb_ctx* c, int which, int transpose, const double* x,
     const int base = c->out_base;
     CU_TRY(c, c->spmv_x.ensure((size_t)(n + 1) * 8));
     CU_TRY(c, c->spmv_y.ensure((size_t)(n + 1) * 8));
-    CU_TRY(c, cudaMemcpyAsync(c->spmv_x.p, x, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    OT_TRY(otmb_h2d(c, c->spmv_x.p, x, (size_t)n * 8, c->stream));
     if (transpose) {
         k_csc_dot<<<grid_for(n, 256), 256, 0, c->stream>>>(c->colptr[which].as<i64>(), c->rowval[which].as<i64>(),
                                                             c->nzval[which].as<double>(), c->spmv_x.as<double>(), n, base,

@@ -75,9 +75,9 @@ int run_velflux(otmb_ctx* c, int mode, const double* a_i, const double* a_j, con
     const size_t M8 = (size_t)c->M * 8;
     DevBuf* b = c->add_tmp;   // scratch: inputs 0,1 (+ rho 2), outputs 3,4
     for (int q = 0; q < 5; ++q) CU_TRY(c, b[q].ensure(M8));
-    CU_TRY(c, cudaMemcpyAsync(b[0].p, a_i, M8, cudaMemcpyHostToDevice, c->stream));
-    CU_TRY(c, cudaMemcpyAsync(b[1].p, a_j, M8, cudaMemcpyHostToDevice, c->stream));
-    if (rho3d) CU_TRY(c, cudaMemcpyAsync(b[2].p, rho3d, M8, cudaMemcpyHostToDevice, c->stream));
+    OT_TRY(otmb_h2d(c, b[0].p, a_i, M8, c->stream));
+    OT_TRY(otmb_h2d(c, b[1].p, a_j, M8, c->stream));
+    if (rho3d) OT_TRY(otmb_h2d(c, b[2].p, rho3d, M8, c->stream));
     GridDims g{(int)c->nx, (int)c->ny, (int)c->nz, c->topo, (int)c->P, (int)c->M};
     const double* dr = rho3d ? b[2].as<double>() : nullptr;
     if (mode == 0)
@@ -126,8 +126,8 @@ int otmb_bgrid_to_cgrid(otmb_ctx* c, const double* u, const double* v, double fi
     const size_t M8 = (size_t)c->M * 8;
     DevBuf* b = c->add_tmp;
     for (int q = 0; q < 4; ++q) CU_TRY(c, b[q].ensure(M8));
-    CU_TRY(c, cudaMemcpyAsync(b[0].p, u, M8, cudaMemcpyHostToDevice, c->stream));
-    CU_TRY(c, cudaMemcpyAsync(b[1].p, v, M8, cudaMemcpyHostToDevice, c->stream));
+    OT_TRY(otmb_h2d(c, b[0].p, u, M8, c->stream));
+    OT_TRY(otmb_h2d(c, b[1].p, v, M8, c->stream));
     GridDims g{(int)c->nx, (int)c->ny, (int)c->nz, c->topo, (int)c->P, (int)c->M};
     k_bgrid2cgrid<<<grid_for(c->M, 256), 256, 0, c->stream>>>(b[0].as<double>(), b[1].as<double>(), fill_value, g,
                                                                b[2].as<double>(), b[3].as<double>());

@@ -661,8 +661,8 @@ def test_fuzz_small_grids_bit_exact(seed):
 
 def test_prebuilt_operator_is_validated():
     """A wrong-shaped pre-built operator is a DimensionMismatch in the reference's sum (src/matrixbuilding.jl:147); here
-    otmb_set_operator checks the caller's CSC before anything reaches the device: colptr length / ends / monotonicity, row
-    range, ascending rows."""
+    otmb_set_operator checks the caller's CSC (colptr ends on the host; monotonicity, row range and ascending rows by a
+    kernel over the uploaded arrays) and a rejected operator is not kept."""
     import ctypes as C
     oc = synthetic.make_config("C1t", seed=5)
     g = gpu_pipeline(oc)
@@ -686,3 +686,43 @@ def test_prebuilt_operator_is_validated():
     # the context is still usable and the good operator gives the reference's sum
     tm = otmb_b200.transportmatrix(ϕ=g["phi"], mlotst=oc.mlotst, gridmetrics=g["gm"], indices=g["ix"], ρ=1035.0, TκH=good)
     assert np.array_equal(tm.T.indptr, g["tm"].T.indptr) and np.array_equal(bits(tm.T.data), bits(g["tm"].T.data))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("change", ["same", "values", "pattern", "other_kappa", "all_four"])
+def test_prebuilt_operators_equal_or_not(change):
+    """Pre-built operators that equal what this call would build take the single-pass route, anything else the
+    generic sparse `+` (src/matrixbuilding.jl:147): either way T is ((Tadv + TκH) + TκVML) + TκVdeep of the
+    operators the caller ends up holding."""
+    import scipy.sparse as sp
+    oc = synthetic.make_ocean(22, 16, 7, "tripolar", seed=11, land_frac=0.2)
+    o = oracle_pipeline(oc)
+    tm, gm = transport_from_oracle_inputs(o, oc)
+    phi = A.FaceFluxes(**o["phi"])
+    kw = dict(ϕ=phi, mlotst=oc.mlotst, gridmetrics=gm, indices=None, ρ=1035.0)
+    H, D = sp.csc_matrix(tm.TκH, copy=True), sp.csc_matrix(tm.TκVdeep, copy=True)
+    if change == "values":
+        H.data[::7] *= 3.0
+    elif change == "pattern":
+        # drop one stored entry of the third column that has a few
+        j = int(np.flatnonzero(np.diff(H.indptr) >= 3)[2])
+        keep = np.ones(H.nnz, bool)
+        keep[H.indptr[j] + 1] = False
+        cols = np.repeat(np.arange(H.shape[1]), np.diff(H.indptr))
+        H = sp.csc_matrix((H.data[keep], (H.indices[keep], cols[keep])), shape=H.shape)
+        H.sort_indices()
+    elif change == "other_kappa":
+        kw["κH"] = 250.0          # H was built with 500: it must be used as supplied, not rebuilt
+    if change == "all_four":
+        got = A.transportmatrix(**kw, Tadv=tm.Tadv, TκH=H, TκVML=tm.TκVML, TκVdeep=D)
+    else:
+        got = A.transportmatrix(**kw, TκH=H, TκVdeep=D)
+    as_orc = lambda m: O.CSC(m.shape[0], m.indptr.astype(np.int64) + 1, m.indices.astype(np.int64) + 1, m.data.astype(np.float64))
+    want = O.spadd(O.spadd(O.spadd(as_orc(got.Tadv), as_orc(H)), as_orc(got.TκVML)), as_orc(D))
+    assert_csc_equal(got.T, want, f"T with supplied operators ({change})", exact=True)
+    assert_csc_equal(got.Tadv, o["tm"]["Tadv"], "Tadv", exact=True)
+    assert_csc_equal(got.TκVML, o["tm"]["TkVML"], "TκVML", exact=True)
+    # and the context is not left in a state that disturbs the next ordinary build
+    again, _ = transport_from_oracle_inputs(o, oc)
+    for oname, gname in NAMES.items():
+        assert_csc_equal(getattr(again, gname), o["tm"][oname], f"after {change}: {oname}", exact=True)
