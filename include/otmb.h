@@ -245,7 +245,11 @@ int otmb_transportmatrix_dump(otmb_ctx* ctx, int mask, const char* path);
  * threads (0 = the calling thread). */
 int otmb_host_widen(const int32_t* src, int64_t* dst, int64_t n, int32_t threads);
 /* a pre-built operator passed by the caller (the Tadv/TκH/TκVML/TκVdeep kwargs, :133-143);
- * indices in params.index_base of the next build */
+ * indices in params.index_base of the next build.  The CSC is checked (N+1 non-decreasing colptr entries from
+ * index_base to index_base + nnz, rows strictly ascending inside [0, N)): OTMB_ERR_BADARG otherwise, and the operator
+ * is not kept.  The next build sums what was supplied with what it builds, (((Tadv + TκH) + TκVML) + TκVdeep), :147;
+ * when a supplied operator equals, bit for bit, what the build's own inputs give, that is done in the single-pass
+ * kernel, otherwise by the generic sparse `+` — the result is the same either way. */
 int otmb_set_operator(otmb_ctx* ctx, int which, int64_t nnz, const int64_t* colptr, const int64_t* rowval,
                       const double* nzval, int32_t index_base);
 
