@@ -341,6 +341,11 @@ int otmb_last_build_ms(otmb_ctx* ctx, float* milliseconds); /* device time of th
  * off saves two driver calls per build — a build is then exactly two launches, the kernel and its completion record) */
 int otmb_set_build_timing(otmb_ctx* ctx, int32_t on);
 int otmb_synchronize(otmb_ctx* ctx);
+/* device self-test: the assembly kernel divides through a two-at-a-time routine (csrc/fdiv.cuh) that must give the
+ * compiler's IEEE-754 quotient bit for bit; this compares the two over 2n operand pairs drawn from `seed` (random bit
+ * patterns, ordinary magnitudes, and exponents at the edges: zero, subnormal, huge, Inf, NaN).  *mismatches must be 0;
+ * first_bad (may be NULL) receives {a, b, routine's quotient, a / b} of one disagreement. */
+int otmb_selftest_division(otmb_ctx* ctx, int64_t n, uint64_t seed, int64_t* mismatches, double first_bad[4]);
 
 #ifdef __cplusplus
 }

@@ -29,6 +29,7 @@ EXPORTS = [
     "otmb_sharded_makeindices", "otmb_set_masstransport", "otmb_sharded_facefluxes", "otmb_sharded_facefluxes_enqueue",
     "otmb_sharded_transportmatrix_build", "otmb_result_checksum",
     "otmb_facefluxes_gm", "otmb_transportmatrix_stream", "otmb_coarsen_build", "otmb_coarsen_fetch", "otmb_transportmatrix_dump",
+    "otmb_selftest_division",
 ]
 
 
@@ -89,6 +90,7 @@ def load():
         "otmb_last_build_ms": ([vp, C.POINTER(C.c_float)], C.c_int),
         "otmb_set_build_timing": ([vp, i32], C.c_int),
         "otmb_synchronize": ([vp], C.c_int),
+        "otmb_selftest_division": ([vp, i64, C.c_uint64, pi64, vp], C.c_int),
         "otmb_velocity2fluxes": ([vp, vp, vp, vp, dbl, vp, vp], C.c_int),
         "otmb_fluxes2velocity": ([vp, vp, vp, vp, dbl, vp, vp], C.c_int),
         "otmb_bgrid_to_cgrid": ([vp, vp, vp, dbl, vp, vp], C.c_int),

@@ -11,8 +11,8 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 INCLUDE = HERE.parent / "include"
 LIB = HERE / "libotmb.so"
-SOURCES = ["ctx.cu", "scan.cu", "geometry.cu", "faceflux.cu", "fused.cu", "fused_v4.cu", "coo.cu", "transport.cu", "redigm.cu", "velocity.cu", "lump.cu", "spmv.cu", "fetch.cu", "comm.cu", "gm.cu"]
-HEADERS = ["common.cuh", "sphere.cuh", "fused_generic.cuh"]
+SOURCES = ["ctx.cu", "scan.cu", "geometry.cu", "faceflux.cu", "fused.cu", "fused_v4.cu", "coo.cu", "transport.cu", "redigm.cu", "velocity.cu", "lump.cu", "spmv.cu", "fetch.cu", "comm.cu", "gm.cu", "selftest.cu"]
+HEADERS = ["common.cuh", "sphere.cuh", "fused_generic.cuh", "fdiv.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

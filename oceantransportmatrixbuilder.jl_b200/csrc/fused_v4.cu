@@ -41,6 +41,7 @@
 #include <type_traits>
 
 #include "fused_generic.cuh"
+#include "fdiv.cuh"
 
 using namespace fusedg;
 
@@ -123,6 +124,15 @@ __device__ __forceinline__ bool inflow(double x, bool take_max) {
     return fabs(x) > __longlong_as_double(1ll);
 }
 __device__ __forceinline__ bool nz(double f) { return f > 0 || f < 0; }
+// q1 = a1 / b1 and q2 = a2 / b2 with overlapping chains (fdiv.cuh); -DOTMB_NO_DIV2 restores two plain divisions
+__device__ __forceinline__ void div_pair(const double a1, const double b1, const double a2, const double b2, double& q1, double& q2) {
+#ifdef OTMB_NO_DIV2
+    q1 = a1 / b1;
+    q2 = a2 / b2;
+#else
+    otmb_fdiv::div2(a1, b1, a2, b2, q1, q2);
+#endif
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int TILE>
@@ -573,8 +583,8 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
                     const double f = UP ? xs[c] : xs[c] / 2;   // active: max / min picked the flux itself
                     const double p = mx ? f : -f;
                     const double rb = (rn[c] + rhoC) / 2;
-                    const double a = -p / (rb * vn[c]);
-                    dd[c] = p / (rb * vC);
+                    double a;
+                    div_pair(-p, rb * vn[c], p, rb * vC, a, dd[c]);
                     bad |= isnan(a) || isnan(dd[c]);
                     const int pp = off1 + __popc(m_adv & low_of(c));
                     srow[pp] = S.rk[c][tid];
@@ -648,8 +658,8 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
                 const int c = q == 0 ? cW : q == 1 ? cE : q == 2 ? cS : cN;
                 if ((m_kh >> c) & 1) {
                     const double ka = P.kH * jl_min(thC * e_own[u], th[u] * e_opp[u]);
-                    const double ts = ka / (d_own[u] * vC);       // row 𝑗 seen from 𝑗
-                    const double tn = ka / (d_opp[u] * vnb[u]);   // row 𝑖 seen from 𝑖
+                    double ts, tn;   // row 𝑗 seen from 𝑗, row 𝑖 seen from 𝑖
+                    div_pair(ka, d_own[u] * vC, ka, d_opp[u] * vnb[u], ts, tn);
                     bad |= isnan(ts) || isnan(tn);
                     kh_dsum = first ? ts : kh_dsum + ts;
                     first = false;
@@ -724,7 +734,8 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
                     const double qs = d * vC, qn = d * (VAH ? (c == cT ? vt_vT : vt_vB) : __ldg(P.v3D + Lc_of(c)));
                     if (m_dp) {
                         const double ka = P.kVdeep * area;
-                        const double ts = ka / qs, tn = ka / qn;
+                        double ts, tn;
+                        div_pair(ka, qs, ka, qn, ts, tn);
                         badd |= isnan(ts) || isnan(tn);
                         dps = firstd ? ts : dps + ts;
                         firstd = false;
@@ -732,7 +743,8 @@ __global__ void __launch_bounds__(TILE + 32, MINB) k_fused_v4(const __grid_const
                     }
                     if (mlm >> c & 1) {
                         const double ka = P.kVML * area;
-                        const double ts = ka / qs, tn = ka / qn;
+                        double ts, tn;
+                        div_pair(ka, qs, ka, qn, ts, tn);
                         badm |= isnan(ts) || isnan(tn);
                         mls = firstm ? ts : mls + ts;
                         firstm = false;

@@ -726,3 +726,16 @@ def test_prebuilt_operators_equal_or_not(change):
     again, _ = transport_from_oracle_inputs(o, oc)
     for oname, gname in NAMES.items():
         assert_csc_equal(getattr(again, gname), o["tm"][oname], f"after {change}: {oname}", exact=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [1, 0x5eed5eed5eed])
+def test_paired_division_equals_the_compilers(seed):
+    """csrc/fdiv.cuh: the two-at-a-time division of the assembly kernel against `/` on the device, bit for bit, over
+    2^28 operand pairs per seed (random bit patterns, ordinary magnitudes, exponent edge cases)."""
+    import ctypes as C
+    c = A.Context(0)
+    bad = C.c_int64(-1)
+    first = (C.c_double * 4)()
+    c.check(c.lib.otmb_selftest_division(c.h, 1 << 27, seed, C.byref(bad), first))
+    assert bad.value == 0, f"{bad.value} quotients differ, e.g. a={first[0]!r} b={first[1]!r}: {first[2]!r} vs {first[3]!r}"
