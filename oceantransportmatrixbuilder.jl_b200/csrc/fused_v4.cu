@@ -1012,6 +1012,8 @@ int otmb_fused_v4_build(otmb_ctx* c, const otmb_tm_params* prm, int build, i64 c
         case 2: return launch_v4<false, true, 416, 2>(c, P);   // 72 registers
         case 3: return launch_v4<false, true, 352, 2, 1>(c, P);   // TκH loads direction by direction
         case 4: return launch_v4<false, true, 352, 2, 2, false, false>(c, P);   // vertical inputs and own volume loaded where they are used
+        case 5: return launch_v4<false, true, 320, 2>(c, P);   // 88 registers, 20 + 2 warps per SM
+        case 6: return launch_v4<false, true, 288, 2>(c, P);   // 96 registers, 18 + 2 warps per SM
         default: break;
     }
 #endif
