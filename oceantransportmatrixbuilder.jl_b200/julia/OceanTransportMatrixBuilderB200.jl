@@ -275,19 +275,25 @@ function oncgrid(u, u_lon, u_lat, v, v_lon, v_lat, gridmetrics)
     r = REF.interpolateontodefaultCgrid(u, u_lon, u_lat, v, v_lon, v_lat, gridmetrics, grid)
     return Array{Float64}(r[1]), Array{Float64}(r[4])
 end
-function _velflux(sym, a::Array{Float64, 3}, b::Array{Float64, 3}, gridmetrics, ρ)
+function _velflux(forward::Bool, a::Array{Float64, 3}, b::Array{Float64, 3}, gridmetrics, ρ)
     c = ctx(); oa = similar(a); ob = similar(b)
     ensure_metrics(c, gridmetrics)
     ρ3 = ρ isa Number ? nothing : Array{Float64}(ρ)
-    GC.@preserve ρ3 check(c, ccall((sym, LIBOTMB), Cint, (PV, PF, PF, PF, Float64, PF, PF),
-                                   c.h, a, b, isnothing(ρ3) ? PF(C_NULL) : pointer(ρ3), ρ isa Number ? Float64(ρ) : 0.0, oa, ob))
+    ρs = ρ isa Number ? Float64(ρ) : 0.0
+    GC.@preserve ρ3 begin
+        p3 = isnothing(ρ3) ? PF(C_NULL) : pointer(ρ3)
+        # (the function name of a ccall has to be a constant: two calls, not a symbol argument)
+        st = forward ? ccall((:otmb_velocity2fluxes, LIBOTMB), Cint, (PV, PF, PF, PF, Float64, PF, PF), c.h, a, b, p3, ρs, oa, ob) :
+                       ccall((:otmb_fluxes2velocity, LIBOTMB), Cint, (PV, PF, PF, PF, Float64, PF, PF), c.h, a, b, p3, ρs, oa, ob)
+        check(c, st)
+    end
     return oa, ob
 end
 function velocity2fluxes(u, u_lon, u_lat, v, v_lon, v_lat, gridmetrics, ρ)          # src/velocities.jl:10-39
     uc, vc = oncgrid(u, u_lon, u_lat, v, v_lon, v_lat, gridmetrics)
-    return _velflux(:otmb_velocity2fluxes, uc, vc, gridmetrics, ρ)
+    return _velflux(true, uc, vc, gridmetrics, ρ)
 end
-fluxes2velocity(ϕᵢ, ϕⱼ, gridmetrics, ρ) = _velflux(:otmb_fluxes2velocity, Array{Float64}(ϕᵢ), Array{Float64}(ϕⱼ), gridmetrics, ρ)   # :50-74
+fluxes2velocity(ϕᵢ, ϕⱼ, gridmetrics, ρ) = _velflux(false, Array{Float64}(ϕᵢ), Array{Float64}(ϕⱼ), gridmetrics, ρ)   # :50-74
 function facefluxesfromvelocities(; uo, uo_lon, uo_lat, vo, vo_lon, vo_lat, gridmetrics, indices, ρ)   # :140-151
     FillValue = uo.properties["_FillValue"]
     @assert isequal(FillValue, vo.properties["_FillValue"])
@@ -432,5 +438,89 @@ end
 
 close(s::Slab) = ccall((:otmb_comm_free, LIBOTMB), Cint, (PV,), s.c.h)
 end # module Sharded
+
+# ------------------------------------------------------------------------------------------------------------------
+# The rest of include/otmb.h: diagnostics, timers, the generic sparse helpers and the hand-driven slab calls.  Nothing
+# above needs them; they are bound so that a Julia host can reach every entry point of the library.
+# ------------------------------------------------------------------------------------------------------------------
+module LowLevel
+import ..LIBOTMB, ..Context, ..ctx, ..check, ..PF, ..PI, ..PV
+using SparseArrays
+
+version() = Int(ccall((:otmb_version, LIBOTMB), Cint, ()))
+device_count() = (n = Ref{Cint}(0); ccall((:otmb_device_count, LIBOTMB), Cint, (Ref{Cint},), n); Int(n[]))
+synchronize(c::Context = ctx()) = check(c, ccall((:otmb_synchronize, LIBOTMB), Cint, (PV,), c.h))
+"give the pooled page-locked blocks that are not in use back to the system"
+host_trim() = ccall((:otmb_host_trim, LIBOTMB), Cint, ())
+"sign-extend Int32 indices into Int64 on `threads` pool threads (the host half of the copy-out pipeline)"
+function host_widen!(dst::Vector{Int64}, src::Vector{Int32}; threads::Integer = 0)
+    length(dst) == length(src) || throw(DimensionMismatch("dst and src differ in length"))
+    ccall((:otmb_host_widen, LIBOTMB), Cint, (Ptr{Int32}, PI, Int64, Int32), src, dst, length(src), threads) == 0 || error("otmb_host_widen")
+    return dst
+end
+
+# timers / counters of a context (CUDA events on the library's stream)
+timer_start(c::Context = ctx()) = check(c, ccall((:otmb_timer_start, LIBOTMB), Cint, (PV,), c.h))
+timer_stop(c::Context = ctx()) = (ms = Ref{Cfloat}(0); check(c, ccall((:otmb_timer_stop, LIBOTMB), Cint, (PV, Ref{Cfloat}), c.h, ms)); Float64(ms[]))
+l2_flush(c::Context = ctx()) = check(c, ccall((:otmb_l2_flush, LIBOTMB), Cint, (PV,), c.h))
+launch_count(c::Context = ctx()) = (n = Ref{Int64}(0); check(c, ccall((:otmb_launch_count, LIBOTMB), Cint, (PV, Ref{Int64}), c.h, n)); n[])
+last_build_ms(c::Context = ctx()) = (ms = Ref{Cfloat}(0); check(c, ccall((:otmb_last_build_ms, LIBOTMB), Cint, (PV, Ref{Cfloat}), c.h, ms)); Float64(ms[]))
+set_build_timing(on::Bool, c::Context = ctx()) = check(c, ccall((:otmb_set_build_timing, LIBOTMB), Cint, (PV, Int32), c.h, on))
+
+"device self-test of the kernel's paired division against `/` (csrc/fdiv.cuh); returns the number of mismatches (must be 0)"
+function selftest_division(n::Integer = 1 << 24, seed::Integer = 1, c::Context = ctx())
+    bad = Ref{Int64}(-1); first_bad = zeros(Float64, 4)
+    check(c, ccall((:otmb_selftest_division, LIBOTMB), Cint, (PV, Int64, UInt64, Ref{Int64}, PF), c.h, n, seed, bad, first_bad))
+    return bad[], first_bad
+end
+
+"SparseArrays.sparse(I, J, V, n, n) on the device (src/matrixbuilding.jl:41; duplicates summed in emit order, zeros kept)"
+function sparse_device(I::Vector{Int64}, J::Vector{Int64}, V::Vector{Float64}, n::Integer, c::Context = ctx())
+    nnz = Ref{Int64}(0)
+    check(c, ccall((:otmb_sparse_build, LIBOTMB), Cint, (PV, Int64, PI, PI, PF, Int64, Ref{Int64}), c.h, length(I), I, J, V, n, nnz))
+    cp = Vector{Int64}(undef, n + 1); rv = Vector{Int64}(undef, nnz[]); nz = Vector{Float64}(undef, nnz[])
+    check(c, ccall((:otmb_sparse_fetch, LIBOTMB), Cint, (PV, PI, PI, PF), c.h, cp, rv, nz))
+    return SparseMatrixCSC{Float64, Int64}(n, n, cp, rv, nz)
+end
+
+"A + B of two N x N SparseMatrixCSC on the device (src/matrixbuilding.jl:147: results equal to zero are dropped)"
+function spadd_device(A::SparseMatrixCSC{Float64, Int64}, B::SparseMatrixCSC{Float64, Int64}, c::Context = ctx())
+    n = size(A, 1); nnz = Ref{Int64}(0)
+    check(c, ccall((:otmb_spadd_build, LIBOTMB), Cint, (PV, Int64, PI, PI, PF, PI, PI, PF, Ref{Int64}),
+                   c.h, n, A.colptr, A.rowval, A.nzval, B.colptr, B.rowval, B.nzval, nnz))
+    cp = Vector{Int64}(undef, n + 1); rv = Vector{Int64}(undef, nnz[]); nz = Vector{Float64}(undef, nnz[])
+    check(c, ccall((:otmb_spadd_fetch, LIBOTMB), Cint, (PV, PI, PI, PF), c.h, cp, rv, nz))
+    return SparseMatrixCSC{Float64, Int64}(n, n, cp, rv, nz)
+end
+
+# slab calls for a host that drives the exchanges itself (e.g. MPI.jl instead of the library's NCCL communicator):
+# whole-level slabs, the carry plane handed in and out by the caller.  `Sharded` above is the packaged form.
+set_slab(c::Context, k_begin::Integer, k_end::Integer) = check(c, ccall((:otmb_set_slab, LIBOTMB), Cint, (PV, Int64, Int64), c.h, k_begin, k_end))
+function slab_counts(c::Context)
+    own, halo = Ref{Int64}(0), Ref{Int64}(0)
+    check(c, ccall((:otmb_slab_counts, LIBOTMB), Cint, (PV, Ref{Int64}, Ref{Int64}), c.h, own, halo))
+    return own[], halo[]
+end
+set_rank_offset(c::Context, w0::Integer) = check(c, ccall((:otmb_set_rank_offset, LIBOTMB), Cint, (PV, Int64), c.h, w0))
+"facefluxes on this context's slab: `carry_in` = ϕtop plane of the slab below (nothing at the bottom), returns (carry_out, valid_uv)"
+function facefluxes_slab(c::Context, umo::Array{Float64, 3}, vmo::Array{Float64, 3}, FillValue, carry_in::Union{Nothing, Matrix{Float64}})
+    nx, ny, _ = size(umo)
+    carry_out = Matrix{Float64}(undef, nx, ny); valid = zeros(Int32, 2)
+    GC.@preserve carry_in check(c, ccall((:otmb_facefluxes_slab, LIBOTMB), Cint,
+        (PV, PF, PF, Float64, PF, PF, Int32, Ptr{Int32}, PF, PF, PF, PF, PF, PF), c.h, umo, vmo, Float64(FillValue),
+        isnothing(carry_in) ? PF(C_NULL) : pointer(carry_in), carry_out, 0, valid, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL))
+    return carry_out, valid
+end
+"the carry chain of `Sharded.facefluxes!` enqueued without waiting for it (umo / vmo set with otmb_set_masstransport)"
+facefluxes_enqueue(c::Context; nchunks::Integer = 0) = check(c, ccall((:otmb_sharded_facefluxes_enqueue, LIBOTMB), Cint, (PV, Int32), c.h, nchunks))
+"all-gather of `count` Int64 per rank over the context's communicator"
+function allgather(c::Context, mine::Vector{Int64}, nranks::Integer)
+    all = Vector{Int64}(undef, nranks * length(mine))
+    check(c, ccall((:otmb_comm_allgather_i64, LIBOTMB), Cint, (PV, PI, Int32, PI), c.h, mine, length(mine), all))
+    return all
+end
+"1 = the carry chain ran over peer memory (CUDA IPC), -1 = over NCCL send / recv, 0 = no chain has run yet"
+chain_transport(c::Context) = (t = Ref{Int32}(0); check(c, ccall((:otmb_comm_chain_transport, LIBOTMB), Cint, (PV, Ref{Int32}), c.h, t)); Int(t[]))
+end # module LowLevel
 
 end # module

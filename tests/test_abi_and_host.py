@@ -206,3 +206,61 @@ def test_bench_cuda_arm_line_and_same_config_as_reference_arm():
     assert rf["frac_step"] <= rf["frac"] * 1.05 and rf["traffic"] is None
     assert d["gpu_launches"] >= 3 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+
+
+def test_julia_shim_binds_every_export_with_matching_types():
+    """Julia is not in the image, so the shim is never executed: every entry point of include/otmb.h must be bound
+    there, and every `ccall` must list, argument by argument, a Julia type that matches the C parameter."""
+    import re
+    root = Path(__file__).resolve().parent.parent
+    header = re.sub(r"/\*.*?\*/", " ", (root / "include" / "otmb.h").read_text(), flags=re.S)
+
+    def c_kind(param):                                  # (base type, levels of indirection) of one C parameter
+        param = re.sub(r"\s+", " ", param.strip())
+        levels = 1 if "[" in param else 0
+        param = re.sub(r"\[[^\]]*\]", "", param)
+        toks = param.split(" ")
+        typ = " ".join(toks[:-1]) if len(toks) > 1 and not toks[-1].endswith("*") else param
+        typ = typ.replace("const ", "").replace(" const", "").strip()
+        return typ.replace("*", "").strip(), levels + typ.count("*")
+
+    decl = {}
+    for m in re.finditer(r"\b(?:int|const char\*)\s+(otmb_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S):
+        params = m.group(2).strip()
+        decl[m.group(1)] = [] if params in ("", "void") else [c_kind(x) for x in params.split(",")]
+    assert len(decl) > 60
+    julia_for = {
+        ("otmb_ctx", 1): {"PV"}, ("otmb_ctx", 2): {"Ref{PV}"}, ("void", 2): {"Ref{PV}"}, ("void", 1): {"PV", "Ptr{UInt8}"},
+        ("double", 0): {"Float64"}, ("double", 1): {"PF", "Ptr{Float64}"}, ("double", 2): {"Ptr{PF}", "PV"},
+        ("int64_t", 0): {"Int64"}, ("int64_t", 1): {"PI", "Ref{Int64}", "Ptr{Int64}"}, ("int64_t", 2): {"Ptr{PI}", "PV"},
+        ("int32_t", 0): {"Int32", "Cint"}, ("int32_t", 1): {"Ptr{Int32}", "Ref{Int32}", "Ref{Cint}", "Ptr{Cint}"},
+        ("int", 0): {"Cint", "Int32"}, ("int", 1): {"Ref{Cint}", "Ptr{Cint}"},
+        ("uint64_t", 0): {"UInt64"}, ("uint64_t", 1): {"Ptr{UInt64}"}, ("float", 1): {"Ref{Cfloat}"},
+        ("char", 1): {"Cstring"}, ("unsigned char", 1): {"Ptr{UInt8}"}, ("uint8_t", 1): {"Ptr{UInt8}"},
+        ("otmb_tm_params", 1): {"Ref{TMParams}"},
+    }
+    shim = (root / "oceantransportmatrixbuilder.jl_b200" / "julia" / "OceanTransportMatrixBuilderB200.jl").read_text()
+    assert not re.search(r"ccall\(\(\s*[a-z_]\w*\s*,", shim), "a ccall names its function through a variable: Julia needs a constant"
+    seen = set()
+    for m in re.finditer(r"ccall\(\(:(otmb_[a-z0-9_]+), LIBOTMB\),\s*\w+,\s*\(", shim):
+        name, i, depth = m.group(1), m.end(), 1
+        start = i
+        while depth:                                   # the type tuple, up to its closing parenthesis
+            depth += {"(": 1, ")": -1}.get(shim[i], 0)
+            i += 1
+        types, cur, braces = [], "", 0
+        for ch in shim[start:i - 1]:                   # split on commas outside {...}
+            braces += {"{": 1, "}": -1}.get(ch, 0)
+            if ch == "," and braces == 0:
+                types.append(cur.strip())
+                cur = ""
+            else:
+                cur += ch
+        types = [t for t in types + [cur.strip()] if t]
+        assert name in decl, f"{name} is not declared in include/otmb.h"
+        assert len(types) == len(decl[name]), f"ccall of {name}: {len(types)} argument types, the header declares {len(decl[name])}"
+        for k, (jt, ck) in enumerate(zip(types, decl[name])):
+            assert ck in julia_for, f"{name} parameter {k}: no rule for C type {ck}"
+            assert jt in julia_for[ck], f"ccall of {name}, argument {k}: Julia type {jt} for C parameter {ck}"
+        seen.add(name)
+    assert set(decl) - seen == set(), f"not bound in the Julia shim: {sorted(set(decl) - seen)}"
