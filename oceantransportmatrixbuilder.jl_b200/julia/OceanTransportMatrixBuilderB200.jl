@@ -216,7 +216,7 @@ function transportmatrix(; ϕ, mlotst, gridmetrics, indices, ρ, κH = 500.0, κ
     # some operators were passed in pre-built (the reference's caching hook, :133-143): upload, build the rest, fetch
     GC.@preserve faces check(c, ccall((:otmb_set_facefluxes, LIBOTMB), Cint, (PV, Ptr{PF}), c.h, pointer.(faces)))
     check(c, ccall((:otmb_set_mlotst, LIBOTMB), Cint, (PV, PF), c.h, ml))
-    check(c, ccall((:otmb_set_rho3d, LIBOTMB), Cint, (PV, PF), c.h, isnothing(ρ3) ? PF(C_NULL) : pointer(ρ3)))
+    GC.@preserve ρ3 check(c, ccall((:otmb_set_rho3d, LIBOTMB), Cint, (PV, PF), c.h, isnothing(ρ3) ? PF(C_NULL) : pointer(ρ3)))
     mask = Int32(32)
     for (m, A) in enumerate(pre)
         if isnothing(A)
