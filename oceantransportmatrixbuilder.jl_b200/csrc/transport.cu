@@ -117,21 +117,31 @@ int rebuild_and_compare(otmb_ctx* c, const otmb_tm_params* prm, int ops, bool* s
     for (int m = 1; ok && m <= 4; ++m)
         if (!(ops >> m & 1)) ok = (i64)f.nnz[m] == held_nnz[m];
     if (ok) {
-        int h = 0;
-        CU_TRY(c, c->held_diff.ensure(8));
-        CU_TRY(c, cudaMemsetAsync(c->held_diff.p, 0, 8, c->stream));
-        const int grid = c->sm_count * 8;
-        for (int m = 1; m <= 4; ++m)
-            if (!(ops >> m & 1)) {
-                int* d = c->held_diff.as<int>();
-                k_same_words<<<grid, 256, 0, c->stream>>>(c->colptr[m].as<u64>(), c->held[m][0].as<u64>(), c->ncols + 1, d);
-                k_same_words<<<grid, 256, 0, c->stream>>>(c->rowval[m].as<u64>(), c->held[m][1].as<u64>(), held_nnz[m], d);
-                k_same_words<<<grid, 256, 0, c->stream>>>(c->nzval[m].as<u64>(), c->held[m][2].as<u64>(), held_nnz[m], d);
-            }
-        CU_TRY(c, cudaGetLastError());
-        CU_TRY(c, cudaMemcpyAsync(&h, c->held_diff.p, 4, cudaMemcpyDeviceToHost, c->stream));
-        CU_TRY(c, cudaStreamSynchronize(c->stream));
-        ok = h == 0;
+        // (a CUDA error in here must not leave the caller's operators set aside: hence the lambda and one exit)
+        auto compare = [&](bool* equal) -> int {
+            int h = 0;
+            CU_TRY(c, c->held_diff.ensure(8));
+            CU_TRY(c, cudaMemsetAsync(c->held_diff.p, 0, 8, c->stream));
+            const int grid = c->sm_count * 8;
+            for (int m = 1; m <= 4; ++m)
+                if (!(ops >> m & 1)) {
+                    int* d = c->held_diff.as<int>();
+                    k_same_words<<<grid, 256, 0, c->stream>>>(c->colptr[m].as<u64>(), c->held[m][0].as<u64>(), c->ncols + 1, d);
+                    k_same_words<<<grid, 256, 0, c->stream>>>(c->rowval[m].as<u64>(), c->held[m][1].as<u64>(), held_nnz[m], d);
+                    k_same_words<<<grid, 256, 0, c->stream>>>(c->nzval[m].as<u64>(), c->held[m][2].as<u64>(), held_nnz[m], d);
+                }
+            CU_TRY(c, cudaGetLastError());
+            CU_TRY(c, cudaMemcpyAsync(&h, c->held_diff.p, 4, cudaMemcpyDeviceToHost, c->stream));
+            CU_TRY(c, cudaStreamSynchronize(c->stream));
+            *equal = h == 0;
+            return OTMB_OK;
+        };
+        const int cst = compare(&ok);
+        if (cst != OTMB_OK) {
+            swap_held(c, ops);
+            for (int m = 1; m <= 4; ++m) c->nnz[m] = held_nnz[m];
+            return cst;
+        }
     }
     if (!ok) {
         swap_held(c, ops);   // the caller's operators back where the generic route reads them

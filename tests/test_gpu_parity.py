@@ -739,3 +739,30 @@ def test_paired_division_equals_the_compilers(seed):
     first = (C.c_double * 4)()
     c.check(c.lib.otmb_selftest_division(c.h, 1 << 27, seed, C.byref(bad), first))
     assert bad.value == 0, f"{bad.value} quotients differ, e.g. a={first[0]!r} b={first[1]!r}: {first[2]!r} vs {first[3]!r}"
+
+
+@pytest.mark.gpu
+def test_staged_and_direct_uploads_give_the_same_results(monkeypatch):
+    """Pageable host arrays of 4 MB and more are staged through page-locked buffers by the host pool (otmb_h2d);
+    OTMB_UPLOAD_DIRECT=1 hands them to cudaMemcpyAsync as they are.  Same face fluxes, bit for bit, with array sizes
+    that are not a multiple of the 16 MB piece, and with a source that is modified right after the call returns."""
+    oc = synthetic.make_ocean(210, 160, 21, "tripolar", seed=4, land_frac=0.25)      # 5.6 MB per 3-D array
+    f = fields(oc)
+    ctx = A.Context(0)
+    gm = A.makegridmetrics(areacello=f["areacello"], volcello=f["volcello"], lon=f["lon"], lat=f["lat"], lev=f["lev"],
+                           lon_vertices=f["lon_vertices"], lat_vertices=f["lat_vertices"], ctx=ctx)
+    ix = A.makeindices(gm.v3D, ctx=ctx)
+
+    def run():
+        F = otmb_b200.Field                                     # ordinary (pageable) numpy arrays, Float64 already
+        umo = F(np.asfortranarray(oc.umo, dtype=np.float64).copy(order="F"), {"_FillValue": oc.fill})
+        vmo = F(np.asfortranarray(oc.vmo, dtype=np.float64).copy(order="F"), {"_FillValue": oc.fill})
+        phi = A.facefluxesfrommasstransport(umo=umo, vmo=vmo, gridmetrics=gm, indices=ix, ctx=ctx)
+        umo.data[...] = -1.0                                    # the call has read its sources in full
+        return [np.array(getattr(phi, k)) for k in A.FACES]
+
+    staged = run()
+    monkeypatch.setenv("OTMB_UPLOAD_DIRECT", "1")
+    direct = run()
+    for a, b in zip(staged, direct):
+        assert np.array_equal(bits(a), bits(b))
