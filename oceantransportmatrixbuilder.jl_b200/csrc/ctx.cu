@@ -44,8 +44,8 @@ __global__ void __launch_bounds__(256) k_fill_lwet32(const u64* __restrict__ mas
 //   phase 1: the one read of v3D — `isnan` -> ballots = the BitArray chunks, written out; the block's wet count
 //   grid.sync()
 //   phase 2: exclusive prefix of the block counts (a few thousand values, summed by every block for itself), then the
-//            block walks its range again FROM THE MASK (1 bit per cell, L2-resident) 32 chunks at a time: per-chunk
-//            prefix, and — when the wet-rank offset is already known (FILL: unsharded contexts) — Lwet3D (`rank3d`,
+//            block walks its range again FROM THE MASK (1 bit per cell, L2-resident), every warp its own contiguous run
+//            of chunks (no block-wide barrier inside the loops): per-chunk prefix, and — when the wet-rank offset is already known (FILL: unsharded contexts) — Lwet3D (`rank3d`,
 //            -1 = dry) and the compacted wet list.
 // No serial dependency between blocks (a decoupled look-back over 38 000 small blocks ran at 43 % of the HBM roofline on
 // the 0.25-degree grid: every block waits for the prefix to travel down the chain), and no second read of v3D.
@@ -56,23 +56,26 @@ __global__ void __launch_bounds__(32 * MI_WARPS) k_makeindices(const double* __r
                                                                u64* __restrict__ mask, uint32_t* __restrict__ wpre,
                                                                int* __restrict__ rank3d, int* __restrict__ lwet, int rank_offset,
                                                                unsigned* __restrict__ block_tot, u64* __restrict__ total) {
-    __shared__ unsigned s_wtot[MI_WARPS];
-    __shared__ unsigned s_base;
+    __shared__ unsigned s_wtot[MI_WARPS];   // the warps' wet counts (phase 1), read again in phase 2
+    __shared__ unsigned s_part[MI_WARPS];   // partial sums of the lower blocks' counts
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    // this block's chunks: rounds of MI_WORDS chunks (8 warps x 4), the same split in both phases
+    // this block's chunks: `rounds` x MI_WORDS of them, the same split in both phases; inside the block every WARP owns a
+    // contiguous run of `rounds` x MI_WPW chunks, so that no loop below needs a block-wide barrier
     const i64 nwords = word1 - word0;
     const i64 rounds_all = (nwords + MI_WORDS - 1) / MI_WORDS;
     const i64 r0 = rounds_all * blockIdx.x / gridDim.x, r1 = rounds_all * (blockIdx.x + 1) / gridDim.x;
+    const i64 rounds = r1 - r0;
+    const i64 wbegin = word0 + r0 * MI_WORDS + (i64)wid * rounds * MI_WPW;   // first chunk of this warp
     const double dry = __longlong_as_double(0x7ff8000000000000ll);
-    // ---------------- phase 1: mask + block count
+    // ---------------- phase 1: mask + counts
     unsigned mine = 0;
-    for (i64 r = r0; r < r1; ++r) {
-        const i64 wfirst = word0 + r * MI_WORDS + wid * MI_WPW;
+    for (i64 r = 0; r < rounds; ++r) {
+        const i64 wfirst = wbegin + r * MI_WPW;
         // A warp has its eight loads in flight only while it waits for them, not while it ballots and stores: the lines
-        // of its next round are requested into L2 now (4 chunks x 512 B = 16 lines, one per lane), so that those loads
-        // find them there (0.25-degree grid: 301 -> 241 us; two rounds ahead, or the mask words of phase 2 as well: 263 us).
-        if (r + 1 < r1 && lane < 4 * MI_WPW) {
-            const i64 nxt = (wfirst + MI_WORDS) * 64 + (i64)lane * 16;
+        // of its next step are requested into L2 now (4 chunks x 512 B = 16 lines, one per lane), so that those loads
+        // find them there (0.25-degree grid: 301 -> 241 us; two steps ahead, or the mask words of phase 2 as well: 263 us).
+        if (r + 1 < rounds && lane < 4 * MI_WPW) {
+            const i64 nxt = (wfirst + MI_WPW) * 64 + (i64)lane * 16;
             if (nxt >= L0 && nxt < L1) asm volatile("prefetch.global.L2 [%0];" ::"l"(v3D + nxt));
         }
         double va[MI_WPW], vb[MI_WPW];
@@ -101,37 +104,27 @@ __global__ void __launch_bounds__(32 * MI_WARPS) k_makeindices(const double* __r
     }
     __threadfence();
     cooperative_groups::this_grid().sync();
-    // ---------------- phase 2: prefix of the block counts, then the block's chunks again from the mask
+    // ---------------- phase 2: prefix of the block counts, then every warp walks its run again from the mask
     unsigned part = 0;
     for (int b = threadIdx.x; b < (int)blockIdx.x; b += blockDim.x) part += __ldcg(block_tot + b);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    __syncthreads();   // s_wtot is reused
-    if (lane == 0) s_wtot[wid] = part;
+    if (lane == 0) s_part[wid] = part;
     __syncthreads();
-    unsigned base = 0;
+    unsigned pre = 0;   // wet cells before this warp's run
 #pragma unroll
-    for (int q = 0; q < MI_WARPS; ++q) base += s_wtot[q];
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *total = (u64)base + __ldcg(block_tot + blockIdx.x);
-    for (i64 r = r0; r < r1; ++r) {
-        const i64 wfirst = word0 + r * MI_WORDS + wid * MI_WPW;
+    for (int q = 0; q < MI_WARPS; ++q) pre += s_part[q] + (q < wid ? s_wtot[q] : 0u);
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+        unsigned t = pre;   // warp 0: the lower blocks' sum
+#pragma unroll
+        for (int q = 0; q < MI_WARPS; ++q) t += s_wtot[q];
+        *total = (u64)t;
+    }
+    for (i64 r = 0; r < rounds; ++r) {
+        const i64 wfirst = wbegin + r * MI_WPW;
         u64 word[MI_WPW];
-        unsigned cnt[MI_WPW], wsum = 0;
 #pragma unroll
-        for (int q = 0; q < MI_WPW; ++q) {
-            word[q] = wfirst + q < word1 ? __ldcg(mask + wfirst + q) : 0ull;
-            cnt[q] = __popcll(word[q]);
-            wsum += cnt[q];
-        }
-        __syncthreads();
-        if (lane == 0) s_wtot[wid] = wsum;
-        __syncthreads();
-        unsigned pre = base, round_tot = 0;
-#pragma unroll
-        for (int q = 0; q < MI_WARPS; ++q) {
-            pre += q < wid ? s_wtot[q] : 0u;
-            round_tot += s_wtot[q];
-        }
+        for (int q = 0; q < MI_WPW; ++q) word[q] = wfirst + q < word1 ? __ldcg(mask + wfirst + q) : 0ull;
 #pragma unroll
         for (int q = 0; q < MI_WPW; ++q) {
             const i64 w = wfirst + q;
@@ -149,9 +142,8 @@ __global__ void __launch_bounds__(32 * MI_WARPS) k_makeindices(const double* __r
                     if (wb) lwet[rb] = (int)b;
                 }
             }
-            pre += cnt[q];
+            pre += __popcll(word[q]);
         }
-        base += round_tot;
     }
 }
 
