@@ -53,7 +53,6 @@ namespace {
 constexpr int ST_SHIFT = 42;
 constexpr u64 ST_MASK = (1ull << ST_SHIFT) - 1;
 constexpr unsigned ST_EPOCHS = 1u << 20;
-__host__ __device__ constexpr u64 st_tag(unsigned flag, unsigned epoch) { return ((u64)((flag << 20) | epoch)) << ST_SHIFT; }
 constexpr int WDATA = 7 * 32;       // staged entries per warp: 7 per column
 constexpr int WCAP = WDATA + 32;    // + one dump slot per lane for absent entries (branch-free staging)
 // candidates in ascending row order, one nibble each, per class
@@ -106,11 +105,6 @@ __device__ __forceinline__ u64 ld_vol(const u64* p) {
     return v;
 }
 __device__ __forceinline__ void st_vol(u64* p, u64 v) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
-__device__ __forceinline__ u64 warp_sum64(u64 v) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-    return v;
-}
 // upwind flux max(ϕ, 0) / min(ϕ, 0), or ϕ/2 when centred (:244-295).  Julia's max/min against the literal 0.0 reduce
 // to one comparison: NaN propagates (both comparisons are false for NaN), max(-0.0, 0.0) = 0.0, min(-0.0, 0.0) = -0.0.
 __device__ __forceinline__ double upflux(double x, bool take_max, bool up) {
@@ -123,7 +117,6 @@ __device__ __forceinline__ bool inflow(double x, bool take_max) {
     if (UP) return take_max ? x > 0.0 : x < 0.0;
     return fabs(x) > __longlong_as_double(1ll);
 }
-__device__ __forceinline__ bool nz(double f) { return f > 0 || f < 0; }
 // q1 = a1 / b1 and q2 = a2 / b2: PAIRED with overlapping chains (fdiv.cuh), otherwise two plain divisions
 // (-DOTMB_NO_DIV2: plain everywhere)
 template <bool PAIRED = true>

@@ -186,10 +186,10 @@ __global__ void __launch_bounds__(128) k_triple(TripleParams P, uint32_t* __rest
         }
     }
     if (over) atomicOr(overflow, 1);
-    if (PASS == 0) {
+    if constexpr (PASS == 0) {
         count[J] = (uint32_t)n;
         return;
-    }
+    } else {
     // rows ascending inside the column, like every SparseMatrixCSC
     for (int a = 1; a < n; ++a) {
         const int r = rows[a];
@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(128) k_triple(TripleParams P, uint32_t* __rest
     const i64 o = start[J];
     out_colptr[J] = o + base;
     for (int q = 0; q < n; ++q) out_rowval[o + q] = rows[q] + base, out_nzval[o + q] = vals[q];
+    }
 }
 
 }  // namespace
