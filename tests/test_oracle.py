@@ -207,3 +207,43 @@ def test_column_streamed_oracle_equals_full_oracle(case):
                 assert s.n == hi - lo and np.array_equal(s.colptr, f.colptr[lo:hi + 1] - f.colptr[lo] + 1), (name, lo, hi)
                 assert np.array_equal(s.rowval, f.rowval[a:b]), (name, lo, hi)
                 assert np.array_equal(s.nzval.view(np.int64), f.nzval[a:b].view(np.int64)), (name, lo, hi)
+
+
+def test_raw_twins_hold_every_file_the_julia_pin_script_reads(tmp_path):
+    """tests/golden/pin_with_julia.jl cannot run here (no Julia).  What can be checked: `npz_to_raw.py` writes, for every
+    golden case, every file the script opens, with the element count the script reshapes it to."""
+    import re
+    import subprocess
+    import sys
+    from pathlib import Path
+    golden = Path(__file__).resolve().parent / "golden"
+    subprocess.run([sys.executable, str(golden / "npz_to_raw.py"), str(tmp_path)], check=True, capture_output=True)
+    script = (golden / "pin_with_julia.jl").read_text()
+    shaped = {"f3": 3, "f2": 2, "fv": -1, "f4": -2}                       # reader -> kind of shape
+    wanted = {(m.group(2) + ".f64", shaped[m.group(1)]) for m in re.finditer(r"\b(f3|f2|fv|f4)\(\"([A-Za-z0-9_]+)\"\)", script)}
+    wanted |= {(m.group(1), 0) for m in re.finditer(r"joinpath\(dir, \"([A-Za-z0-9_]+\.(?:f64|i64|u64))\"\)", script)}
+    for mat in re.findall(r":\w+ => \"(\w+)\"", script):                  # the five matrices' CSC fields
+        wanted |= {(f"{mat}_colptr.i64", 0), (f"{mat}_rowval.i64", 0), (f"{mat}_nzval.f64", 0)}
+    for name in ("name", "n"):                                            # loop variables of the script, not files
+        wanted = {w for w in wanted if w[0] != name + ".f64"}
+    assert len(wanted) > 30
+    cases = sorted(p for p in tmp_path.iterdir() if p.is_dir())
+    assert len(cases) == len(list(golden.glob("case_*.npz"))) > 0
+    for case in cases:
+        meta = (case / "meta.txt").read_text().split()
+        assert len(meta) == 8
+        nx, ny, nz = map(int, meta[:3])
+        use3d = meta[7] == "1"
+        for fname, kind in sorted(wanted):
+            if fname == "rho3d.f64" and not use3d:
+                continue
+            f = case / fname
+            assert f.exists(), f"{case.name}: the Julia script reads {fname}, npz_to_raw.py did not write it"
+            n = f.stat().st_size // 8
+            expect = {3: nx * ny * nz, 2: nx * ny, -1: 4 * nx * ny, -2: nx * ny * 4}.get(kind)
+            if expect is not None:
+                assert n == expect, f"{case.name}/{fname}: {n} elements, the script reshapes to {expect}"
+        N = (case / "Lwet.i64").stat().st_size // 8
+        for mat in ("T", "Tadv", "TkH", "TkVML", "TkVdeep"):
+            assert (case / f"{mat}_colptr.i64").stat().st_size // 8 == N + 1
+            assert (case / f"{mat}_rowval.i64").stat().st_size == (case / f"{mat}_nzval.f64").stat().st_size
