@@ -300,8 +300,9 @@ int otmb_bgrid_to_cgrid(otmb_ctx* ctx, const double* u, const double* v, double 
 /* lump_and_spray(wet3D, vol, T; di, dj, dk), src/extratools.jl:38-112, default mask only:
  * LUMP (N_c x N, volume-weighted average onto di x dj x dk boxes split into connected components of T's stored
  * pattern), SPRAY (N x N_c, = LUMP' with ones) and the coarse volumes.  vol: N doubles (volumes of the wet
- * cells).  T's pattern: t_colptr / t_rowval (host, base t_index_base), or NULL to use the T of the last
- * otmb_transportmatrix_build on this context.  Results in index_base; two-phase like transportmatrix. */
+ * cells).  T's pattern: t_colptr / t_rowval (host, base t_index_base; checked like a pre-built operator: N+1
+ * non-decreasing colptr entries, rows ascending inside [0, N), OTMB_ERR_BADARG otherwise), or NULL to use the T of the
+ * last otmb_transportmatrix_build on this context.  Results in index_base; two-phase like transportmatrix. */
 int otmb_lump_and_spray_build(otmb_ctx* ctx, int64_t di, int64_t dj, int64_t dk, const double* vol,
                               const int64_t* t_colptr, const int64_t* t_rowval, int32_t t_index_base,
                               int32_t index_base, int64_t* n_coarse);

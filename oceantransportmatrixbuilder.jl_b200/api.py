@@ -546,6 +546,8 @@ def lump_and_spray(wet3D, vol, T, mask=None, *, di=2, dj=2, dk=1, ctx=None):
     N = ctx.resident["N"]
     vol = np.ascontiguousarray(vol, dtype=np.float64)
     Tc = sp.csc_matrix(T)
+    if not Tc.has_sorted_indices:                 # a SparseMatrixCSC always is; the library checks the pattern it is given
+        Tc = Tc.sorted_indices()
     assert Tc.shape == (N, N) and vol.shape == (N,)
     cp, rv = Tc.indptr.astype(np.int64), Tc.indices.astype(np.int64)
     Nc = C.c_int64()

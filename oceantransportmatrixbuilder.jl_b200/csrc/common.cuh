@@ -217,6 +217,7 @@ int otmb_scan_u32_to_i64(otmb_ctx* ctx, const uint32_t* in, i64* out, i64 n, u64
 
 // internal entry points across translation units
 int otmb_need(otmb_ctx* ctx, bool cond, const char* what);
+int otmb_check_csc_dev(otmb_ctx* ctx, const i64* colptr, const i64* rowval, i64 n, i64 nnz, i64 base, int* verdict);   // transport.cu
 int otmb_h2d(otmb_ctx* ctx, void* dst, const void* src, size_t bytes, cudaStream_t st);   // fetch.cu: pageable sources are staged by the host pool
 int otmb_upload3d(otmb_ctx* ctx, DevBuf& buf, const double* host);   // whole (nx,ny,nz) array, or only the slab window
 int otmb_fused_build(otmb_ctx* ctx, const otmb_tm_params* prm, int mask, bool two_pass);

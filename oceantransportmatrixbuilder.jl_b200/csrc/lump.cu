@@ -225,11 +225,20 @@ int otmb_lump_and_spray_build(otmb_ctx* c, int64_t di, int64_t dj, int64_t dk, c
     const i64 nboxes = (i64)P.nbx * P.nby * P.nbz;
     // T's stored pattern: the caller's, or the T of the last transportmatrix build on this context
     if (t_colptr) {
+        // the caller's pattern is checked like a pre-built operator (otmb_set_operator): the two ends of colptr here,
+        // monotonicity, row range and order by a kernel over the uploaded arrays
+        const char* const bad_t = "lump_and_spray: T's colptr / rowval are not the pattern of an N x N SparseMatrixCSC "
+                                  "(N+1 non-decreasing colptr entries from t_index_base, rows ascending inside [0, N))";
+        if (t_index_base != 0 && t_index_base != 1) return otmb_fail(c, OTMB_ERR_BADARG, "t_index_base must be 0 or 1");
         const i64 tn = t_colptr[N] - t_index_base;
+        if (t_colptr[0] != t_index_base || tn < 0) return otmb_fail(c, OTMB_ERR_BADARG, bad_t);
         CU_TRY(c, c->add_tmp[0].ensure((size_t)(N + 1) * 8));
         CU_TRY(c, c->add_tmp[1].ensure((size_t)(tn + 1) * 8));
         OT_TRY(otmb_h2d(c, c->add_tmp[0].p, t_colptr, (size_t)(N + 1) * 8, c->stream));
         if (tn > 0) OT_TRY(otmb_h2d(c, c->add_tmp[1].p, t_rowval, (size_t)tn * 8, c->stream));
+        int verdict = 0;
+        OT_TRY(otmb_check_csc_dev(c, c->add_tmp[0].as<i64>(), c->add_tmp[1].as<i64>(), N, tn, t_index_base, &verdict));
+        if (verdict) return otmb_fail(c, OTMB_ERR_BADARG, bad_t);
         P.t_colptr = c->add_tmp[0].as<i64>();
         P.t_rowval = c->add_tmp[1].as<i64>();
         P.t_base = t_index_base;

@@ -158,6 +158,21 @@ int rebuild_and_compare(otmb_ctx* c, const otmb_tm_params* prm, int ops, bool* s
 }
 }  // namespace
 
+// O(nnz) checks of a CSC pattern that is already on the device (k_check_csc): *verdict bit 0 = colptr is not a
+// non-decreasing sequence inside [base, base + nnz], bit 1 = a row outside [0, n) or not strictly ascending in its column
+int otmb_check_csc_dev(otmb_ctx* c, const i64* colptr, const i64* rowval, i64 n, i64 nnz, i64 base, int* verdict) {
+    *verdict = 0;
+    CU_TRY(c, c->held_diff.ensure(8));
+    CU_TRY(c, cudaMemsetAsync(c->held_diff.p, 0, 8, c->stream));
+    if (n > 0) {
+        k_check_csc<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(colptr, rowval, n, nnz, base, c->held_diff.as<int>());
+        CU_TRY(c, cudaGetLastError());
+    }
+    CU_TRY(c, cudaMemcpyAsync(verdict, c->held_diff.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return OTMB_OK;
+}
+
 extern "C" {
 
 int otmb_transportmatrix_build(otmb_ctx* c, const otmb_tm_params* prm, int64_t nnz_out[5]) {
@@ -290,21 +305,13 @@ int otmb_set_operator(otmb_ctx* c, int which, int64_t nnz, const int64_t* colptr
     CU_TRY(c, c->colptr[which].ensure((size_t)(n + 1) * 8));
     CU_TRY(c, c->rowval[which].ensure((size_t)(nnz + 1) * 8));
     CU_TRY(c, c->nzval[which].ensure((size_t)(nnz + 1) * 8));
-    CU_TRY(c, c->held_diff.ensure(8));
-    CU_TRY(c, cudaMemsetAsync(c->held_diff.p, 0, 8, c->stream));
     OT_TRY(otmb_h2d(c, c->colptr[which].p, colptr, (size_t)(n + 1) * 8, c->stream));
     if (nnz > 0) {
         OT_TRY(otmb_h2d(c, c->rowval[which].p, rowval, (size_t)nnz * 8, c->stream));
         OT_TRY(otmb_h2d(c, c->nzval[which].p, nzval, (size_t)nnz * 8, c->stream));
     }
     int verdict = 0;
-    if (n > 0) {
-        k_check_csc<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->colptr[which].as<i64>(), c->rowval[which].as<i64>(), n, nnz,
-                                                                        (i64)index_base, c->held_diff.as<int>());
-        CU_TRY(c, cudaGetLastError());
-    }
-    CU_TRY(c, cudaMemcpyAsync(&verdict, c->held_diff.p, 4, cudaMemcpyDeviceToHost, c->stream));
-    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    OT_TRY(otmb_check_csc_dev(c, c->colptr[which].as<i64>(), c->rowval[which].as<i64>(), n, nnz, index_base, &verdict));
     if (verdict & 1) return otmb_fail(c, OTMB_ERR_BADARG, bad_colptr);
     if (verdict & 2)
         return otmb_fail(c, OTMB_ERR_BADARG, "pre-built operator: row indices must be strictly ascending inside every column and "

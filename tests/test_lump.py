@@ -93,6 +93,27 @@ def test_gpu_lump_errors():
     Tasym = sp.csc_matrix(sp.triu(T))                                            # SimpleGraph would throw
     with pytest.raises(A.OTMBError):
         otmb_b200.lump_and_spray(wet, vol, Tasym)
+    # a caller-supplied pattern that is not an N x N CSC is refused by the library, like a pre-built operator
+    import ctypes as C
+    ctx = otmb_b200.default_context()
+    otmb_b200.lump_and_spray(wet, vol, T)                                        # leaves this grid's indices resident
+    Tc = sp.csc_matrix(T); Tc.sort_indices()
+    N = Tc.shape[0]
+    cp, rv = Tc.indptr.astype(np.int64), Tc.indices.astype(np.int64)
+    volc = np.ascontiguousarray(vol, dtype=np.float64)
+
+    def build(cp, rv):
+        Nc = C.c_int64()
+        return ctx.lib.otmb_lump_and_spray_build(ctx.h, 2, 2, 1, A._ptr(volc), A._ptr(cp), A._ptr(rv), 0, 0, C.byref(Nc))
+
+    assert build(cp, rv) == 0
+    bad = cp.copy(); bad[-1] = -3
+    assert build(bad, rv) == otmb_b200._lib.ERR_BADARG
+    bad = cp.copy(); bad[4], bad[5] = bad[5], bad[4] - 1                          # not monotone
+    assert build(bad, rv) == otmb_b200._lib.ERR_BADARG
+    bad = rv.copy(); bad[2] = N + 5                                               # row outside the matrix
+    assert build(cp, bad) == otmb_b200._lib.ERR_BADARG
+    assert build(cp, rv) == 0                                                     # and the context still works
 
 
 # ------------------------------------------------------------------------------------------ T_c = LUMP * T * SPRAY
